@@ -1,0 +1,234 @@
+/* lfs_b200 -- C ABI of the B200-native 3DGS training rasterizer (sm_100a).
+ *
+ * This header is the drop-in boundary.  The reference (MrNeRF/LichtFeld-Studio) has no C ABI of its own:
+ * its boundary is the C++ operator surface of two static archives (gsplat_backend / fastgs_backend).
+ * Every entry point below names the reference interface it replaces (file:line, paths relative to the
+ * reference repo root).  The thin C++/libtorch dispatch that re-exports the reference's exact symbols
+ * (namespace gsplat / fast_gs) on top of this ABI lives in lichtfeld-studio_b200/host/ and the binding a
+ * maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes only; every data pointer is a DEVICE pointer unless the name
+ * ends in _host; all tensors are contiguous, fp32 unless noted; `stream` is a cudaStream_t passed as
+ * void* (NULL = legacy default stream).  Functions return 0 on success or a negative lfs_status and never
+ * fall back to a CPU path.  lfs_last_error() gives a human readable message for the calling thread.
+ */
+#ifndef LFS_B200_H
+#define LFS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LFS_ABI_VERSION 1
+
+typedef enum lfs_status {
+    LFS_OK = 0,
+    LFS_ERR_INVALID_ARG = -1,
+    LFS_ERR_UNSUPPORTED = -2, /* valid in the reference, not implemented here: fails loudly */
+    LFS_ERR_CUDA = -3,
+    LFS_ERR_ALLOC = -4,
+    LFS_ERR_CAPACITY = -5 /* a capacity-bounded buffer overflowed; grow and retry */
+} lfs_status;
+
+/* gsplat/Common.h:46-50 */
+typedef enum lfs_camera_model { LFS_PINHOLE = 0, LFS_ORTHO = 1, LFS_FISHEYE = 2 } lfs_camera_model;
+/* gsplat/Cameras.h:16-22 */
+typedef enum lfs_shutter_type {
+    LFS_ROLLING_TOP_TO_BOTTOM = 0,
+    LFS_ROLLING_LEFT_TO_RIGHT = 1,
+    LFS_ROLLING_BOTTOM_TO_TOP = 2,
+    LFS_ROLLING_RIGHT_TO_LEFT = 3,
+    LFS_GLOBAL = 4
+} lfs_shutter_type;
+/* gsplat/Cameras.h:27-44 UnscentedTransformParameters (same defaults) */
+typedef struct lfs_ut_params {
+    float alpha;                  /* 0.1 */
+    float beta;                   /* 2.0 */
+    float kappa;                  /* 0.0 */
+    float in_image_margin_factor; /* 0.1 */
+    int32_t require_all_sigma_points_valid; /* 1 */
+} lfs_ut_params;
+
+/* Output / scratch allocation callback.  Plays the role of the at::empty calls inside the reference ops
+ * (gsplat/Intersect.cpp:82-85) and of fastgs' resize callbacks std::function<char*(size_t)>
+ * (fastgs/rasterization/include/forward.h:14-17).  Must return a device pointer aligned to 256 bytes that
+ * stays valid until the caller releases it; `tag` identifies the buffer (see each function). */
+typedef void* (*lfs_alloc_fn)(void* ctx, int tag, size_t bytes);
+
+const char* lfs_last_error(void);
+int lfs_abi_version(void);
+/* number of kernels launched by this library on behalf of the calling process (bench.py gpu_launches) */
+uint64_t lfs_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * gsplat operator surface (3DGUT path)
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* Replaces gsplat::projection_ut_3dgs_fused / launch_projection_ut_3dgs_fused_kernel
+ * (gsplat/Ops.h:69-98, gsplat/Projection.h:12-40, kernel gsplat/ProjectionUT3DGSFused.cu:17-203).
+ * means [N,3], quats [N,4] wxyz, scales [N,3], opacities [N] or NULL, viewmats0 [C,4,4] row-major w2c,
+ * Ks [C,3,3].  Outputs radii [C,N,2] i32, means2d [C,N,2], depths [C,N], conics [C,N,3],
+ * compensations [C,N] or NULL.  Culled entries: radii = 0, other outputs untouched (as the reference).
+ * Supported: LFS_PINHOLE, LFS_GLOBAL, no distortion (viewmats1 / radial / tangential / thin_prism NULL);
+ * anything else returns LFS_ERR_UNSUPPORTED. */
+int lfs_projection_ut_3dgs_fused(const float* means, const float* quats, const float* scales,
+                                 const float* opacities, const float* viewmats0, const float* viewmats1,
+                                 const float* Ks, uint32_t N, uint32_t C, uint32_t image_width,
+                                 uint32_t image_height, float eps2d, float near_plane, float far_plane,
+                                 float radius_clip, int camera_model, const lfs_ut_params* ut_params, int rs_type,
+                                 const float* radial_coeffs, const float* tangential_coeffs,
+                                 const float* thin_prism_coeffs, int32_t* radii, float* means2d, float* depths,
+                                 float* conics, float* compensations, void* stream);
+
+/* Replaces gsplat::spherical_harmonics_fwd / launch_spherical_harmonics_fwd_kernel
+ * (gsplat/Ops.h:12-17, gsplat/SphericalHarmonics.h:11-19, kernel gsplat/SphericalHarmonicsCUDA.cu:374-399).
+ * dirs [n,3], coeffs [n,K,3], masks [n] (bool bytes) or NULL -> colors [n,3] (masked rows untouched). */
+int lfs_spherical_harmonics_fwd(uint32_t degrees_to_use, const float* dirs, const float* coeffs,
+                                const uint8_t* masks, uint32_t n, uint32_t K, float* colors, void* stream);
+
+/* Replaces gsplat::spherical_harmonics_bwd (gsplat/Ops.h:18-25, kernel gsplat/SphericalHarmonicsCUDA.cu:445-481).
+ * Writes v_coeffs [n,K,3] completely (zeros for inactive bases and masked rows, i.e. the reference's
+ * at::zeros_like + kernel); v_dirs [n,3] or NULL likewise. */
+int lfs_spherical_harmonics_bwd(uint32_t K, uint32_t degrees_to_use, const float* dirs, const float* coeffs,
+                                const uint8_t* masks, const float* v_colors, uint32_t n, float* v_coeffs,
+                                float* v_dirs, void* stream);
+
+/* Replaces gsplat::intersect_tile (gsplat/Ops.h:28-38, gsplat/Intersect.cpp:15-122; kernels
+ * gsplat/IntersectTile.cu:24-114 and the CUB sort :290-328).  Non-packed layout only.
+ * means2d [C,N,2], radii [C,N,2] i32, depths [C,N] -> tiles_per_gauss [C,N] i32 (caller allocated),
+ * and, through `alloc`, isect_ids [n_isects] i64 (tag 1) and flatten_ids [n_isects] i32 (tag 2); scratch is
+ * requested with tag 0 and may be released when the call returns.  Like the reference this call blocks
+ * once to read n_isects.  Outputs are bit-identical to the reference for identical inputs. */
+#define LFS_TAG_SCRATCH 0
+#define LFS_TAG_ISECT_IDS 1
+#define LFS_TAG_FLATTEN_IDS 2
+int lfs_intersect_tile(const float* means2d, const int32_t* radii, const float* depths, uint32_t C, uint32_t N,
+                       uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, int sort,
+                       int32_t* tiles_per_gauss, lfs_alloc_fn alloc, void* alloc_ctx, int64_t** isect_ids,
+                       int32_t** flatten_ids, int64_t* n_isects_host, void* stream);
+
+/* Replaces gsplat::intersect_offset (gsplat/Ops.h:39-43, kernel gsplat/IntersectTile.cu:206-252).
+ * offsets [C, tile_height, tile_width] i32. */
+int lfs_intersect_offset(const int64_t* isect_ids, int64_t n_isects, uint32_t C, uint32_t tile_width,
+                         uint32_t tile_height, int32_t* offsets, void* stream);
+
+/* Replaces gsplat::rasterize_to_pixels_from_world_3dgs_fwd / launch_..._fwd_kernel<CDIM>
+ * (gsplat/Ops.h:100-129, gsplat/Rasterization.h:100-135, kernel gsplat/RasterizeToPixelsFromWorld3DGSFwd.cu:20-279).
+ * means [N,3], quats [N,4] (normalised), scales [N,3], colors [C,N,channels], opacities [C,N],
+ * backgrounds [C,channels] or NULL, masks [C,th,tw] bool bytes or NULL, tile_offsets [C,th,tw] i32,
+ * flatten_ids [n_isects] i32 -> renders [C,H,W,channels], alphas [C,H,W,1], last_ids [C,H,W] i32.
+ * Supported: channels == 3, tile_size == 16, LFS_PINHOLE, LFS_GLOBAL, no distortion.  For C > 1 the
+ * gaussian id of a flattened index g is g % N (the reference kernel is single-camera).
+ * Scratch (per-instance records) is requested through `alloc` with tag 0. */
+int lfs_rasterize_to_pixels_from_world_3dgs_fwd(
+    const float* means, const float* quats, const float* scales, const float* colors, const float* opacities,
+    const float* backgrounds, const uint8_t* masks, uint32_t N, uint32_t C, uint32_t channels,
+    uint32_t image_width, uint32_t image_height, uint32_t tile_size, const float* viewmats0,
+    const float* viewmats1, const float* Ks, int camera_model, const lfs_ut_params* ut_params, int rs_type,
+    const float* radial_coeffs, const float* tangential_coeffs, const float* thin_prism_coeffs,
+    const int32_t* tile_offsets, const int32_t* flatten_ids, int64_t n_isects, lfs_alloc_fn alloc,
+    void* alloc_ctx, float* renders, float* alphas, int32_t* last_ids, void* stream);
+
+/* Replaces gsplat::rasterize_to_pixels_from_world_3dgs_bwd / launch_..._bwd_kernel<CDIM>
+ * (gsplat/Ops.h:131-166, gsplat/Rasterization.h:137-174, kernel gsplat/RasterizeToPixelsFromWorld3DGSBwd.cu:17-372).
+ * Outputs v_means [N,3], v_quats [N,4], v_scales [N,3], v_colors [C,N,3], v_opacities [C,N] are fully
+ * written (zero-filled then accumulated, like the reference's at::zeros_like + atomics). */
+int lfs_rasterize_to_pixels_from_world_3dgs_bwd(
+    const float* means, const float* quats, const float* scales, const float* colors, const float* opacities,
+    const float* backgrounds, const uint8_t* masks, uint32_t N, uint32_t C, uint32_t image_width,
+    uint32_t image_height, uint32_t tile_size, const float* viewmats0, const float* viewmats1, const float* Ks,
+    int camera_model, const lfs_ut_params* ut_params, int rs_type, const float* radial_coeffs,
+    const float* tangential_coeffs, const float* thin_prism_coeffs, const int32_t* tile_offsets,
+    const int32_t* flatten_ids, int64_t n_isects, const float* render_alphas, const int32_t* last_ids,
+    const float* v_render_colors, const float* v_render_alphas, lfs_alloc_fn alloc, void* alloc_ctx,
+    float* v_means, float* v_quats, float* v_scales, float* v_colors, float* v_opacities, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * fused Adam
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* Replaces fast_gs::optimizer::adam_step / adam_step_wrapper
+ * (fastgs/optimizer/include/adam.h:9-20, adam_api.h:11-21, kernel adam_kernels.cuh:13-36).  Same formula,
+ * same argument meaning (bias corrections passed as reciprocals computed in double by the caller,
+ * src/training/optimizers/fused_adam.cpp:78-79). */
+int lfs_adam_step(float* param, float* exp_avg, float* exp_avg_sq, const float* param_grad, int64_t n_elements,
+                  float lr, float beta1, float beta2, float eps, float bias_correction1_rcp,
+                  float bias_correction2_sqrt_rcp, void* stream);
+
+/* Multi-tensor form: one launch over a flat arena made of `n_segments` consecutive segments
+ * (segment s covers elements [seg_begin[s], seg_begin[s+1]) and uses lr[s], bc1_rcp[s], bc2_sqrt_rcp[s]);
+ * replaces the 6 per-group launches of FusedAdam::step (src/training/optimizers/fused_adam.cpp:22-95).
+ * Segment boundaries must be multiples of 4 elements.  If zero_grad != 0 the gradient arena is cleared in
+ * the same pass (the reference's zero_grad(set_to_none) + torch::zeros of the next backward).
+ * seg_begin_host [n_segments+1], lr_host/bc1_rcp_host/bc2_sqrt_rcp_host [n_segments] are HOST arrays,
+ * n_segments <= 16. */
+int lfs_adam_step_multi(float* params, float* exp_avg, float* exp_avg_sq, float* grads, int n_segments,
+                        const int64_t* seg_begin_host, const float* lr_host, const float* bc1_rcp_host,
+                        const float* bc2_sqrt_rcp_host, float beta1, float beta2, float eps, int zero_grad,
+                        void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * fused training step (the fast path; what bench.py times)
+ *
+ * Plays the role of gs::training::rasterize + GUTRasterizationFunction / SphericalHarmonicsFunction forward
+ * and backward (src/training/rasterization/rasterizer.cpp:46-437, rasterizer_autograd.cpp:12-392) with the
+ * SplatData activations (src/core/splat_data.cpp:267-286) fused in; one call per view, no host sync.
+ * Parameter / gradient / Adam arenas are PLANAR fp32 buffers owned by the caller (so torch.distributed /
+ * NCCL can all-reduce the gradient arena in place):
+ *   plane order  means xyz | sh0 rgb | shN[(k-1)*3+ch], k=1..K-1 | scaling xyz | rotation wxyz | opacity
+ *   plane pitch  N_pad = round_up(N, 4) floats;  total (11 + 3K) * N_pad floats, K = (sh_degree_max+1)^2.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct lfs_trainer_desc {
+    uint32_t n_gaussians;
+    uint32_t sh_degree_max; /* 0..4; K = (d+1)^2 coefficients per channel */
+    uint32_t width, height;
+    float eps2d;       /* 0.3   (rasterizer.cpp:176) */
+    float near_plane;  /* 0.01  (rasterizer.cpp:177) */
+    float far_plane;   /* 1e4   (rasterizer.cpp:178) */
+    float radius_clip; /* 0     (rasterizer.cpp:179) */
+    lfs_ut_params ut;
+    uint64_t instance_capacity; /* max tile-Gaussian instances per view; 0 = 8*N + 64K */
+} lfs_trainer_desc;
+
+typedef enum lfs_image_format { LFS_IMG_U8_HWC = 0, LFS_IMG_F32_HWC = 1, LFS_IMG_F32_CHW = 2 } lfs_image_format;
+
+uint64_t lfs_trainer_arena_floats(const lfs_trainer_desc* desc);
+void* lfs_trainer_create(const lfs_trainer_desc* desc); /* NULL on failure (see lfs_last_error) */
+void lfs_trainer_destroy(void* trainer);
+uint64_t lfs_trainer_scratch_bytes(void* trainer);
+uint64_t lfs_trainer_instance_capacity(void* trainer);
+
+/* reference SplatData layout (means [N,3], sh0 [N,1,3], shN [N,K-1,3], scaling [N,3], rotation [N,4],
+ * opacity [N,1]; include/core/splat_data.hpp:104-109)  <->  planar arena */
+int lfs_trainer_pack(void* trainer, const float* means, const float* sh0, const float* shN, const float* scaling,
+                     const float* rotation, const float* opacity, float* arena, void* stream);
+int lfs_trainer_unpack(void* trainer, const float* arena, float* means, float* sh0, float* shN, float* scaling,
+                       float* rotation, float* opacity, void* stream);
+
+/* forward of one view.  viewmat_host [16] row-major w2c and K_host [9] are HOST arrays (the reference keeps
+ * cameras on the host side too, include/core/camera.hpp:53-65); bg_host [3] or NULL.
+ * image_out [H,W,3] / alpha_out [H,W] are optional device outputs (image = rgb + (1-alpha)*bg). */
+int lfs_trainer_view_forward(void* trainer, const float* params_arena, const float* viewmat_host,
+                             const float* K_host, uint32_t active_sh_degree, const float* bg_host, float* image_out,
+                             float* alpha_out, void* stream);
+/* L1 photometric loss of the last forward against `target` (device); loss_accum (device float, may be NULL)
+ * += scale * sum|render - target|;  sets the upstream gradient for lfs_trainer_view_backward. */
+int lfs_trainer_view_loss_l1(void* trainer, const void* target, int target_format, float scale, float* loss_accum,
+                             void* stream);
+/* alternative: caller-provided upstream gradients v_image [H,W,3], v_alpha [H,W] or NULL (device) */
+int lfs_trainer_view_set_grad(void* trainer, const float* v_image, const float* v_alpha, void* stream);
+/* backward of the last forward: grads_arena += d loss / d raw parameters */
+int lfs_trainer_view_backward(void* trainer, const float* params_arena, float* grads_arena, void* stream);
+/* blocks on `stream`; returns LFS_ERR_CAPACITY if the last forward overflowed instance_capacity */
+int lfs_trainer_stats(void* trainer, uint64_t* n_instances, uint64_t* n_buckets, void* stream);
+
+/* library options: "blend_tma" = 0/1 (stage per-tile records with cp.async.bulk + mbarrier; default 1) */
+int lfs_set_option(const char* name, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LFS_B200_H */

@@ -1,0 +1,36 @@
+// lfs_b200 -- error plumbing and library-level entry points.
+#include "common.cuh"
+#include "raster.cuh"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+
+namespace lfs {
+
+static thread_local char g_err[1024] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+} // namespace lfs
+
+extern "C" const char* lfs_last_error(void) { return lfs::g_err; }
+extern "C" int lfs_abi_version(void) { return LFS_ABI_VERSION; }
+extern "C" uint64_t lfs_launch_count(void) { return lfs::g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int lfs_set_option(const char* name, int value) {
+    if (name && std::string(name) == "blend_tma") {
+        lfs::raster_options().use_tma = value ? 1 : 0;
+        return LFS_OK;
+    }
+    lfs::set_error("set_option: unknown option '%s'", name ? name : "(null)");
+    return LFS_ERR_INVALID_ARG;
+}

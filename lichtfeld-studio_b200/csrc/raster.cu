@@ -1,0 +1,611 @@
+// lfs_b200 -- from-world alpha-blend rasterizer kernels (see raster.cuh for the formulation and layouts).
+// Reference behaviour being reproduced: gsplat/RasterizeToPixelsFromWorld3DGSFwd.cu:58-279 (forward) and
+// gsplat/RasterizeToPixelsFromWorld3DGSBwd.cu:63-372 + gsplat/Utils.cuh:104-158 (backward).
+#include "raster.cuh"
+#include "sort_scan.cuh"
+
+namespace lfs {
+
+RasterOptions& raster_options() {
+    static RasterOptions o;
+    return o;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// expand: one thread per sorted instance -> tile-local rational-quadratic record
+// ------------------------------------------------------------------------------------------------------
+constexpr int kExThreads = 256;
+
+__device__ __forceinline__ uint32_t find_tile(const int32_t* __restrict__ off, uint32_t n, uint32_t j) {
+    // largest t in [0, n) with off[t] <= j
+    uint32_t lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if ((uint32_t)__ldg(off + mid) <= j)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(kExThreads)
+    k_expand_instances(const GaussRec* __restrict__ gauss, const int32_t* __restrict__ inst_gid,
+                       const int32_t* __restrict__ tile_off, const uint32_t* __restrict__ sorted_tile_keys,
+                       const ViewCam* __restrict__ cams, const uint32_t n_tiles_per_cam, const uint32_t tile_w,
+                       const uint32_t C, const uint32_t n_cap, const uint32_t* __restrict__ n_dev,
+                       InstRec* __restrict__ inst) {
+    uint32_t n = n_cap;
+    if (n_dev) {
+        const uint32_t nd = *n_dev;
+        n = nd < n_cap ? nd : n_cap;
+    }
+    const uint32_t n_tiles_total = C * n_tiles_per_cam;
+    for (uint32_t j = blockIdx.x * kExThreads + threadIdx.x; j < n; j += gridDim.x * kExThreads) {
+        const uint32_t g = (uint32_t)__ldg(inst_gid + j);
+        const uint32_t ft = sorted_tile_keys ? __ldg(sorted_tile_keys + j) : find_tile(tile_off, n_tiles_total, j);
+        const uint32_t cam = ft / n_tiles_per_cam, t = ft - cam * n_tiles_per_cam;
+        const uint32_t ty = t / tile_w, tx = t - ty * tile_w;
+        const float cxp = cams[cam].cx, cyp = cams[cam].cy;
+        const float Xo = (float)(tx * kTile + kTile / 2) - cxp;
+        const float Yo = (float)(ty * kTile + kTile / 2) - cyp;
+
+        const float4* gp = reinterpret_cast<const float4*>(gauss + g);
+        const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1), g2 = __ldg(gp + 2), g3 = __ldg(gp + 3);
+        const f3 vx = mk3(g0.x, g0.y, g0.z), vy = mk3(g0.w, g1.x, g1.y), w2 = mk3(g1.z, g1.w, g2.x);
+        const f3 gro = mk3(g2.y, g2.z, g2.w);
+
+        const f3 v0 = w2 + vx * Xo + vy * Yo;
+        const f3 c0 = cross(v0, gro), cxv = cross(vx, gro), cyv = cross(vy, gro);
+        float4 A, B, Cc;
+        A.x = kNScale * dot(c0, c0);
+        A.y = kNScale * 2.f * dot(c0, cxv);
+        A.z = kNScale * 2.f * dot(c0, cyv);
+        A.w = kNScale * dot(cxv, cxv);
+        B.x = kNScale * 2.f * dot(cxv, cyv);
+        B.y = kNScale * dot(cyv, cyv);
+        B.z = dot(v0, v0);
+        B.w = 2.f * dot(v0, vx);
+        Cc.x = 2.f * dot(v0, vy);
+        Cc.y = dot(vx, vx);
+        Cc.z = 2.f * dot(vx, vy);
+        Cc.w = dot(vy, vy);
+        float4* out = reinterpret_cast<float4*>(inst + j);
+        out[0] = A;
+        out[1] = B;
+        out[2] = Cc;
+        out[3] = g3; // opacity, rgb
+    }
+}
+
+int launch_expand_instances(const RasterBuffers& rb, const ViewCam* cams_dev, uint32_t n_tiles_per_cam,
+                            uint32_t tile_w, uint32_t n_inst_cap, const uint32_t* n_inst_dev,
+                            const uint32_t* sorted_tile_keys, uint32_t C, uint32_t N, cudaStream_t stream) {
+    (void)N;
+    if (n_inst_cap == 0)
+        return LFS_OK;
+    const unsigned want = div_up(n_inst_cap, kExThreads);
+    const unsigned grid = want < (unsigned)(kNumSMs * 32) ? want : (unsigned)(kNumSMs * 32);
+    k_expand_instances<<<grid, kExThreads, 0, stream>>>(rb.gauss, rb.inst_gid, rb.tile_off, sorted_tile_keys, cams_dev,
+                                                        n_tiles_per_cam, tile_w, C, n_inst_cap, n_inst_dev, rb.inst);
+    LFS_LAUNCH_OK("k_expand_instances");
+    return LFS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// bucket bookkeeping
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_bucket_counts(const int32_t* __restrict__ tile_off, const uint32_t n_tiles,
+                                uint32_t* __restrict__ counts) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles)
+        return;
+    const int32_t c = tile_off[t + 1] - tile_off[t];
+    counts[t] = c > 0 ? (uint32_t)((c + kBucket - 1) / kBucket) : 0u;
+}
+__global__ void k_store_total(const uint32_t* __restrict__ total, uint32_t* __restrict__ off_last) {
+    *off_last = *total;
+}
+
+int launch_bucket_offsets(const RasterBuffers& rb, uint32_t n_tiles_total, uint32_t* n_buckets_dev, void* scan_scratch,
+                          uint32_t* counts_tmp, cudaStream_t stream) {
+    k_bucket_counts<<<div_up(n_tiles_total, 256), 256, 0, stream>>>(rb.tile_off, n_tiles_total, counts_tmp);
+    LFS_LAUNCH_OK("k_bucket_counts");
+    int rc = exclusive_scan_u32(counts_tmp, nullptr, rb.bucket_off, n_buckets_dev, n_tiles_total, nullptr, scan_scratch,
+                                stream);
+    if (rc)
+        return rc;
+    k_store_total<<<1, 1, 0, stream>>>(n_buckets_dev, rb.bucket_off + n_tiles_total);
+    LFS_LAUNCH_OK("k_store_total");
+    return LFS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// forward blend
+// ------------------------------------------------------------------------------------------------------
+constexpr int kBatch = 64; // InstRec per smem stage (4 KB)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile("{\n\t"
+                 ".reg .pred p;\n\t"
+                 "WAIT_LOOP:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra WAIT_DONE;\n\t"
+                 "bra WAIT_LOOP;\n\t"
+                 "WAIT_DONE:\n\t"
+                 "}" ::"r"(smem_u32(bar)),
+                 "r"(parity)
+                 : "memory");
+}
+// 1-D bulk async copy global -> shared (TMA engine), completion counted in bytes on `bar`
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct PixAcc {
+    float r, g, b, T;
+    uint32_t ncon;
+    bool done;
+};
+
+// evaluate `nrec` records of one staged batch for this pixel
+__device__ __forceinline__ void blend_batch(const float4* __restrict__ s, const int nrec, const uint32_t first_li,
+                                            const float dx, const float dy, const bool write_ckpt,
+                                            float4* __restrict__ ckpt_px /* + bucket*256 stride */, PixAcc& a) {
+    for (int t = 0; t < nrec; ++t) {
+        const uint32_t li = first_li + t;
+        if (write_ckpt && (li & (kBucket - 1)) == 0)
+            ckpt_px[(size_t)(li >> 5) * kTilePix] = make_float4(a.r, a.g, a.b, a.T);
+        const float4 A = s[4 * t], B = s[4 * t + 1], Cc = s[4 * t + 2], E = s[4 * t + 3];
+        const float Nv = fmaf(dy, fmaf(dy, B.y, A.z), fmaf(dx, fmaf(dy, B.x, fmaf(dx, A.w, A.y)), A.x));
+        const float Dv = fmaf(dy, fmaf(dy, Cc.w, Cc.x), fmaf(dx, fmaf(dy, Cc.z, fmaf(dx, Cc.y, B.w)), B.z));
+        const float vis = ex2_approx(Nv * rcp_approx(Dv));
+        const float alpha = fminf(kAlphaMax, E.x * vis);
+        if (alpha < kAlphaMin)
+            continue;
+        const float next_T = a.T * (1.0f - alpha);
+        if (next_T <= kTMin) {
+            a.done = true;
+            break;
+        }
+        const float w = alpha * a.T;
+        a.r = fmaf(w, E.y, a.r);
+        a.g = fmaf(w, E.z, a.g);
+        a.b = fmaf(w, E.w, a.b);
+        a.T = next_T;
+        a.ncon = li + 1;
+    }
+}
+
+template <bool USE_TMA>
+__global__ void __launch_bounds__(kTilePix)
+    k_blend_fwd(const RasterBuffers rb, const uint32_t width, const uint32_t height, const uint32_t tile_w,
+                const uint32_t tile_h, const bool write_ckpt, const float* __restrict__ backgrounds,
+                const uint8_t* __restrict__ masks, float* __restrict__ renders, float* __restrict__ alphas,
+                int32_t* __restrict__ last_ids) {
+    __shared__ __align__(128) float4 s_rec[2][kBatch * 4];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ uint32_t s_max[kTilePix / 32];
+
+    const uint32_t tile = blockIdx.x, cam = blockIdx.y;
+    const uint32_t n_tiles = tile_w * tile_h;
+    const uint32_t ft = cam * n_tiles + tile;
+    const uint32_t ty = tile / tile_w, tx = tile - ty * tile_w;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lx = tid & (kTile - 1), ly = tid >> 4;
+    const uint32_t px = tx * kTile + lx, py = ty * kTile + ly;
+    const bool inside = px < width && py < height;
+    const float dx = (float)lx - 7.5f, dy = (float)ly - 7.5f;
+
+    const int32_t start = rb.tile_off[ft];
+    int32_t end = rb.tile_off[ft + 1];
+    const int32_t cnt_raw = end > start ? end - start : 0;
+    if (masks && !masks[ft])
+        end = start;
+    const int32_t cnt = end > start ? end - start : 0;
+    const uint32_t boff = rb.bucket_off ? rb.bucket_off[ft] : 0u;
+    if (write_ckpt) { // bucket -> tile map for the backward (unmasked count: bucket_off is mask-agnostic)
+        const uint32_t nb = (uint32_t)(cnt_raw + kBucket - 1) / kBucket;
+        for (uint32_t k = tid; k < nb; k += kTilePix)
+            rb.bucket_tile[boff + k] = ft;
+    }
+    float4* ckpt_px = write_ckpt ? rb.ckpt + (size_t)boff * kTilePix + tid : nullptr;
+
+    PixAcc a;
+    a.r = a.g = a.b = 0.f;
+    a.T = 1.f;
+    a.ncon = 0;
+    a.done = !inside;
+
+    const float4* gsrc = reinterpret_cast<const float4*>(rb.inst + start);
+    const int nbatch = (cnt + kBatch - 1) / kBatch;
+
+    if (USE_TMA) {
+        if (tid == 0) {
+            mbar_init(&s_bar[0], 1);
+            mbar_init(&s_bar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int k = 0; k < 2 && k < nbatch; ++k) {
+                const uint32_t nrec = (uint32_t)min(kBatch, cnt - k * kBatch);
+                mbar_expect_tx(&s_bar[k], nrec * (uint32_t)sizeof(InstRec));
+                tma_load_1d(&s_rec[k][0], gsrc + (size_t)k * kBatch * 4, nrec * (uint32_t)sizeof(InstRec), &s_bar[k]);
+            }
+        }
+        int consumed = 0; // batches whose barrier has been waited on
+        for (int k = 0; k < nbatch; ++k) {
+            const int buf = k & 1;
+            mbar_wait(&s_bar[buf], (uint32_t)((k >> 1) & 1));
+            consumed = k + 1;
+            const int nrec = min(kBatch, cnt - k * kBatch);
+            if (!a.done)
+                blend_batch(&s_rec[buf][0], nrec, (uint32_t)(k * kBatch), dx, dy, write_ckpt, ckpt_px, a);
+            const int ndone = __syncthreads_count(a.done);
+            if (ndone == kTilePix)
+                break;
+            if (tid == 0 && k + 2 < nbatch) {
+                const uint32_t nr2 = (uint32_t)min(kBatch, cnt - (k + 2) * kBatch);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&s_bar[buf], nr2 * (uint32_t)sizeof(InstRec));
+                tma_load_1d(&s_rec[buf][0], gsrc + (size_t)(k + 2) * kBatch * 4, nr2 * (uint32_t)sizeof(InstRec),
+                            &s_bar[buf]);
+            }
+        }
+        // early exit: one more batch may still be in flight into this CTA's shared memory -- drain it
+        if (tid == 0 && consumed < nbatch)
+            mbar_wait(&s_bar[consumed & 1], (uint32_t)((consumed >> 1) & 1));
+    } else {
+        if (nbatch > 0) {
+            if ((int)tid < min(kBatch, cnt) * 4)
+                s_rec[0][tid] = ld_nc4(gsrc + tid);
+            __syncthreads();
+        }
+        for (int k = 0; k < nbatch; ++k) {
+            const int buf = k & 1;
+            const bool has_next = k + 1 < nbatch;
+            float4 pre = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int next_f4 = has_next ? min(kBatch, cnt - (k + 1) * kBatch) * 4 : 0;
+            if ((int)tid < next_f4)
+                pre = ld_nc4(gsrc + (size_t)(k + 1) * kBatch * 4 + tid);
+            const int nrec = min(kBatch, cnt - k * kBatch);
+            if (!a.done)
+                blend_batch(&s_rec[buf][0], nrec, (uint32_t)(k * kBatch), dx, dy, write_ckpt, ckpt_px, a);
+            if ((int)tid < next_f4)
+                s_rec[buf ^ 1][tid] = pre;
+            const int ndone = __syncthreads_count(a.done);
+            if (ndone == kTilePix)
+                break;
+        }
+    }
+
+    if (inside) {
+        const size_t pix = ((size_t)cam * height + py) * width + px;
+        rb.pix_state[pix] = make_float4(a.r, a.g, a.b, a.T);
+        rb.n_contrib[pix] = (int32_t)a.ncon;
+        if (renders) {
+            float br = 0.f, bgc = 0.f, bb = 0.f;
+            if (backgrounds) {
+                br = backgrounds[cam * 3], bgc = backgrounds[cam * 3 + 1], bb = backgrounds[cam * 3 + 2];
+            }
+            renders[pix * 3] = fmaf(a.T, br, a.r);
+            renders[pix * 3 + 1] = fmaf(a.T, bgc, a.g);
+            renders[pix * 3 + 2] = fmaf(a.T, bb, a.b);
+        }
+        if (alphas)
+            alphas[pix] = 1.0f - a.T;
+        if (last_ids)
+            last_ids[pix] = a.ncon > 0 ? start + (int32_t)a.ncon - 1 : 0;
+    }
+    // per-tile maximum contributor count (lets the backward skip whole buckets)
+    uint32_t m = a.ncon;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((tid & 31) == 0)
+        s_max[tid >> 5] = m;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t mm = 0;
+#pragma unroll
+        for (int w = 0; w < kTilePix / 32; ++w)
+            mm = max(mm, s_max[w]);
+        rb.tile_max_contrib[ft] = mm;
+    }
+}
+
+int launch_blend_fwd(const RasterBuffers& rb, uint32_t C, uint32_t width, uint32_t height, uint32_t tile_w,
+                     uint32_t tile_h, bool write_ckpt, const float* backgrounds, const uint8_t* masks, float* renders,
+                     float* alphas, int32_t* last_ids, cudaStream_t stream) {
+    if (C == 0 || tile_w == 0 || tile_h == 0)
+        return LFS_OK;
+    dim3 grid(tile_w * tile_h, C);
+    if (raster_options().use_tma)
+        k_blend_fwd<true><<<grid, kTilePix, 0, stream>>>(rb, width, height, tile_w, tile_h, write_ckpt, backgrounds,
+                                                         masks, renders, alphas, last_ids);
+    else
+        k_blend_fwd<false><<<grid, kTilePix, 0, stream>>>(rb, width, height, tile_w, tile_h, write_ckpt, backgrounds,
+                                                          masks, renders, alphas, last_ids);
+    LFS_LAUNCH_OK("k_blend_fwd");
+    return LFS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// backward blend: one warp per 32-instance bucket
+// ------------------------------------------------------------------------------------------------------
+constexpr int kBwdWarps = 4;
+
+__device__ __forceinline__ void quat_to_rotmat_dev(const float4 q_wxyz, float R[9], float& inv_norm, float qn[4]) {
+    float w = q_wxyz.x, x = q_wxyz.y, y = q_wxyz.z, z = q_wxyz.w;
+    inv_norm = rsqrtf(x * x + y * y + z * z + w * w);
+    x *= inv_norm, y *= inv_norm, z *= inv_norm, w *= inv_norm;
+    qn[0] = w, qn[1] = x, qn[2] = y, qn[3] = z;
+    const float x2 = x * x, y2 = y * y, z2 = z * z, xy = x * y, xz = x * z, yz = y * z, wx = w * x, wy = w * y,
+                wz = w * z;
+    R[0] = 1.f - 2.f * (y2 + z2), R[1] = 2.f * (xy - wz), R[2] = 2.f * (xz + wy);
+    R[3] = 2.f * (xy + wz), R[4] = 1.f - 2.f * (x2 + z2), R[5] = 2.f * (yz - wx);
+    R[6] = 2.f * (xz - wy), R[7] = 2.f * (yz + wx), R[8] = 1.f - 2.f * (x2 + y2);
+}
+
+__global__ void __launch_bounds__(kBwdWarps * 32)
+    k_blend_bwd(const RasterBuffers rb, const ViewCam* __restrict__ cams, const float4* __restrict__ v_pix,
+                const float* __restrict__ quats, const float* __restrict__ scales, const float* __restrict__ means,
+                const uint32_t N, const uint32_t width, const uint32_t height, const uint32_t tile_w,
+                const uint32_t tile_h, const uint32_t n_bucket_cap, const uint32_t* __restrict__ n_buckets_dev,
+                float* __restrict__ v_means, float* __restrict__ v_quats, float* __restrict__ v_scales,
+                float* __restrict__ v_colors, float* __restrict__ v_opacities) {
+    __shared__ float4 sA[kBwdWarps][32];
+    __shared__ float4 sB[kBwdWarps][32];
+    __shared__ int32_t sN[kBwdWarps][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t b = blockIdx.x * kBwdWarps + warp;
+    uint32_t nbk = *n_buckets_dev;
+    nbk = nbk < n_bucket_cap ? nbk : n_bucket_cap;
+    if (b >= nbk)
+        return;
+    const uint32_t n_tiles = tile_w * tile_h;
+    const uint32_t ft = rb.bucket_tile[b];
+    const uint32_t cam = ft / n_tiles, tile = ft - cam * n_tiles;
+    const uint32_t ty = tile / tile_w, tx = tile - ty * tile_w;
+    const int32_t tstart = rb.tile_off[ft], tend = rb.tile_off[ft + 1];
+    const uint32_t local_b = b - rb.bucket_off[ft];
+    if (local_b * kBucket >= rb.tile_max_contrib[ft])
+        return;
+    const uint32_t li = local_b * kBucket + lane; // tile-local instance index of this lane
+    const int32_t inst = tstart + (int32_t)li;
+    const bool valid = inst < tend;
+
+    float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A, Cc = A, E = A;
+    uint32_t g = 0;
+    if (valid) {
+        const float4* rp = reinterpret_cast<const float4*>(rb.inst + inst);
+        A = ld_nc4(rp), B = ld_nc4(rp + 1), Cc = ld_nc4(rp + 2), E = ld_nc4(rp + 3);
+        g = (uint32_t)__ldg(rb.inst_gid + inst);
+    }
+
+    // rotating pixel state
+    int32_t ncon = 0;
+    float car = 0.f, cag = 0.f, cab = 0.f, T = 0.f;
+    float vr = 0.f, vg = 0.f, vb = 0.f, ga = 0.f;
+    // per-instance accumulators
+    float an0 = 0.f, an1 = 0.f, an2 = 0.f, an3 = 0.f, an4 = 0.f, an5 = 0.f;
+    float ad0 = 0.f, ad1 = 0.f, ad2 = 0.f, ad3 = 0.f, ad4 = 0.f, ad5 = 0.f;
+    float aop = 0.f, acr = 0.f, acg = 0.f, acb = 0.f;
+
+    const float4* ck = rb.ckpt + (size_t)b * kTilePix;
+
+    for (int i = 0; i < kTilePix + 31; ++i) {
+        if ((i & 31) == 0 && i < kTilePix) {
+            __syncwarp();
+            const int p = i + lane;
+            const uint32_t px = tx * kTile + (p & 15), py = ty * kTile + (p >> 4);
+            float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a4;
+            int32_t nc = 0;
+            if (px < width && py < height) {
+                const size_t pix = ((size_t)cam * height + py) * width + px;
+                nc = __ldg(rb.n_contrib + pix);
+                if ((uint32_t)nc > local_b * kBucket) { // this pixel reaches the bucket: checkpoint is valid
+                    const float4 c4 = ld_nc4(ck + p);
+                    const float4 f4 = __ldg(rb.pix_state + pix);
+                    a4 = make_float4(f4.x - c4.x, f4.y - c4.y, f4.z - c4.z, c4.w);
+                    b4 = __ldg(v_pix + pix);
+                } else {
+                    nc = 0;
+                }
+            }
+            sA[warp][lane] = a4;
+            sB[warp][lane] = b4;
+            sN[warp][lane] = nc;
+            __syncwarp();
+        }
+        if (i > 0) {
+            ncon = __shfl_up_sync(0xffffffffu, ncon, 1);
+            car = __shfl_up_sync(0xffffffffu, car, 1);
+            cag = __shfl_up_sync(0xffffffffu, cag, 1);
+            cab = __shfl_up_sync(0xffffffffu, cab, 1);
+            T = __shfl_up_sync(0xffffffffu, T, 1);
+            vr = __shfl_up_sync(0xffffffffu, vr, 1);
+            vg = __shfl_up_sync(0xffffffffu, vg, 1);
+            vb = __shfl_up_sync(0xffffffffu, vb, 1);
+            ga = __shfl_up_sync(0xffffffffu, ga, 1);
+        }
+        if (lane == 0) {
+            if (i < kTilePix) {
+                const float4 a4 = sA[warp][i & 31], b4 = sB[warp][i & 31];
+                ncon = sN[warp][i & 31];
+                car = a4.x, cag = a4.y, cab = a4.z, T = a4.w;
+                vr = b4.x, vg = b4.y, vb = b4.z, ga = b4.w;
+            } else {
+                ncon = 0;
+            }
+        }
+        const int idx = i - lane;
+        const bool active = valid && idx >= 0 && idx < kTilePix && (int32_t)li < ncon;
+        if (!active)
+            continue;
+        const float dx = (float)(idx & 15) - 7.5f, dy = (float)(idx >> 4) - 7.5f;
+        const float Nv = fmaf(dy, fmaf(dy, B.y, A.z), fmaf(dx, fmaf(dy, B.x, fmaf(dx, A.w, A.y)), A.x));
+        const float Dv = fmaf(dy, fmaf(dy, Cc.w, Cc.x), fmaf(dx, fmaf(dy, Cc.z, fmaf(dx, Cc.y, B.w)), B.z));
+        const float rD = rcp_approx(Dv);
+        const float p2 = Nv * rD;
+        const float vis = ex2_approx(p2);
+        const float a_raw = E.x * vis;
+        const float alpha = fminf(kAlphaMax, a_raw);
+        if (alpha < kAlphaMin)
+            continue;
+        const float w = T * alpha;
+        acr = fmaf(w, vr, acr);
+        acg = fmaf(w, vg, acg);
+        acb = fmaf(w, vb, acb);
+        car = fmaf(-w, E.y, car);
+        cag = fmaf(-w, E.z, cag);
+        cab = fmaf(-w, E.w, cab);
+        const float om = 1.0f - alpha;
+        const float ra = __fdividef(1.0f, om);
+        const float v_alpha = (T * E.y - car * ra) * vr + (T * E.z - cag * ra) * vg + (T * E.w - cab * ra) * vb + ga * ra;
+        if (a_raw <= kAlphaMax) {
+            aop = fmaf(vis, v_alpha, aop);
+            const float v_p2 = v_alpha * a_raw * kLn2;
+            const float vN = v_p2 * rD;
+            const float vD = -vN * p2;
+            const float dxx = dx * dx, dxy = dx * dy, dyy = dy * dy;
+            an0 += vN;
+            an1 = fmaf(vN, dx, an1);
+            an2 = fmaf(vN, dy, an2);
+            an3 = fmaf(vN, dxx, an3);
+            an4 = fmaf(vN, dxy, an4);
+            an5 = fmaf(vN, dyy, an5);
+            ad0 += vD;
+            ad1 = fmaf(vD, dx, ad1);
+            ad2 = fmaf(vD, dy, ad2);
+            ad3 = fmaf(vD, dxx, ad3);
+            ad4 = fmaf(vD, dxy, ad4);
+            ad5 = fmaf(vD, dyy, ad5);
+        }
+        T *= om;
+    }
+
+    if (!valid)
+        return;
+    // ---- per-instance chain rule: polynomial coefficients -> (vx, vy, w2, gro) -> (mean, quat, scale)
+    const ViewCam& cm = cams[cam];
+    const uint32_t gid = g % N;
+    const float4* gp = reinterpret_cast<const float4*>(rb.gauss + g);
+    const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1), g2 = __ldg(gp + 2);
+    const f3 vx = mk3(g0.x, g0.y, g0.z), vy = mk3(g0.w, g1.x, g1.y), w2 = mk3(g1.z, g1.w, g2.x);
+    const f3 gro = mk3(g2.y, g2.z, g2.w);
+    const float Xo = (float)(tx * kTile + kTile / 2) - cm.cx;
+    const float Yo = (float)(ty * kTile + kTile / 2) - cm.cy;
+    const f3 v0 = w2 + vx * Xo + vy * Yo;
+    const f3 c0 = cross(v0, gro), cxv = cross(vx, gro), cyv = cross(vy, gro);
+    // un-scale the N' coefficient gradients
+    const float gn0 = kNScale * an0, gn1x = kNScale * an1, gn1y = kNScale * an2, gn2xx = kNScale * an3,
+                gn2xy = kNScale * an4, gn2yy = kNScale * an5;
+    const f3 v_c0 = (c0 * gn0 + cxv * gn1x + cyv * gn1y) * 2.f;
+    const f3 v_cxv = (c0 * gn1x + cxv * gn2xx + cyv * gn2xy) * 2.f;
+    const f3 v_cyv = (c0 * gn1y + cxv * gn2xy + cyv * gn2yy) * 2.f;
+    f3 v_v0 = (v0 * ad0 + vx * ad1 + vy * ad2) * 2.f;
+    f3 v_vx = (v0 * ad1 + vx * ad3 + vy * ad4) * 2.f;
+    f3 v_vy = (v0 * ad2 + vx * ad4 + vy * ad5) * 2.f;
+    // c = a x gro :  dL/da += gro x v_c ,  dL/dgro += v_c x a
+    v_v0 = v_v0 + cross(gro, v_c0);
+    v_vx = v_vx + cross(gro, v_cxv);
+    v_vy = v_vy + cross(gro, v_cyv);
+    const f3 v_gro = cross(v_c0, v0) + cross(v_cxv, vx) + cross(v_cyv, vy);
+    // v0 = w2 + Xo vx + Yo vy
+    const f3 v_w2 = v_v0;
+    v_vx = v_vx + v_v0 * Xo;
+    v_vy = v_vy + v_v0 * Yo;
+
+    const float4 q = __ldg(reinterpret_cast<const float4*>(quats) + gid);
+    const f3 sc = mk3(__ldg(scales + 3 * gid), __ldg(scales + 3 * gid + 1), __ldg(scales + 3 * gid + 2));
+    const f3 mu = mk3(__ldg(means + 3 * gid), __ldg(means + 3 * gid + 1), __ldg(means + 3 * gid + 2));
+    float R[9], inv_norm, qn[4];
+    quat_to_rotmat_dev(q, R, inv_norm, qn);
+    const float is[3] = {1.0f / sc.x, 1.0f / sc.y, 1.0f / sc.z};
+    const float omu[3] = {cm.org[0] - mu.x, cm.org[1] - mu.y, cm.org[2] - mu.z};
+    const float ifx = 1.0f / cm.fx, ify = 1.0f / cm.fy;
+    const float vvx[3] = {v_vx.x * ifx, v_vx.y * ifx, v_vx.z * ifx};
+    const float vvy[3] = {v_vy.x * ify, v_vy.y * ify, v_vy.z * ify};
+    const float vw2[3] = {v_w2.x, v_w2.y, v_w2.z};
+    const float vgro[3] = {v_gro.x, v_gro.y, v_gro.z};
+    // v_M[a][i] (M = S^-1 R^T, M[a][i] = R[i][a] / s_a)
+    float vM[3][3];
+#pragma unroll
+    for (int a_ = 0; a_ < 3; ++a_)
+#pragma unroll
+        for (int i_ = 0; i_ < 3; ++i_)
+            vM[a_][i_] = vvx[a_] * cm.R[0 + i_] + vvy[a_] * cm.R[3 + i_] + vw2[a_] * cm.R[6 + i_] + vgro[a_] * omu[i_];
+    float v_mean[3], v_scale[3], GR[3][3];
+#pragma unroll
+    for (int i_ = 0; i_ < 3; ++i_) {
+        float s = 0.f;
+#pragma unroll
+        for (int a_ = 0; a_ < 3; ++a_)
+            s += R[i_ * 3 + a_] * is[a_] * vgro[a_];
+        v_mean[i_] = -s;
+    }
+#pragma unroll
+    for (int a_ = 0; a_ < 3; ++a_) {
+        float s = 0.f;
+#pragma unroll
+        for (int i_ = 0; i_ < 3; ++i_) {
+            GR[i_][a_] = vM[a_][i_] * is[a_];
+            s += R[i_ * 3 + a_] * vM[a_][i_];
+        }
+        v_scale[a_] = -is[a_] * is[a_] * s;
+    }
+    // quat_to_rotmat VJP (same algebra as the reference's Utils.cuh:104-126; G[r][c] = dL/dR[r][c])
+    const float qw = qn[0], qx = qn[1], qy = qn[2], qz = qn[3];
+    float vq[4];
+    vq[0] = 2.f * (qx * (GR[2][1] - GR[1][2]) + qy * (GR[0][2] - GR[2][0]) + qz * (GR[1][0] - GR[0][1]));
+    vq[1] = 2.f * (-2.f * qx * (GR[1][1] + GR[2][2]) + qy * (GR[1][0] + GR[0][1]) + qz * (GR[2][0] + GR[0][2]) +
+                   qw * (GR[2][1] - GR[1][2]));
+    vq[2] = 2.f * (qx * (GR[1][0] + GR[0][1]) - 2.f * qy * (GR[0][0] + GR[2][2]) + qz * (GR[2][1] + GR[1][2]) +
+                   qw * (GR[0][2] - GR[2][0]));
+    vq[3] = 2.f * (qx * (GR[2][0] + GR[0][2]) + qy * (GR[2][1] + GR[1][2]) - 2.f * qz * (GR[0][0] + GR[1][1]) +
+                   qw * (GR[1][0] - GR[0][1]));
+    const float dq = vq[0] * qn[0] + vq[1] * qn[1] + vq[2] * qn[2] + vq[3] * qn[3];
+
+    atomicAdd(v_means + 3 * gid, v_mean[0]);
+    atomicAdd(v_means + 3 * gid + 1, v_mean[1]);
+    atomicAdd(v_means + 3 * gid + 2, v_mean[2]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        atomicAdd(v_quats + 4 * gid + k, (vq[k] - dq * qn[k]) * inv_norm);
+    atomicAdd(v_scales + 3 * gid, v_scale[0]);
+    atomicAdd(v_scales + 3 * gid + 1, v_scale[1]);
+    atomicAdd(v_scales + 3 * gid + 2, v_scale[2]);
+    atomicAdd(v_colors + 3 * (size_t)g, acr);
+    atomicAdd(v_colors + 3 * (size_t)g + 1, acg);
+    atomicAdd(v_colors + 3 * (size_t)g + 2, acb);
+    atomicAdd(v_opacities + g, aop);
+}
+
+int launch_blend_bwd(const RasterBuffers& rb, const ViewCam* cams_dev, const float4* v_pix, const float* quats,
+                     const float* scales, const float* means, uint32_t C, uint32_t N, uint32_t width, uint32_t height,
+                     uint32_t tile_w, uint32_t tile_h, uint32_t n_bucket_cap, const uint32_t* n_buckets_dev,
+                     float* v_means, float* v_quats, float* v_scales, float* v_colors, float* v_opacities,
+                     cudaStream_t stream) {
+    (void)C;
+    if (n_bucket_cap == 0)
+        return LFS_OK;
+    k_blend_bwd<<<div_up(n_bucket_cap, kBwdWarps), kBwdWarps * 32, 0, stream>>>(
+        rb, cams_dev, v_pix, quats, scales, means, N, width, height, tile_w, tile_h, n_bucket_cap, n_buckets_dev,
+        v_means, v_quats, v_scales, v_colors, v_opacities);
+    LFS_LAUNCH_OK("k_blend_bwd");
+    return LFS_OK;
+}
+
+} // namespace lfs

@@ -1,0 +1,92 @@
+// lfs_b200 -- from-world (3DGUT) alpha-blend rasterizer: data layout + launch API shared by the
+// gsplat-surface ops and the fused trainer.
+//
+// B200-first reformulation (NOT the reference's per-pixel ray algebra):
+// for a PINHOLE / GLOBAL-shutter camera every pixel ray leaves the same origin o and its direction is
+// affine in the pixel coordinate, d(px,py) = R^T((px-cx)/fx, (py-cy)/fy, 1).  The reference's response
+//   power = -1/2 |normalize(M d) x M(o-mu)|^2          (RasterizeToPixelsFromWorld3DGSFwd.cu:233-237)
+// is therefore exactly   power = -1/2 |v x gro|^2 / |v|^2   with  v = M d  affine in (px,py)  and
+// gro = M(o-mu) constant per Gaussian, i.e. a RATIO OF TWO QUADRATIC POLYNOMIALS in the pixel coordinate.
+// Expanding both polynomials around the centre of a 16x16 tile keeps every term O(result) (no catastrophic
+// cancellation; the cross product v0 x gro is evaluated once per (tile, Gaussian) with the same
+// conditioning as the reference) and turns the per-(pixel, Gaussian) work into 10 FMA + rcp + ex2.
+//
+//   GaussRec (64 B, one per camera-Gaussian pair): vx, vy, w2 (columns of M R^T scaled by 1/fx, 1/fy, 1),
+//                                                  gro, opacity, rgb
+//   InstRec  (64 B, one per sorted tile-Gaussian instance, contiguous per tile):
+//        N'(dx,dy) = n0 + n1x dx + n1y dy + n2xx dx^2 + n2xy dx dy + n2yy dy^2   (already x -1/2 log2 e)
+//        D (dx,dy) = d0 + d1x dx + ...                                             (> 0)
+//        alpha = min(0.999, opacity * 2^(N'/D)),  dx,dy = pixel centre - tile centre in [-7.5, 7.5]
+//   Ckpt     (16 B per pixel per 32-instance bucket): (rgb accumulated so far, T) at the bucket start,
+//            written by the forward, consumed by the backward (one warp per bucket, lane = instance, pixel
+//            state rotating through the lanes: per-Gaussian gradients live in registers, no reduction).
+#pragma once
+#include "common.cuh"
+
+namespace lfs {
+
+struct alignas(16) GaussRec {
+    float vx[3], vy[3], w2[3], gro[3];
+    float opacity;
+    float rgb[3];
+};
+static_assert(sizeof(GaussRec) == 64, "GaussRec must be 64 bytes");
+
+struct alignas(16) InstRec {
+    float n0, n1x, n1y, n2xx; // float4 A
+    float n2xy, n2yy, d0, d1x; // float4 B
+    float d1y, d2xx, d2xy, d2yy; // float4 C
+    float opacity, r, g, b; // float4 E
+};
+static_assert(sizeof(InstRec) == 64, "InstRec must be 64 bytes");
+
+constexpr float kNScale = -0.72134752044448170368f; // -0.5 * log2(e)
+constexpr float kLn2 = 0.69314718055994530942f;
+constexpr float kAlphaMin = 1.0f / 255.0f;
+constexpr float kAlphaMax = 0.999f;
+constexpr float kTMin = 1e-4f;
+
+struct RasterBuffers {
+    // inputs
+    const GaussRec* gauss;     // [C*N]
+    const int32_t* tile_off;   // [n_tiles_total + 1] (start of every (camera, tile); last = n_inst)
+    const int32_t* inst_gid;   // [n_inst] flattened (camera*N + gaussian) id per sorted instance
+    // per-instance / per-bucket scratch
+    InstRec* inst;             // [n_inst_cap]
+    uint32_t* bucket_off;      // [n_tiles_total + 1] exclusive scan of ceil(count/32)
+    uint32_t* bucket_tile;     // [n_bucket_cap]
+    float4* ckpt;              // [n_bucket_cap * 256]
+    uint32_t* tile_max_contrib; // [n_tiles_total]
+    // per-pixel state
+    float4* pix_state;         // [C*H*W] (rgb before background, T_final)
+    int32_t* n_contrib;        // [C*H*W] tile-local index + 1 of the last contributor (0 = none)
+};
+
+// Tunables (process-wide; set through lfs_set_option).
+struct RasterOptions {
+    int use_tma = 1; // stage InstRec batches with cp.async.bulk + mbarrier (1) or register-staged loads (0)
+};
+RasterOptions& raster_options();
+
+int launch_expand_instances(const RasterBuffers& rb, const ViewCam* cams_dev /* [C] device */, uint32_t n_tiles_per_cam,
+                            uint32_t tile_w, uint32_t n_inst_cap, const uint32_t* n_inst_dev,
+                            const uint32_t* sorted_tile_keys /* nullable: per-instance tile id within camera */,
+                            uint32_t C, uint32_t N, cudaStream_t stream);
+
+int launch_bucket_offsets(const RasterBuffers& rb, uint32_t n_tiles_total, uint32_t* n_buckets_dev, void* scan_scratch,
+                          uint32_t* counts_tmp, cudaStream_t stream);
+
+// forward blend. renders/alphas/last_ids (gsplat layouts) are optional; backgrounds [C,3] / masks optional.
+int launch_blend_fwd(const RasterBuffers& rb, uint32_t C, uint32_t width, uint32_t height, uint32_t tile_w,
+                     uint32_t tile_h, bool write_ckpt, const float* backgrounds, const uint8_t* masks, float* renders,
+                     float* alphas, int32_t* last_ids, cudaStream_t stream);
+
+// backward blend: v_pix [C*H*W] = (dL/d rgb, T_final * (dL/d alpha - <bg, dL/d rgb>)).
+// Accumulates (atomics) into v_means [N,3], v_quats [N,4], v_scales [N,3], v_colors [C*N,3], v_opacities [C*N].
+int launch_blend_bwd(const RasterBuffers& rb, const ViewCam* cams_dev, const float4* v_pix, const float* quats,
+                     const float* scales, const float* means, uint32_t C, uint32_t N, uint32_t width, uint32_t height,
+                     uint32_t tile_w, uint32_t tile_h, uint32_t n_bucket_cap, const uint32_t* n_buckets_dev,
+                     float* v_means, float* v_quats, float* v_scales, float* v_colors, float* v_opacities,
+                     cudaStream_t stream);
+
+} // namespace lfs

@@ -1,0 +1,277 @@
+// lfs_b200 -- gsplat-surface rasterization ops on top of raster.cu:
+//   lfs_rasterize_to_pixels_from_world_3dgs_fwd / _bwd
+// drop-ins for gsplat::rasterize_to_pixels_from_world_3dgs_fwd/bwd (reference gsplat/Rasterization.cpp:20-261).
+#include "projection.cuh"
+#include "raster.cuh"
+#include "sort_scan.cuh"
+
+namespace lfs {
+
+__global__ void k_make_cams(const float* __restrict__ viewmats, const float* __restrict__ Ks, uint32_t C, int width,
+                            int height, ViewCam* __restrict__ cams) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C)
+        cams[c] = make_viewcam(viewmats + 16 * c, Ks + 9 * c, width, height);
+}
+
+// GaussRec for every (camera, Gaussian) pair from activated parameters (quats need not be unit length:
+// normalised with rsqrt exactly where the reference's quat_to_rotmat does, Utils.cuh:80-87).
+__global__ void __launch_bounds__(256)
+    k_prep_gaussians(const float* __restrict__ means, const float* __restrict__ quats,
+                     const float* __restrict__ scales, const float* __restrict__ colors,
+                     const float* __restrict__ opacities, const ViewCam* __restrict__ cams, const uint32_t N,
+                     const uint32_t total, GaussRec* __restrict__ out) {
+    const uint32_t idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= total)
+        return;
+    const uint32_t cam = idx / N, gid = idx - cam * N;
+    const ViewCam& cm = cams[cam];
+    const float4 q = __ldg(reinterpret_cast<const float4*>(quats) + gid);
+    float w = q.x, x = q.y, y = q.z, z = q.w;
+    const float inv_norm = rsqrtf(x * x + y * y + z * z + w * w);
+    x *= inv_norm, y *= inv_norm, z *= inv_norm, w *= inv_norm;
+    const float x2 = x * x, y2 = y * y, z2 = z * z, xy = x * y, xz = x * z, yz = y * z, wx = w * x, wy = w * y,
+                wz = w * z;
+    // columns of R_g divided by the matching scale = rows of M = S^-1 R_g^T
+    const float isx = 1.0f / __ldg(scales + 3 * gid), isy = 1.0f / __ldg(scales + 3 * gid + 1),
+                isz = 1.0f / __ldg(scales + 3 * gid + 2);
+    const f3 m0 = mk3(1.f - 2.f * (y2 + z2), 2.f * (xy + wz), 2.f * (xz - wy)) * isx;
+    const f3 m1 = mk3(2.f * (xy - wz), 1.f - 2.f * (x2 + z2), 2.f * (yz + wx)) * isy;
+    const f3 m2 = mk3(2.f * (xz + wy), 2.f * (yz - wx), 1.f - 2.f * (x2 + y2)) * isz;
+    const f3 r0 = mk3(cm.R[0], cm.R[1], cm.R[2]), r1 = mk3(cm.R[3], cm.R[4], cm.R[5]),
+             r2 = mk3(cm.R[6], cm.R[7], cm.R[8]);
+    const float ifx = 1.0f / cm.fx, ify = 1.0f / cm.fy;
+    const f3 omu = mk3(cm.org[0] - __ldg(means + 3 * gid), cm.org[1] - __ldg(means + 3 * gid + 1),
+                       cm.org[2] - __ldg(means + 3 * gid + 2));
+    float4* o = reinterpret_cast<float4*>(out + idx);
+    const f3 vx = mk3(dot(m0, r0), dot(m1, r0), dot(m2, r0)) * ifx;
+    const f3 vy = mk3(dot(m0, r1), dot(m1, r1), dot(m2, r1)) * ify;
+    const f3 w2 = mk3(dot(m0, r2), dot(m1, r2), dot(m2, r2));
+    const f3 gro = mk3(dot(m0, omu), dot(m1, omu), dot(m2, omu));
+    o[0] = make_float4(vx.x, vx.y, vx.z, vy.x);
+    o[1] = make_float4(vy.y, vy.z, w2.x, w2.y);
+    o[2] = make_float4(w2.z, gro.x, gro.y, gro.z);
+    o[3] = make_float4(__ldg(opacities + idx), __ldg(colors + 3 * (size_t)idx), __ldg(colors + 3 * (size_t)idx + 1),
+                       __ldg(colors + 3 * (size_t)idx + 2));
+}
+
+__global__ void k_copy_offsets(const int32_t* __restrict__ src, uint32_t n, int32_t last, int32_t* __restrict__ dst) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        dst[i] = src[i];
+    if (i == n)
+        dst[n] = last;
+}
+
+// v_pix = (dL/drgb, T_final * (dL/dalpha - <bg, dL/drgb>))
+__global__ void __launch_bounds__(256)
+    k_pack_vpix(const float* __restrict__ v_colors, const float* __restrict__ v_alphas,
+                const float4* __restrict__ pix_state, const float* __restrict__ backgrounds, const uint32_t hw,
+                const uint32_t total, float4* __restrict__ v_pix) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= total)
+        return;
+    const float r = v_colors[3 * (size_t)i], g = v_colors[3 * (size_t)i + 1], b = v_colors[3 * (size_t)i + 2];
+    float va = v_alphas[i];
+    if (backgrounds) {
+        const uint32_t cam = i / hw;
+        va -= backgrounds[3 * cam] * r + backgrounds[3 * cam + 1] * g + backgrounds[3 * cam + 2] * b;
+    }
+    v_pix[i] = make_float4(r, g, b, pix_state[i].w * va);
+}
+
+struct RasterScratch {
+    ViewCam* cams;
+    GaussRec* gauss;
+    int32_t* tile_off;
+    InstRec* inst;
+    uint32_t* bucket_off;
+    uint32_t* counts_tmp;
+    uint32_t* n_buckets;
+    uint32_t* bucket_tile;
+    float4* ckpt;
+    uint32_t* tile_max;
+    float4* pix_state;
+    int32_t* n_contrib;
+    float4* v_pix;
+    void* scan_scratch;
+    size_t bytes;
+};
+
+static RasterScratch carve_scratch(void* blob, uint32_t C, uint32_t N, uint32_t n_tiles_total, uint64_t n_isects,
+                                   uint64_t n_pix, bool bwd) {
+    Carver c(blob);
+    RasterScratch s;
+    s.cams = c.take<ViewCam>(C);
+    s.gauss = c.take<GaussRec>((size_t)C * N);
+    s.tile_off = c.take<int32_t>(n_tiles_total + 1);
+    s.inst = c.take<InstRec>(n_isects ? n_isects : 1);
+    s.bucket_off = c.take<uint32_t>(n_tiles_total + 1);
+    s.counts_tmp = c.take<uint32_t>(n_tiles_total + 1);
+    s.n_buckets = c.take<uint32_t>(4);
+    s.tile_max = c.take<uint32_t>(n_tiles_total);
+    s.pix_state = c.take<float4>(n_pix);
+    s.n_contrib = c.take<int32_t>(n_pix);
+    s.scan_scratch = c.take<char>(scan_scratch_bytes(n_tiles_total + 1));
+    const uint64_t n_bucket_cap = n_isects / kBucket + n_tiles_total + 1;
+    if (bwd) {
+        s.bucket_tile = c.take<uint32_t>(n_bucket_cap);
+        s.ckpt = c.take<float4>(n_bucket_cap * kTilePix);
+        s.v_pix = c.take<float4>(n_pix);
+    } else {
+        s.bucket_tile = nullptr;
+        s.ckpt = nullptr;
+        s.v_pix = nullptr;
+    }
+    s.bytes = c.total();
+    return s;
+}
+
+static int check_common(uint32_t tile_size, int camera_model, int rs_type, const float* viewmats1,
+                        const float* radial, const float* tangential, const float* thin_prism, const char* who) {
+    LFS_UNSUPPORTED(tile_size != (uint32_t)kTile, "%s: tile_size %u not implemented (16 only)", who, tile_size);
+    LFS_UNSUPPORTED(camera_model != LFS_PINHOLE, "%s: only the PINHOLE camera model is implemented", who);
+    LFS_UNSUPPORTED(rs_type != LFS_GLOBAL || viewmats1 != nullptr, "%s: rolling shutter is not implemented", who);
+    LFS_UNSUPPORTED(radial || tangential || thin_prism, "%s: lens distortion is not implemented", who);
+    return LFS_OK;
+}
+
+// shared front half: cameras, GaussRec, offsets, expansion, bucket offsets
+static int raster_front(const RasterScratch& s, RasterBuffers& rb, const float* means, const float* quats,
+                        const float* scales, const float* colors, const float* opacities, uint32_t N, uint32_t C,
+                        uint32_t width, uint32_t height, const float* viewmats, const float* Ks,
+                        const int32_t* tile_offsets, const int32_t* flatten_ids, int64_t n_isects, bool bwd,
+                        cudaStream_t stream) {
+    const uint32_t tile_w = (width + kTile - 1) / kTile, tile_h = (height + kTile - 1) / kTile;
+    const uint32_t n_tiles = tile_w * tile_h, n_tiles_total = C * n_tiles;
+    k_make_cams<<<div_up(C, 32), 32, 0, stream>>>(viewmats, Ks, C, (int)width, (int)height, s.cams);
+    LFS_LAUNCH_OK("k_make_cams");
+    k_prep_gaussians<<<div_up((uint64_t)C * N, 256), 256, 0, stream>>>(means, quats, scales, colors, opacities, s.cams, N,
+                                                                       C * N, s.gauss);
+    LFS_LAUNCH_OK("k_prep_gaussians");
+    k_copy_offsets<<<div_up(n_tiles_total + 1, 256), 256, 0, stream>>>(tile_offsets, n_tiles_total, (int32_t)n_isects,
+                                                                       s.tile_off);
+    LFS_LAUNCH_OK("k_copy_offsets");
+    rb.gauss = s.gauss;
+    rb.tile_off = s.tile_off;
+    rb.inst_gid = flatten_ids;
+    rb.inst = s.inst;
+    rb.bucket_off = s.bucket_off;
+    rb.bucket_tile = s.bucket_tile;
+    rb.ckpt = s.ckpt;
+    rb.tile_max_contrib = s.tile_max;
+    rb.pix_state = s.pix_state;
+    rb.n_contrib = s.n_contrib;
+    int rc = launch_expand_instances(rb, s.cams, n_tiles, tile_w, (uint32_t)n_isects, nullptr, nullptr, C, N, stream);
+    if (rc)
+        return rc;
+    if (bwd) {
+        rc = launch_bucket_offsets(rb, n_tiles_total, s.n_buckets, s.scan_scratch, s.counts_tmp, stream);
+        if (rc)
+            return rc;
+    } else {
+        rb.bucket_off = nullptr;
+    }
+    return LFS_OK;
+}
+
+} // namespace lfs
+
+extern "C" int lfs_rasterize_to_pixels_from_world_3dgs_fwd(
+    const float* means, const float* quats, const float* scales, const float* colors, const float* opacities,
+    const float* backgrounds, const uint8_t* masks, uint32_t N, uint32_t C, uint32_t channels, uint32_t image_width,
+    uint32_t image_height, uint32_t tile_size, const float* viewmats0, const float* viewmats1, const float* Ks,
+    int camera_model, const lfs_ut_params* ut_params, int rs_type, const float* radial_coeffs,
+    const float* tangential_coeffs, const float* thin_prism_coeffs, const int32_t* tile_offsets,
+    const int32_t* flatten_ids, int64_t n_isects, lfs_alloc_fn alloc, void* alloc_ctx, float* renders, float* alphas,
+    int32_t* last_ids, void* stream_) {
+    using namespace lfs;
+    (void)ut_params;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LFS_CHECK_ARG(means && quats && scales && colors && opacities && viewmats0 && Ks && tile_offsets && renders &&
+                      alphas && last_ids && alloc,
+                  "rasterize_fwd: null required pointer");
+    LFS_CHECK_ARG(n_isects == 0 || flatten_ids, "rasterize_fwd: flatten_ids is null");
+    LFS_UNSUPPORTED(channels != 3, "rasterize_fwd: channels=%u not implemented (3 only)", channels);
+    int rc = check_common(tile_size, camera_model, rs_type, viewmats1, radial_coeffs, tangential_coeffs,
+                          thin_prism_coeffs, "rasterize_fwd");
+    if (rc)
+        return rc;
+    if (C == 0 || image_width == 0 || image_height == 0)
+        return LFS_OK;
+    LFS_CHECK_ARG(n_isects >= 0 && n_isects < (1ll << 31), "rasterize_fwd: bad n_isects");
+    const uint32_t tile_w = (image_width + kTile - 1) / kTile, tile_h = (image_height + kTile - 1) / kTile;
+    const uint32_t n_tiles_total = C * tile_w * tile_h;
+    const uint64_t n_pix = (uint64_t)C * image_width * image_height;
+    RasterScratch sz = carve_scratch(nullptr, C, N, n_tiles_total, (uint64_t)n_isects, n_pix, false);
+    void* blob = alloc(alloc_ctx, LFS_TAG_SCRATCH, sz.bytes);
+    if (!blob) {
+        set_error("rasterize_fwd: scratch allocation of %zu bytes failed", sz.bytes);
+        return LFS_ERR_ALLOC;
+    }
+    RasterScratch s = carve_scratch(blob, C, N, n_tiles_total, (uint64_t)n_isects, n_pix, false);
+    RasterBuffers rb{};
+    rc = raster_front(s, rb, means, quats, scales, colors, opacities, N, C, image_width, image_height, viewmats0, Ks,
+                      tile_offsets, flatten_ids, n_isects, false, stream);
+    if (rc)
+        return rc;
+    return launch_blend_fwd(rb, C, image_width, image_height, tile_w, tile_h, false, backgrounds, masks, renders, alphas,
+                            last_ids, stream);
+}
+
+extern "C" int lfs_rasterize_to_pixels_from_world_3dgs_bwd(
+    const float* means, const float* quats, const float* scales, const float* colors, const float* opacities,
+    const float* backgrounds, const uint8_t* masks, uint32_t N, uint32_t C, uint32_t image_width,
+    uint32_t image_height, uint32_t tile_size, const float* viewmats0, const float* viewmats1, const float* Ks,
+    int camera_model, const lfs_ut_params* ut_params, int rs_type, const float* radial_coeffs,
+    const float* tangential_coeffs, const float* thin_prism_coeffs, const int32_t* tile_offsets,
+    const int32_t* flatten_ids, int64_t n_isects, const float* render_alphas, const int32_t* last_ids,
+    const float* v_render_colors, const float* v_render_alphas, lfs_alloc_fn alloc, void* alloc_ctx, float* v_means,
+    float* v_quats, float* v_scales, float* v_colors, float* v_opacities, void* stream_) {
+    using namespace lfs;
+    (void)ut_params;
+    // The forward is recomputed here with per-bucket checkpoints (the gsplat signature carries none), so the
+    // caller's render_alphas / last_ids are validated but not consumed: the recomputation reproduces them.
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LFS_CHECK_ARG(means && quats && scales && colors && opacities && viewmats0 && Ks && tile_offsets &&
+                      render_alphas && last_ids && v_render_colors && v_render_alphas && alloc && v_means && v_quats &&
+                      v_scales && v_colors && v_opacities,
+                  "rasterize_bwd: null required pointer");
+    int rc = check_common(tile_size, camera_model, rs_type, viewmats1, radial_coeffs, tangential_coeffs,
+                          thin_prism_coeffs, "rasterize_bwd");
+    if (rc)
+        return rc;
+    LFS_CUDA_OK(cudaMemsetAsync(v_means, 0, sizeof(float) * 3 * (size_t)N, stream));
+    LFS_CUDA_OK(cudaMemsetAsync(v_quats, 0, sizeof(float) * 4 * (size_t)N, stream));
+    LFS_CUDA_OK(cudaMemsetAsync(v_scales, 0, sizeof(float) * 3 * (size_t)N, stream));
+    LFS_CUDA_OK(cudaMemsetAsync(v_colors, 0, sizeof(float) * 3 * (size_t)C * N, stream));
+    LFS_CUDA_OK(cudaMemsetAsync(v_opacities, 0, sizeof(float) * (size_t)C * N, stream));
+    if (C == 0 || N == 0 || n_isects <= 0 || image_width == 0 || image_height == 0)
+        return LFS_OK; // reference: kernel launch skipped when n_isects == 0 (…Bwd.cu:434-437)
+    LFS_CHECK_ARG(flatten_ids && n_isects < (1ll << 31), "rasterize_bwd: bad flatten_ids / n_isects");
+    const uint32_t tile_w = (image_width + kTile - 1) / kTile, tile_h = (image_height + kTile - 1) / kTile;
+    const uint32_t n_tiles_total = C * tile_w * tile_h;
+    const uint64_t n_pix = (uint64_t)C * image_width * image_height;
+    RasterScratch sz = carve_scratch(nullptr, C, N, n_tiles_total, (uint64_t)n_isects, n_pix, true);
+    void* blob = alloc(alloc_ctx, LFS_TAG_SCRATCH, sz.bytes);
+    if (!blob) {
+        set_error("rasterize_bwd: scratch allocation of %zu bytes failed", sz.bytes);
+        return LFS_ERR_ALLOC;
+    }
+    RasterScratch s = carve_scratch(blob, C, N, n_tiles_total, (uint64_t)n_isects, n_pix, true);
+    RasterBuffers rb{};
+    rc = raster_front(s, rb, means, quats, scales, colors, opacities, N, C, image_width, image_height, viewmats0, Ks,
+                      tile_offsets, flatten_ids, n_isects, true, stream);
+    if (rc)
+        return rc;
+    rc = launch_blend_fwd(rb, C, image_width, image_height, tile_w, tile_h, true, nullptr, masks, nullptr, nullptr,
+                          nullptr, stream);
+    if (rc)
+        return rc;
+    k_pack_vpix<<<div_up(n_pix, 256), 256, 0, stream>>>(v_render_colors, v_render_alphas, s.pix_state, backgrounds,
+                                                        image_width * image_height, (uint32_t)n_pix, s.v_pix);
+    LFS_LAUNCH_OK("k_pack_vpix");
+    const uint32_t n_bucket_cap = (uint32_t)((uint64_t)n_isects / kBucket + n_tiles_total + 1);
+    return launch_blend_bwd(rb, s.cams, s.v_pix, quats, scales, means, C, N, image_width, image_height, tile_w, tile_h,
+                            n_bucket_cap, s.n_buckets, v_means, v_quats, v_scales, v_colors, v_opacities, stream);
+}

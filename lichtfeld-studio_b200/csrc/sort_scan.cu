@@ -1,0 +1,299 @@
+// lfs_b200 -- device-wide exclusive scan + stable LSD radix sort (see sort_scan.cuh).
+#include "sort_scan.cuh"
+
+namespace lfs {
+
+__device__ __forceinline__ uint32_t resolve_n(uint32_t n_cap, const uint32_t* n_dev) {
+    if (n_dev) {
+        const uint32_t n = *n_dev;
+        return n < n_cap ? n : n_cap;
+    }
+    return n_cap;
+}
+
+// inclusive scan of one value per thread across a block of `blockDim.x` (<= 1024) threads.
+// s_warp must hold 33 uint32.  Returns inclusive prefix; *block_total gets the block sum.
+__device__ __forceinline__ uint32_t block_inclusive_scan(uint32_t v, uint32_t* s_warp, uint32_t* block_total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_warps = (blockDim.x + 31) >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o)
+            x += y;
+    }
+    if (lane == 31)
+        s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = (lane < n_warps) ? s_warp[lane] : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o)
+                w += y;
+        }
+        s_warp[lane] = w; // inclusive over warps
+        if (lane == 31)
+            s_warp[32] = w;
+    }
+    __syncthreads();
+    const uint32_t warp_off = (warp == 0) ? 0u : s_warp[warp - 1];
+    *block_total = s_warp[32];
+    const uint32_t r = x + warp_off;
+    __syncthreads(); // s_warp may be reused by the caller
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------- scan
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ uint32_t scan_fetch(const uint32_t* in, const uint32_t* gather, uint32_t i) {
+    return gather ? __ldg(in + __ldg(gather + i)) : __ldg(in + i);
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+    k_scan_block_sums(const uint32_t* __restrict__ in, const uint32_t* __restrict__ gather, uint32_t n_cap,
+                      const uint32_t* __restrict__ n_dev, uint32_t* __restrict__ sums) {
+    __shared__ uint32_t s_warp[33];
+    const uint32_t n = resolve_n(n_cap, n_dev);
+    const uint32_t base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k)
+        if (base + k < n)
+            s += scan_fetch(in, gather, base + k);
+    uint32_t total;
+    block_inclusive_scan(s, s_warp, &total);
+    if (threadIdx.x == 0)
+        sums[blockIdx.x] = total;
+}
+
+// single CTA: exclusive scan of the block sums in place, writes the grand total
+__global__ void __launch_bounds__(1024)
+    k_scan_sums(uint32_t* __restrict__ sums, uint32_t n_cap, const uint32_t* __restrict__ n_dev,
+                uint32_t* __restrict__ total_out) {
+    __shared__ uint32_t s_warp[33];
+    const uint32_t n = resolve_n(n_cap, n_dev);
+    const uint32_t nblk = (n + kScanTile - 1) / kScanTile;
+    uint32_t carry = 0;
+    for (uint32_t start = 0; start < nblk; start += blockDim.x) {
+        const uint32_t i = start + threadIdx.x;
+        const uint32_t v = (i < nblk) ? sums[i] : 0u;
+        uint32_t total;
+        const uint32_t incl = block_inclusive_scan(v, s_warp, &total);
+        if (i < nblk)
+            sums[i] = carry + incl - v;
+        carry += total;
+    }
+    if (threadIdx.x == 0 && total_out)
+        *total_out = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+    k_scan_apply(const uint32_t* __restrict__ in, const uint32_t* __restrict__ gather, uint32_t* __restrict__ out,
+                 const uint32_t* __restrict__ sums, uint32_t n_cap, const uint32_t* __restrict__ n_dev) {
+    __shared__ uint32_t s_warp[33];
+    const uint32_t n = resolve_n(n_cap, n_dev);
+    const uint32_t base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    uint32_t v[kScanItems];
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        v[k] = (base + k < n) ? scan_fetch(in, gather, base + k) : 0u;
+        s += v[k];
+    }
+    uint32_t total;
+    const uint32_t incl = block_inclusive_scan(s, s_warp, &total);
+    uint32_t run = sums[blockIdx.x] + incl - s;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        if (base + k < n)
+            out[base + k] = run;
+        run += v[k];
+    }
+}
+
+int exclusive_scan_u32(const uint32_t* in, const uint32_t* gather, uint32_t* out, uint32_t* total_out,
+                       uint32_t n_cap, const uint32_t* n_dev, void* scratch, cudaStream_t stream) {
+    uint32_t* sums = static_cast<uint32_t*>(scratch);
+    const unsigned nblk = div_up(n_cap, kScanTile);
+    if (n_cap == 0) {
+        if (total_out)
+            LFS_CUDA_OK(cudaMemsetAsync(total_out, 0, sizeof(uint32_t), stream));
+        return LFS_OK;
+    }
+    k_scan_block_sums<<<nblk, kScanThreads, 0, stream>>>(in, gather, n_cap, n_dev, sums);
+    LFS_LAUNCH_OK("k_scan_block_sums");
+    k_scan_sums<<<1, 1024, 0, stream>>>(sums, n_cap, n_dev, total_out);
+    LFS_LAUNCH_OK("k_scan_sums");
+    k_scan_apply<<<nblk, kScanThreads, 0, stream>>>(in, gather, out, sums, n_cap, n_dev);
+    LFS_LAUNCH_OK("k_scan_apply");
+    return LFS_OK;
+}
+
+// ------------------------------------------------------------------------------------------- radix sort
+__global__ void __launch_bounds__(kRsThreads)
+    k_rs_hist(const uint32_t* __restrict__ keys, uint32_t n_cap, const uint32_t* __restrict__ n_dev, int shift,
+              int ndig, uint32_t nblk, uint32_t* __restrict__ table) {
+    extern __shared__ uint32_t sh[];
+    const uint32_t n = resolve_n(n_cap, n_dev);
+    for (int d = threadIdx.x; d < ndig; d += kRsThreads)
+        sh[d] = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * kRsTile;
+    if (base < n) {
+        const int lane = threadIdx.x & 31;
+#pragma unroll 4
+        for (int r = 0; r < kRsItems; ++r) {
+            const uint32_t i = base + r * kRsThreads + threadIdx.x;
+            const bool valid = i < n;
+            const uint32_t d = valid ? ((__ldg(keys + i) >> shift) & (uint32_t)(ndig - 1)) : (uint32_t)ndig;
+            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            if (valid && (__ffs(peers) - 1) == lane)
+                atomicAdd(&sh[d], (uint32_t)__popc(peers));
+        }
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < ndig; d += kRsThreads)
+        table[(size_t)d * nblk + blockIdx.x] = sh[d];
+}
+
+// grid = ndig CTAs: exclusive scan of row d over the blocks, totals[d] = row sum
+__global__ void __launch_bounds__(256)
+    k_rs_scan_rows(uint32_t* __restrict__ table, uint32_t nblk, uint32_t* __restrict__ totals) {
+    __shared__ uint32_t s_warp[33];
+    uint32_t* row = table + (size_t)blockIdx.x * nblk;
+    uint32_t carry = 0;
+    for (uint32_t start = 0; start < nblk; start += blockDim.x) {
+        const uint32_t i = start + threadIdx.x;
+        const uint32_t v = (i < nblk) ? row[i] : 0u;
+        uint32_t total;
+        const uint32_t incl = block_inclusive_scan(v, s_warp, &total);
+        if (i < nblk)
+            row[i] = carry + incl - v;
+        carry += total;
+    }
+    if (threadIdx.x == 0)
+        totals[blockIdx.x] = carry;
+}
+
+// one CTA of 1024 threads: base[d] = exclusive scan of totals (ndig <= 2048)
+__global__ void __launch_bounds__(1024)
+    k_rs_scan_totals(const uint32_t* __restrict__ totals, uint32_t* __restrict__ base, int ndig) {
+    __shared__ uint32_t s_warp[33];
+    const int d0 = 2 * threadIdx.x, d1 = d0 + 1;
+    const uint32_t a = d0 < ndig ? totals[d0] : 0u;
+    const uint32_t b = d1 < ndig ? totals[d1] : 0u;
+    uint32_t total;
+    const uint32_t incl = block_inclusive_scan(a + b, s_warp, &total);
+    const uint32_t excl = incl - (a + b);
+    if (d0 < ndig)
+        base[d0] = excl;
+    if (d1 < ndig)
+        base[d1] = excl + a;
+}
+
+__global__ void __launch_bounds__(kRsThreads)
+    k_rs_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                 uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n_cap,
+                 const uint32_t* __restrict__ n_dev, int shift, int ndig, uint32_t nblk,
+                 const uint32_t* __restrict__ table, const uint32_t* __restrict__ base) {
+    extern __shared__ uint32_t sh[];
+    constexpr int kWarps = kRsThreads / 32;
+    uint32_t* whist = sh;                 // [kWarps][ndig]
+    uint32_t* sbase = sh + kWarps * ndig; // [ndig]
+    const uint32_t n = resolve_n(n_cap, n_dev);
+    const uint32_t blk_base = blockIdx.x * kRsTile;
+    if (blk_base >= n)
+        return;
+    for (int d = threadIdx.x; d < kWarps * ndig; d += kRsThreads)
+        whist[d] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t wbase = blk_base + warp * (kRsItems * 32);
+    uint32_t* wh = whist + warp * ndig;
+    uint32_t key[kRsItems], val[kRsItems], lrank[kRsItems];
+#pragma unroll
+    for (int r = 0; r < kRsItems; ++r) {
+        const uint32_t i = wbase + r * 32 + lane;
+        const bool valid = i < n;
+        key[r] = valid ? __ldg(keys_in + i) : 0u;
+        val[r] = valid ? __ldg(vals_in + i) : 0u;
+        const uint32_t d = valid ? ((key[r] >> shift) & (uint32_t)(ndig - 1)) : (uint32_t)ndig;
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t rank = __popc(peers & lt_mask);
+        const uint32_t before = valid ? wh[d] : 0u;
+        __syncwarp();
+        if (valid && rank == 0)
+            wh[d] = before + (uint32_t)__popc(peers);
+        __syncwarp();
+        lrank[r] = before + rank;
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < ndig; d += kRsThreads) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            const uint32_t t = whist[w * ndig + d];
+            whist[w * ndig + d] = run;
+            run += t;
+        }
+        sbase[d] = base[d] + table[(size_t)d * nblk + blockIdx.x];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kRsItems; ++r) {
+        const uint32_t i = wbase + r * 32 + lane;
+        if (i < n) {
+            const uint32_t d = (key[r] >> shift) & (uint32_t)(ndig - 1);
+            const uint32_t pos = sbase[d] + wh[d] + lrank[r];
+            keys_out[pos] = key[r];
+            vals_out[pos] = val[r];
+        }
+    }
+}
+
+int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t n_cap,
+                     const uint32_t* n_dev, int begin_bit, int n_bits, void* scratch, int* result_in_b,
+                     cudaStream_t stream) {
+    *result_in_b = 0;
+    if (n_cap == 0 || n_bits <= 0)
+        return LFS_OK;
+    // per-device attribute; cheap enough to set on every call (one process may drive several devices)
+    LFS_CUDA_OK(cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(sizeof(uint32_t) * (kRsThreads / 32 + 1) * (1 << kRsMaxBits))));
+    const RadixPlan plan = make_radix_plan(begin_bit, n_bits);
+    const uint32_t nblk = div_up(n_cap, kRsTile);
+    uint32_t* table = static_cast<uint32_t*>(scratch);
+    uint32_t* totals = table + (size_t)(1 << kRsMaxBits) * (nblk + 1);
+    uint32_t* base = totals + (1 << kRsMaxBits);
+    uint32_t *kin = keys_a, *vin = vals_a, *kout = keys_b, *vout = vals_b;
+    for (int p = 0; p < plan.n_pass; ++p) {
+        const int ndig = 1 << plan.bits[p];
+        k_rs_hist<<<nblk, kRsThreads, sizeof(uint32_t) * ndig, stream>>>(kin, n_cap, n_dev, plan.shift[p], ndig, nblk,
+                                                                         table);
+        LFS_LAUNCH_OK("k_rs_hist");
+        k_rs_scan_rows<<<ndig, 256, 0, stream>>>(table, nblk, totals);
+        LFS_LAUNCH_OK("k_rs_scan_rows");
+        k_rs_scan_totals<<<1, 1024, 0, stream>>>(totals, base, ndig);
+        LFS_LAUNCH_OK("k_rs_scan_totals");
+        k_rs_scatter<<<nblk, kRsThreads, sizeof(uint32_t) * (kRsThreads / 32 + 1) * ndig, stream>>>(
+            kin, vin, kout, vout, n_cap, n_dev, plan.shift[p], ndig, nblk, table, base);
+        LFS_LAUNCH_OK("k_rs_scatter");
+        uint32_t* t = kin;
+        kin = kout;
+        kout = t;
+        t = vin;
+        vin = vout;
+        vout = t;
+    }
+    *result_in_b = (plan.n_pass & 1);
+    return LFS_OK;
+}
+
+} // namespace lfs

@@ -1,0 +1,614 @@
+// lfs_b200 -- fused training step (one view): raw parameters -> image -> loss gradient -> raw-parameter
+// gradients, with no host synchronisation and no intermediate torch ops.  It plays the role of the
+// reference's gs::training::rasterize + autograd glue (src/training/rasterization/rasterizer.cpp:46-437,
+// rasterizer_autograd.cpp:12-392) for the 3DGUT path, with the activations of SplatData
+// (src/core/splat_data.cpp:267-286: sigmoid / exp / normalize / cat) and the SH evaluation fused into the
+// per-Gaussian kernels, as the reference's fastgs preprocess does for its EWA path
+// (fastgs/rasterization/include/kernels_forward.cuh:18-205).
+//
+// Parameter / gradient / Adam-state arenas are PLANAR (SoA): plane p holds N_pad floats, planes in the
+// reference's parameter-group order (strategies/strategy_utils.cpp:35-40):
+//   means x,y,z | sh0 r,g,b | shN (k=1..K-1) x (r,g,b) | scaling x,y,z | rotation w,x,y,z | opacity
+// so that one thread per Gaussian reads/writes every plane fully coalesced and the fused Adam / the NCCL
+// all-reduce see one flat fp32 buffer of (11 + 3K) * N_pad floats (59 N at SH degree 3).
+#include "intersect.cuh"
+#include "projection.cuh"
+#include "raster.cuh"
+#include "sh.cuh"
+#include "sort_scan.cuh"
+
+#include <new>
+
+namespace lfs {
+
+struct Planes {
+    uint32_t Np, K;
+    __host__ __device__ uint32_t mean(int c) const { return (uint32_t)c; }
+    __host__ __device__ uint32_t sh(int k, int ch) const { return k == 0 ? 3u + ch : 6u + (k - 1) * 3u + ch; }
+    __host__ __device__ uint32_t scaling(int c) const { return 6u + 3u * (K - 1) + c; }
+    __host__ __device__ uint32_t rotation(int c) const { return 9u + 3u * (K - 1) + c; }
+    __host__ __device__ uint32_t opacity() const { return 13u + 3u * (K - 1); }
+    __host__ __device__ uint32_t count() const { return 11u + 3u * K; }
+};
+
+struct Trainer {
+    lfs_trainer_desc d;
+    Planes pl;
+    uint32_t tile_w, tile_h, n_tiles;
+    uint32_t inst_cap, bucket_cap;
+    // device buffers (one cudaMalloc'd blob)
+    char* blob = nullptr;
+    size_t blob_bytes = 0;
+    ViewCam* cam_dev;
+    GaussRec* gauss;
+    TileRect* rects;
+    int32_t* counts;
+    uint32_t *dk_a, *dk_b, *pm_a, *pm_b, *off;
+    uint32_t* n_inst; // [4] device counters: n_inst, n_buckets, overflow flag
+    uint32_t *tk_a, *tk_b, *tv_a, *tv_b;
+    int32_t* tile_off;
+    uint32_t *bucket_off, *bucket_counts, *bucket_tile, *tile_max;
+    InstRec* inst;
+    float4* ckpt;
+    float4* pix_state;
+    int32_t* n_contrib;
+    float4* v_pix;
+    float *v_means, *v_quats, *v_scales, *v_colors, *v_opac;
+    float *act_means, *act_quats, *act_scales; // activated AoS copies for the blend-backward epilogue
+    float* loss_partials;
+    void *scan_scr, *sort_scr;
+    const uint32_t* sorted_keys = nullptr;
+    const uint32_t* sorted_vals = nullptr;
+    ViewCam cam_host;
+    float bg[3];
+    uint32_t active_degree = 0;
+    uint32_t* stats_host = nullptr; // pinned: n_inst, n_buckets
+};
+
+static size_t trainer_carve(Trainer& t, void* base) {
+    Carver c(base);
+    const uint32_t N = t.d.n_gaussians;
+    const uint64_t npix = (uint64_t)t.d.width * t.d.height;
+    t.cam_dev = c.take<ViewCam>(1);
+    t.gauss = c.take<GaussRec>(N);
+    t.rects = c.take<TileRect>(N);
+    t.counts = c.take<int32_t>(N);
+    t.dk_a = c.take<uint32_t>(N), t.dk_b = c.take<uint32_t>(N);
+    t.pm_a = c.take<uint32_t>(N), t.pm_b = c.take<uint32_t>(N);
+    t.off = c.take<uint32_t>(N);
+    t.n_inst = c.take<uint32_t>(4);
+    t.tk_a = c.take<uint32_t>(t.inst_cap), t.tk_b = c.take<uint32_t>(t.inst_cap);
+    t.tv_a = c.take<uint32_t>(t.inst_cap), t.tv_b = c.take<uint32_t>(t.inst_cap);
+    t.tile_off = c.take<int32_t>(t.n_tiles + 1);
+    t.bucket_off = c.take<uint32_t>(t.n_tiles + 1);
+    t.bucket_counts = c.take<uint32_t>(t.n_tiles + 1);
+    t.bucket_tile = c.take<uint32_t>(t.bucket_cap);
+    t.tile_max = c.take<uint32_t>(t.n_tiles);
+    t.inst = c.take<InstRec>(t.inst_cap);
+    t.ckpt = c.take<float4>((size_t)t.bucket_cap * kTilePix);
+    t.pix_state = c.take<float4>(npix);
+    t.n_contrib = c.take<int32_t>(npix);
+    t.v_pix = c.take<float4>(npix);
+    t.v_means = c.take<float>(3 * (size_t)N);
+    t.v_quats = c.take<float>(4 * (size_t)N);
+    t.v_scales = c.take<float>(3 * (size_t)N);
+    t.v_colors = c.take<float>(3 * (size_t)N);
+    t.v_opac = c.take<float>(N);
+    t.act_means = c.take<float>(3 * (size_t)N);
+    t.act_quats = c.take<float>(4 * (size_t)N);
+    t.act_scales = c.take<float>(3 * (size_t)N);
+    t.loss_partials = c.take<float>(t.n_tiles + 1);
+    t.scan_scr = c.take<char>(scan_scratch_bytes(N > t.n_tiles + 1 ? N : t.n_tiles + 1));
+    t.sort_scr = c.take<char>(radix_scratch_bytes(N > t.inst_cap ? N : t.inst_cap));
+    return c.total();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// AoS (reference SplatData layout) <-> planar arena
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    k_pack_arena(const float* __restrict__ means, const float* __restrict__ sh0, const float* __restrict__ shN,
+                 const float* __restrict__ scaling, const float* __restrict__ rotation,
+                 const float* __restrict__ opacity, const uint32_t N, const Planes pl, float* __restrict__ arena,
+                 const int to_arena) {
+    const uint32_t g = blockIdx.x * 256 + threadIdx.x;
+    if (g >= N)
+        return;
+    const size_t Np = pl.Np;
+#define MOVE(aos_ptr, aos_index, plane)                                   \
+    do {                                                                  \
+        float* a_ = const_cast<float*>(aos_ptr) + (aos_index);            \
+        float* p_ = arena + (size_t)(plane) * Np + g;                     \
+        if (to_arena)                                                     \
+            *p_ = *a_;                                                    \
+        else                                                              \
+            *a_ = *p_;                                                    \
+    } while (0)
+    for (int c = 0; c < 3; ++c)
+        MOVE(means, 3 * (size_t)g + c, pl.mean(c));
+    for (int c = 0; c < 3; ++c)
+        MOVE(sh0, 3 * (size_t)g + c, pl.sh(0, c));
+    for (uint32_t k = 1; k < pl.K; ++k)
+        for (int c = 0; c < 3; ++c)
+            MOVE(shN, ((size_t)g * (pl.K - 1) + (k - 1)) * 3 + c, pl.sh((int)k, c));
+    for (int c = 0; c < 3; ++c)
+        MOVE(scaling, 3 * (size_t)g + c, pl.scaling(c));
+    for (int c = 0; c < 4; ++c)
+        MOVE(rotation, 4 * (size_t)g + c, pl.rotation(c));
+    MOVE(opacity, (size_t)g, pl.opacity());
+#undef MOVE
+}
+
+// ------------------------------------------------------------------------------------------------------
+// per-Gaussian forward: activations + UT projection + SH colour + GaussRec + tile rectangle + depth key
+// ------------------------------------------------------------------------------------------------------
+struct PreCfg {
+    float eps2d, near_plane, far_plane, radius_clip;
+    lfs_ut_params ut;
+    int degree;
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+__global__ void __launch_bounds__(256)
+    k_preprocess_fwd(const float* __restrict__ arena, const Planes pl, const uint32_t N, const ViewCam cam,
+                     const PreCfg cfg, GaussRec* __restrict__ gauss, TileRect* __restrict__ rects,
+                     int32_t* __restrict__ counts, uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ ident,
+                     float* __restrict__ act_means, float* __restrict__ act_quats, float* __restrict__ act_scales) {
+    const uint32_t g = blockIdx.x * 256 + threadIdx.x;
+    if (g >= N)
+        return;
+    const size_t Np = pl.Np;
+    auto P = [&](uint32_t plane) { return __ldg(arena + (size_t)plane * Np + g); };
+    const f3 mean = mk3(P(pl.mean(0)), P(pl.mean(1)), P(pl.mean(2)));
+    const f3 scale = mk3(__expf(P(pl.scaling(0))), __expf(P(pl.scaling(1))), __expf(P(pl.scaling(2))));
+    float qw = P(pl.rotation(0)), qx = P(pl.rotation(1)), qy = P(pl.rotation(2)), qz = P(pl.rotation(3));
+    { // torch::nn::functional::normalize (eps 1e-12), splat_data.cpp:279
+        const float nrm = fmaxf(sqrtf(qw * qw + qx * qx + qy * qy + qz * qz), 1e-12f);
+        const float inv = 1.0f / nrm;
+        qw *= inv, qx *= inv, qy *= inv, qz *= inv;
+    }
+    const float op = sigmoidf_(P(pl.opacity()));
+
+    const UTOut o = ut_project_pinhole(cam, mean, make_float4(qw, qx, qy, qz), scale, true, op, cfg.eps2d,
+                                       cfg.near_plane, cfg.far_plane, cfg.radius_clip, cfg.ut);
+    ident[g] = g;
+    if (!o.ok) {
+        counts[g] = 0;
+        rects[g] = TileRect{0, 0, 0, 0};
+        depth_keys[g] = 0xFFFFFFFFu;
+        return;
+    }
+    uint32_t x0, y0, x1, y1;
+    tile_rect(o.mx, o.my, o.rx, o.ry, (float)kTile, (uint32_t)cam.tile_w, (uint32_t)cam.tile_h, x0, y0, x1, y1);
+    const int32_t cnt = (int32_t)((y1 - y0) * (x1 - x0));
+    counts[g] = cnt;
+    rects[g] = TileRect{(unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1};
+    depth_keys[g] = cnt > 0 ? __float_as_uint(o.depth) : 0xFFFFFFFFu;
+    if (cnt <= 0)
+        return;
+
+    // view-dependent colour: clamp_min(SH(dir) + 0.5, 0)   (rasterizer.cpp:250-266)
+    const f3 dir = mk3(mean.x - cam.org[0], mean.y - cam.org[1], mean.z - cam.org[2]);
+    f3 col = sh_to_color(cfg.degree, dir, [&](int k) { return mk3(P(pl.sh(k, 0)), P(pl.sh(k, 1)), P(pl.sh(k, 2))); });
+    col = mk3(fmaxf(col.x + 0.5f, 0.f), fmaxf(col.y + 0.5f, 0.f), fmaxf(col.z + 0.5f, 0.f));
+
+    // GaussRec (same algebra as k_prep_gaussians)
+    float w = qw, x = qx, y = qy, z = qz;
+    const float inv_norm = rsqrtf(x * x + y * y + z * z + w * w);
+    x *= inv_norm, y *= inv_norm, z *= inv_norm, w *= inv_norm;
+    const float x2 = x * x, y2 = y * y, z2 = z * z, xy = x * y, xz = x * z, yz = y * z, wx = w * x, wy = w * y,
+                wz = w * z;
+    const f3 m0 = mk3(1.f - 2.f * (y2 + z2), 2.f * (xy + wz), 2.f * (xz - wy)) * (1.0f / scale.x);
+    const f3 m1 = mk3(2.f * (xy - wz), 1.f - 2.f * (x2 + z2), 2.f * (yz + wx)) * (1.0f / scale.y);
+    const f3 m2 = mk3(2.f * (xz + wy), 2.f * (yz - wx), 1.f - 2.f * (x2 + y2)) * (1.0f / scale.z);
+    const f3 r0 = mk3(cam.R[0], cam.R[1], cam.R[2]), r1 = mk3(cam.R[3], cam.R[4], cam.R[5]),
+             r2 = mk3(cam.R[6], cam.R[7], cam.R[8]);
+    const float ifx = 1.0f / cam.fx, ify = 1.0f / cam.fy;
+    const f3 omu = mk3(cam.org[0] - mean.x, cam.org[1] - mean.y, cam.org[2] - mean.z);
+    const f3 vx = mk3(dot(m0, r0), dot(m1, r0), dot(m2, r0)) * ifx;
+    const f3 vy = mk3(dot(m0, r1), dot(m1, r1), dot(m2, r1)) * ify;
+    const f3 w2 = mk3(dot(m0, r2), dot(m1, r2), dot(m2, r2));
+    const f3 gro = mk3(dot(m0, omu), dot(m1, omu), dot(m2, omu));
+    float4* og = reinterpret_cast<float4*>(gauss + g);
+    og[0] = make_float4(vx.x, vx.y, vx.z, vy.x);
+    og[1] = make_float4(vy.y, vy.z, w2.x, w2.y);
+    og[2] = make_float4(w2.z, gro.x, gro.y, gro.z);
+    og[3] = make_float4(op, col.x, col.y, col.z);
+    // activated copies consumed by the blend-backward epilogue (quat / scale chain rule)
+    act_means[3 * (size_t)g] = mean.x, act_means[3 * (size_t)g + 1] = mean.y, act_means[3 * (size_t)g + 2] = mean.z;
+    reinterpret_cast<float4*>(act_quats)[g] = make_float4(qw, qx, qy, qz);
+    act_scales[3 * (size_t)g] = scale.x, act_scales[3 * (size_t)g + 1] = scale.y, act_scales[3 * (size_t)g + 2] = scale.z;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// per-Gaussian backward: colour clamp mask -> SH VJP -> activation VJPs -> += raw-parameter gradients;
+// clears the per-view activated-space accumulators for the next view.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    k_preprocess_bwd(const float* __restrict__ arena, float* __restrict__ grads, const Planes pl, const uint32_t N,
+                     const ViewCam cam, const int degree, const int32_t* __restrict__ counts,
+                     float* __restrict__ v_means, float* __restrict__ v_quats, float* __restrict__ v_scales,
+                     float* __restrict__ v_colors, float* __restrict__ v_opac) {
+    const uint32_t g = blockIdx.x * 256 + threadIdx.x;
+    if (g >= N || counts[g] <= 0)
+        return;
+    const size_t Np = pl.Np;
+    auto P = [&](uint32_t plane) { return __ldg(arena + (size_t)plane * Np + g); };
+    auto ACC = [&](uint32_t plane, float v) { grads[(size_t)plane * Np + g] += v; };
+
+    f3 vm = mk3(v_means[3 * (size_t)g], v_means[3 * (size_t)g + 1], v_means[3 * (size_t)g + 2]);
+    const float4 vq = reinterpret_cast<float4*>(v_quats)[g];
+    const f3 vs = mk3(v_scales[3 * (size_t)g], v_scales[3 * (size_t)g + 1], v_scales[3 * (size_t)g + 2]);
+    f3 vc = mk3(v_colors[3 * (size_t)g], v_colors[3 * (size_t)g + 1], v_colors[3 * (size_t)g + 2]);
+    const float vo = v_opac[g];
+    v_means[3 * (size_t)g] = v_means[3 * (size_t)g + 1] = v_means[3 * (size_t)g + 2] = 0.f;
+    reinterpret_cast<float4*>(v_quats)[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    v_scales[3 * (size_t)g] = v_scales[3 * (size_t)g + 1] = v_scales[3 * (size_t)g + 2] = 0.f;
+    v_colors[3 * (size_t)g] = v_colors[3 * (size_t)g + 1] = v_colors[3 * (size_t)g + 2] = 0.f;
+    v_opac[g] = 0.f;
+
+    const f3 mean = mk3(P(pl.mean(0)), P(pl.mean(1)), P(pl.mean(2)));
+    const f3 dir = mk3(mean.x - cam.org[0], mean.y - cam.org[1], mean.z - cam.org[2]);
+    auto coef = [&](int k) { return mk3(P(pl.sh(k, 0)), P(pl.sh(k, 1)), P(pl.sh(k, 2))); };
+    // clamp_min(c + 0.5, 0) passes the gradient where c + 0.5 >= 0
+    const f3 col = sh_to_color(degree, dir, coef);
+    if (col.x + 0.5f < 0.f)
+        vc.x = 0.f;
+    if (col.y + 0.5f < 0.f)
+        vc.y = 0.f;
+    if (col.z + 0.5f < 0.f)
+        vc.z = 0.f;
+    const f3 vdir = sh_vjp(degree, dir, vc, true, coef, [&](int k, f3 gk) {
+        ACC(pl.sh(k, 0), gk.x);
+        ACC(pl.sh(k, 1), gk.y);
+        ACC(pl.sh(k, 2), gk.z);
+    });
+    vm = vm + vdir;
+    ACC(pl.mean(0), vm.x);
+    ACC(pl.mean(1), vm.y);
+    ACC(pl.mean(2), vm.z);
+    // scale = exp(raw)
+    ACC(pl.scaling(0), vs.x * __expf(P(pl.scaling(0))));
+    ACC(pl.scaling(1), vs.y * __expf(P(pl.scaling(1))));
+    ACC(pl.scaling(2), vs.z * __expf(P(pl.scaling(2))));
+    // opacity = sigmoid(raw)
+    const float op = sigmoidf_(P(pl.opacity()));
+    ACC(pl.opacity(), vo * op * (1.0f - op));
+    // q_n = q / max(|q|, eps)
+    const float qw = P(pl.rotation(0)), qx = P(pl.rotation(1)), qy = P(pl.rotation(2)), qz = P(pl.rotation(3));
+    const float nrm = fmaxf(sqrtf(qw * qw + qx * qx + qy * qy + qz * qz), 1e-12f);
+    const float inv = 1.0f / nrm;
+    const float nw = qw * inv, nx = qx * inv, ny = qy * inv, nz = qz * inv;
+    const float dq = vq.x * nw + vq.y * nx + vq.z * ny + vq.w * nz;
+    ACC(pl.rotation(0), (vq.x - dq * nw) * inv);
+    ACC(pl.rotation(1), (vq.y - dq * nx) * inv);
+    ACC(pl.rotation(2), (vq.z - dq * ny) * inv);
+    ACC(pl.rotation(3), (vq.w - dq * nz) * inv);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// L1 photometric loss on (rgb + T * bg) and its gradient packed for the backward
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    k_loss_l1(const float4* __restrict__ pix_state, const void* __restrict__ target, const int fmt,
+              const uint32_t width, const uint32_t height, const float bg_r, const float bg_g, const float bg_b,
+              const float scale, float4* __restrict__ v_pix, float* __restrict__ partials) {
+    __shared__ float s_sum[8];
+    const uint32_t npix = width * height;
+    float acc = 0.f;
+    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < npix; i += gridDim.x * 256) {
+        const float4 s = pix_state[i];
+        float tr, tg, tb;
+        if (fmt == LFS_IMG_U8_HWC) {
+            const uint8_t* t = static_cast<const uint8_t*>(target) + 3 * (size_t)i;
+            tr = t[0] * (1.0f / 255.0f), tg = t[1] * (1.0f / 255.0f), tb = t[2] * (1.0f / 255.0f);
+        } else if (fmt == LFS_IMG_F32_HWC) {
+            const float* t = static_cast<const float*>(target) + 3 * (size_t)i;
+            tr = t[0], tg = t[1], tb = t[2];
+        } else { // F32 CHW
+            const float* t = static_cast<const float*>(target);
+            tr = t[i], tg = t[npix + i], tb = t[2 * (size_t)npix + i];
+        }
+        const float dr = fmaf(s.w, bg_r, s.x) - tr, dg = fmaf(s.w, bg_g, s.y) - tg, db = fmaf(s.w, bg_b, s.z) - tb;
+        acc += fabsf(dr) + fabsf(dg) + fabsf(db);
+        const float vr = (dr > 0.f ? scale : (dr < 0.f ? -scale : 0.f));
+        const float vg = (dg > 0.f ? scale : (dg < 0.f ? -scale : 0.f));
+        const float vb = (db > 0.f ? scale : (db < 0.f ? -scale : 0.f));
+        v_pix[i] = make_float4(vr, vg, vb, -s.w * (bg_r * vr + bg_g * vg + bg_b * vb));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0)
+        s_sum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w)
+            t += s_sum[w];
+        partials[blockIdx.x] = t * scale;
+    }
+}
+__global__ void k_loss_finish(const float* __restrict__ partials, const int n, float* __restrict__ loss_accum) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < n; ++i)
+            t += partials[i];
+        *loss_accum += t;
+    }
+}
+
+// external upstream gradients (parity tests / custom losses): v_image [H,W,3], v_alpha [H,W] or null
+__global__ void __launch_bounds__(256)
+    k_pack_vpix_ext(const float* __restrict__ v_image, const float* __restrict__ v_alpha,
+                    const float4* __restrict__ pix_state, const float bg_r, const float bg_g, const float bg_b,
+                    const uint32_t npix, float4* __restrict__ v_pix) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= npix)
+        return;
+    const float r = v_image[3 * (size_t)i], g = v_image[3 * (size_t)i + 1], b = v_image[3 * (size_t)i + 2];
+    const float va = (v_alpha ? v_alpha[i] : 0.f) - (bg_r * r + bg_g * g + bg_b * b);
+    v_pix[i] = make_float4(r, g, b, pix_state[i].w * va);
+}
+
+__global__ void __launch_bounds__(256)
+    k_export_image(const float4* __restrict__ pix_state, const float bg_r, const float bg_g, const float bg_b,
+                   const uint32_t npix, float* __restrict__ image, float* __restrict__ alpha) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= npix)
+        return;
+    const float4 s = pix_state[i];
+    if (image) {
+        image[3 * (size_t)i] = fmaf(s.w, bg_r, s.x);
+        image[3 * (size_t)i + 1] = fmaf(s.w, bg_g, s.y);
+        image[3 * (size_t)i + 2] = fmaf(s.w, bg_b, s.z);
+    }
+    if (alpha)
+        alpha[i] = 1.0f - s.w;
+}
+
+} // namespace lfs
+
+// ==========================================================================================================
+using namespace lfs;
+
+extern "C" uint64_t lfs_trainer_arena_floats(const lfs_trainer_desc* d) {
+    if (!d)
+        return 0;
+    const uint32_t K = (d->sh_degree_max + 1) * (d->sh_degree_max + 1);
+    const uint64_t Np = ((uint64_t)d->n_gaussians + 3) / 4 * 4;
+    return (11ull + 3ull * K) * Np;
+}
+
+extern "C" void* lfs_trainer_create(const lfs_trainer_desc* d) {
+    if (!d || d->n_gaussians == 0 || d->width == 0 || d->height == 0 || d->sh_degree_max > 4) {
+        set_error("trainer_create: bad descriptor");
+        return nullptr;
+    }
+    Trainer* t = new (std::nothrow) Trainer();
+    if (!t)
+        return nullptr;
+    t->d = *d;
+    t->pl.Np = (d->n_gaussians + 3) / 4 * 4;
+    t->pl.K = (d->sh_degree_max + 1) * (d->sh_degree_max + 1);
+    t->tile_w = (d->width + kTile - 1) / kTile;
+    t->tile_h = (d->height + kTile - 1) / kTile;
+    t->n_tiles = t->tile_w * t->tile_h;
+    if (t->tile_w >= 65536 || t->tile_h >= 65536) {
+        set_error("trainer_create: image too large");
+        delete t;
+        return nullptr;
+    }
+    uint64_t cap = d->instance_capacity ? d->instance_capacity : (uint64_t)d->n_gaussians * 8 + 65536;
+    if (cap >= (1ull << 31))
+        cap = (1ull << 31) - 1;
+    t->inst_cap = (uint32_t)cap;
+    t->bucket_cap = t->inst_cap / kBucket + t->n_tiles + 1;
+    t->blob_bytes = trainer_carve(*t, nullptr);
+    if (cudaMalloc(&t->blob, t->blob_bytes) != cudaSuccess) {
+        set_error("trainer_create: cudaMalloc(%zu bytes) failed", t->blob_bytes);
+        delete t;
+        return nullptr;
+    }
+    trainer_carve(*t, t->blob);
+    cudaMemset(t->v_means, 0, sizeof(float) * 3 * (size_t)d->n_gaussians);
+    cudaMemset(t->v_quats, 0, sizeof(float) * 4 * (size_t)d->n_gaussians);
+    cudaMemset(t->v_scales, 0, sizeof(float) * 3 * (size_t)d->n_gaussians);
+    cudaMemset(t->v_colors, 0, sizeof(float) * 3 * (size_t)d->n_gaussians);
+    cudaMemset(t->v_opac, 0, sizeof(float) * (size_t)d->n_gaussians);
+    cudaMemset(t->n_inst, 0, sizeof(uint32_t) * 4);
+    if (cudaMallocHost(&t->stats_host, sizeof(uint32_t) * 4) != cudaSuccess)
+        t->stats_host = nullptr;
+    return t;
+}
+
+extern "C" void lfs_trainer_destroy(void* h) {
+    Trainer* t = static_cast<Trainer*>(h);
+    if (!t)
+        return;
+    if (t->blob)
+        cudaFree(t->blob);
+    if (t->stats_host)
+        cudaFreeHost(t->stats_host);
+    delete t;
+}
+
+extern "C" uint64_t lfs_trainer_scratch_bytes(void* h) { return h ? static_cast<Trainer*>(h)->blob_bytes : 0; }
+extern "C" uint64_t lfs_trainer_instance_capacity(void* h) { return h ? static_cast<Trainer*>(h)->inst_cap : 0; }
+
+static int pack_common(void* h, float* means, float* sh0, float* shN, float* scaling, float* rotation, float* opacity,
+                       float* arena, int to_arena, void* stream) {
+    Trainer* t = static_cast<Trainer*>(h);
+    LFS_CHECK_ARG(t && means && sh0 && scaling && rotation && opacity && arena, "trainer_pack: null pointer");
+    LFS_CHECK_ARG(t->pl.K == 1 || shN, "trainer_pack: shN is null");
+    k_pack_arena<<<div_up(t->d.n_gaussians, 256), 256, 0, (cudaStream_t)stream>>>(
+        means, sh0, shN, scaling, rotation, opacity, t->d.n_gaussians, t->pl, arena, to_arena);
+    LFS_LAUNCH_OK("k_pack_arena");
+    return LFS_OK;
+}
+extern "C" int lfs_trainer_pack(void* h, const float* means, const float* sh0, const float* shN, const float* scaling,
+                                const float* rotation, const float* opacity, float* arena, void* stream) {
+    return pack_common(h, const_cast<float*>(means), const_cast<float*>(sh0), const_cast<float*>(shN),
+                       const_cast<float*>(scaling), const_cast<float*>(rotation), const_cast<float*>(opacity), arena, 1,
+                       stream);
+}
+extern "C" int lfs_trainer_unpack(void* h, const float* arena, float* means, float* sh0, float* shN, float* scaling,
+                                  float* rotation, float* opacity, void* stream) {
+    return pack_common(h, means, sh0, shN, scaling, rotation, opacity, const_cast<float*>(arena), 0, stream);
+}
+
+extern "C" int lfs_trainer_view_forward(void* h, const float* params_arena, const float* viewmat_host,
+                                        const float* K_host, uint32_t active_sh_degree, const float* bg_host,
+                                        float* image_out, float* alpha_out, void* stream_) {
+    Trainer* t = static_cast<Trainer*>(h);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LFS_CHECK_ARG(t && params_arena && viewmat_host && K_host, "trainer_view_forward: null pointer");
+    LFS_CHECK_ARG(active_sh_degree <= t->d.sh_degree_max, "trainer_view_forward: active degree %u > max %u",
+                  active_sh_degree, t->d.sh_degree_max);
+    const uint32_t N = t->d.n_gaussians;
+    t->cam_host = make_viewcam(viewmat_host, K_host, (int)t->d.width, (int)t->d.height);
+    t->active_degree = active_sh_degree;
+    for (int k = 0; k < 3; ++k)
+        t->bg[k] = bg_host ? bg_host[k] : 0.f;
+    LFS_CUDA_OK(cudaMemcpyAsync(t->cam_dev, &t->cam_host, sizeof(ViewCam), cudaMemcpyHostToDevice, stream));
+
+    PreCfg cfg{t->d.eps2d, t->d.near_plane, t->d.far_plane, t->d.radius_clip, t->d.ut, (int)active_sh_degree};
+    k_preprocess_fwd<<<div_up(N, 256), 256, 0, stream>>>(params_arena, t->pl, N, t->cam_host, cfg, t->gauss, t->rects,
+                                                         t->counts, t->dk_a, t->pm_a, t->act_means, t->act_quats,
+                                                         t->act_scales);
+    LFS_LAUNCH_OK("k_preprocess_fwd");
+    int in_b = 0;
+    int rc = radix_sort_pairs(t->dk_a, t->pm_a, t->dk_b, t->pm_b, N, nullptr, 0, 32, t->sort_scr, &in_b, stream);
+    if (rc)
+        return rc;
+    const uint32_t* perm = in_b ? t->pm_b : t->pm_a;
+    rc = exclusive_scan_u32(reinterpret_cast<const uint32_t*>(t->counts), perm, t->off, t->n_inst, N, nullptr,
+                            t->scan_scr, stream);
+    if (rc)
+        return rc;
+    rc = launch_emit_instances(perm, t->off, N, t->rects, t->tile_w, 0, t->inst_cap, t->n_inst, t->tk_a, t->tv_a,
+                               stream);
+    if (rc)
+        return rc;
+    rc = radix_sort_pairs(t->tk_a, t->tv_a, t->tk_b, t->tv_b, t->inst_cap, t->n_inst, 0, tile_key_bits(t->n_tiles),
+                          t->sort_scr, &in_b, stream);
+    if (rc)
+        return rc;
+    t->sorted_keys = in_b ? t->tk_b : t->tk_a;
+    t->sorted_vals = in_b ? t->tv_b : t->tv_a;
+    rc = launch_tile_offsets(t->sorted_keys, t->inst_cap, t->n_inst, t->n_tiles, t->tile_off, stream);
+    if (rc)
+        return rc;
+
+    RasterBuffers rb{};
+    rb.gauss = t->gauss;
+    rb.tile_off = t->tile_off;
+    rb.inst_gid = reinterpret_cast<const int32_t*>(t->sorted_vals);
+    rb.inst = t->inst;
+    rb.bucket_off = t->bucket_off;
+    rb.bucket_tile = t->bucket_tile;
+    rb.ckpt = t->ckpt;
+    rb.tile_max_contrib = t->tile_max;
+    rb.pix_state = t->pix_state;
+    rb.n_contrib = t->n_contrib;
+    rc = launch_bucket_offsets(rb, t->n_tiles, t->n_inst + 1, t->scan_scr, t->bucket_counts, stream);
+    if (rc)
+        return rc;
+    rc = launch_expand_instances(rb, t->cam_dev, t->n_tiles, t->tile_w, t->inst_cap, t->n_inst, t->sorted_keys, 1, N,
+                                 stream);
+    if (rc)
+        return rc;
+    rc = launch_blend_fwd(rb, 1, t->d.width, t->d.height, t->tile_w, t->tile_h, true, nullptr, nullptr, nullptr,
+                          nullptr, nullptr, stream);
+    if (rc)
+        return rc;
+    if (image_out || alpha_out) {
+        const uint32_t npix = t->d.width * t->d.height;
+        k_export_image<<<div_up(npix, 256), 256, 0, stream>>>(t->pix_state, t->bg[0], t->bg[1], t->bg[2], npix,
+                                                              image_out, alpha_out);
+        LFS_LAUNCH_OK("k_export_image");
+    }
+    if (t->stats_host)
+        LFS_CUDA_OK(cudaMemcpyAsync(t->stats_host, t->n_inst, sizeof(uint32_t) * 2, cudaMemcpyDeviceToHost, stream));
+    return LFS_OK;
+}
+
+extern "C" int lfs_trainer_view_loss_l1(void* h, const void* target, int target_format, float scale,
+                                        float* loss_accum, void* stream_) {
+    Trainer* t = static_cast<Trainer*>(h);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LFS_CHECK_ARG(t && target, "trainer_view_loss_l1: null pointer");
+    LFS_CHECK_ARG(target_format >= 0 && target_format <= 2, "trainer_view_loss_l1: bad target format");
+    const unsigned grid = t->n_tiles < (unsigned)(kNumSMs * 8) ? t->n_tiles : (unsigned)(kNumSMs * 8);
+    k_loss_l1<<<grid, 256, 0, stream>>>(t->pix_state, target, target_format, t->d.width, t->d.height, t->bg[0], t->bg[1],
+                                        t->bg[2], scale, t->v_pix, t->loss_partials);
+    LFS_LAUNCH_OK("k_loss_l1");
+    if (loss_accum) {
+        k_loss_finish<<<1, 32, 0, stream>>>(t->loss_partials, (int)grid, loss_accum);
+        LFS_LAUNCH_OK("k_loss_finish");
+    }
+    return LFS_OK;
+}
+
+extern "C" int lfs_trainer_view_set_grad(void* h, const float* v_image, const float* v_alpha, void* stream_) {
+    Trainer* t = static_cast<Trainer*>(h);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LFS_CHECK_ARG(t && v_image, "trainer_view_set_grad: null pointer");
+    const uint32_t npix = t->d.width * t->d.height;
+    k_pack_vpix_ext<<<div_up(npix, 256), 256, 0, stream>>>(v_image, v_alpha, t->pix_state, t->bg[0], t->bg[1], t->bg[2],
+                                                           npix, t->v_pix);
+    LFS_LAUNCH_OK("k_pack_vpix_ext");
+    return LFS_OK;
+}
+
+extern "C" int lfs_trainer_view_backward(void* h, const float* params_arena, float* grads_arena, void* stream_) {
+    Trainer* t = static_cast<Trainer*>(h);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LFS_CHECK_ARG(t && params_arena && grads_arena, "trainer_view_backward: null pointer");
+    LFS_CHECK_ARG(t->sorted_vals != nullptr, "trainer_view_backward: no forward has been run");
+    const uint32_t N = t->d.n_gaussians;
+    RasterBuffers rb{};
+    rb.gauss = t->gauss;
+    rb.tile_off = t->tile_off;
+    rb.inst_gid = reinterpret_cast<const int32_t*>(t->sorted_vals);
+    rb.inst = t->inst;
+    rb.bucket_off = t->bucket_off;
+    rb.bucket_tile = t->bucket_tile;
+    rb.ckpt = t->ckpt;
+    rb.tile_max_contrib = t->tile_max;
+    rb.pix_state = t->pix_state;
+    rb.n_contrib = t->n_contrib;
+    int rc = launch_blend_bwd(rb, t->cam_dev, t->v_pix, t->act_quats, t->act_scales, t->act_means, 1, N, t->d.width,
+                              t->d.height, t->tile_w, t->tile_h, t->bucket_cap, t->n_inst + 1, t->v_means, t->v_quats,
+                              t->v_scales, t->v_colors, t->v_opac, stream);
+    if (rc)
+        return rc;
+    k_preprocess_bwd<<<div_up(N, 256), 256, 0, stream>>>(params_arena, grads_arena, t->pl, N, t->cam_host,
+                                                         (int)t->active_degree, t->counts, t->v_means, t->v_quats,
+                                                         t->v_scales, t->v_colors, t->v_opac);
+    LFS_LAUNCH_OK("k_preprocess_bwd");
+    return LFS_OK;
+}
+
+extern "C" int lfs_trainer_stats(void* h, uint64_t* n_instances, uint64_t* n_buckets, void* stream_) {
+    Trainer* t = static_cast<Trainer*>(h);
+    LFS_CHECK_ARG(t, "trainer_stats: null handle");
+    LFS_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream_));
+    uint32_t v[2] = {0, 0};
+    if (t->stats_host) {
+        v[0] = t->stats_host[0], v[1] = t->stats_host[1];
+    } else {
+        LFS_CUDA_OK(cudaMemcpy(v, t->n_inst, sizeof(v), cudaMemcpyDeviceToHost));
+    }
+    if (n_instances)
+        *n_instances = v[0];
+    if (n_buckets)
+        *n_buckets = v[1];
+    if (v[0] > t->inst_cap) {
+        set_error("trainer: %u instances exceed the capacity %u; recreate the trainer with a larger "
+                  "instance_capacity", v[0], t->inst_cap);
+        return LFS_ERR_CAPACITY;
+    }
+    return LFS_OK;
+}

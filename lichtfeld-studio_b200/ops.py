@@ -1,0 +1,237 @@
+"""Host-side mirror of the reference's gsplat operator surface (gsplat/Ops.h:12-166) over torch tensors.
+
+Same function names, argument meaning and error behaviour as the reference ops (inputs must be CUDA +
+contiguous, else ValueError like the reference's CHECK_INPUT -> c10::Error, gsplat/Common.h:12-17); every
+function forwards to the C ABI in include/lfs_b200.h.  torch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ALLOC_FN, PINHOLE, SHUTTER_GLOBAL, UTParams, check, load
+
+
+def _chk(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    return t
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _Alloc:
+    """lfs_alloc_fn backed by torch's caching allocator; keeps buffers alive until released."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs = {}
+        self.keep = []
+        self.cb = ALLOC_FN(self._alloc)
+
+    def _alloc(self, _ctx, tag, nbytes):
+        try:
+            t = torch.empty(max(int(nbytes), 1) + 256, dtype=torch.uint8, device=self.device)
+            off = (-t.data_ptr()) % 256
+            self.keep.append(t)
+            self.bufs[int(tag)] = (t, off, int(nbytes))
+            return t.data_ptr() + off
+        except Exception:  # out of memory -> NULL -> LFS_ERR_ALLOC
+            return None
+
+    def tensor(self, tag: int, dtype: torch.dtype, numel: int) -> torch.Tensor:
+        t, off, nbytes = self.bufs[tag]
+        return t[off:off + nbytes].view(dtype)[:numel]
+
+
+def projection_ut_3dgs_fused(means, quats, scales, opacities, viewmats0, viewmats1, Ks, image_width, image_height,
+                             eps2d, near_plane, far_plane, radius_clip, calc_compensations, camera_model=PINHOLE,
+                             ut_params: Optional[UTParams] = None, rs_type=SHUTTER_GLOBAL, radial_coeffs=None,
+                             tangential_coeffs=None, thin_prism_coeffs=None):
+    """gsplat::projection_ut_3dgs_fused (gsplat/Ops.h:69-98) -> (radii, means2d, depths, conics, compensations)."""
+    lib = load()
+    _chk(means, "means"), _chk(quats, "quats"), _chk(scales, "scales"), _chk(viewmats0, "viewmats0"), _chk(Ks, "Ks")
+    if opacities is not None:
+        _chk(opacities, "opacities")
+    N, Cc = means.shape[0], Ks.shape[0]
+    dev = means.device
+    radii = torch.empty((Cc, N, 2), dtype=torch.int32, device=dev)
+    means2d = torch.empty((Cc, N, 2), dtype=torch.float32, device=dev)
+    depths = torch.empty((Cc, N), dtype=torch.float32, device=dev)
+    conics = torch.empty((Cc, N, 3), dtype=torch.float32, device=dev)
+    comp = torch.zeros((Cc, N), dtype=torch.float32, device=dev) if calc_compensations else None
+    ut = ut_params or UTParams.default()
+    check(lib.lfs_projection_ut_3dgs_fused(
+        _p(means), _p(quats), _p(scales), _p(opacities), _p(viewmats0), _p(viewmats1), _p(Ks), N, Cc, image_width,
+        image_height, eps2d, near_plane, far_plane, radius_clip, camera_model, C.byref(ut), rs_type,
+        _p(radial_coeffs), _p(tangential_coeffs), _p(thin_prism_coeffs), _p(radii), _p(means2d), _p(depths),
+        _p(conics), _p(comp), _stream()))
+    return radii, means2d, depths, conics, comp
+
+
+def spherical_harmonics_fwd(degrees_to_use: int, dirs, coeffs, masks=None):
+    """gsplat::spherical_harmonics_fwd (gsplat/Ops.h:12-17). dirs [...,3], coeffs [...,K,3] -> colors [...,3]."""
+    lib = load()
+    _chk(dirs, "dirs"), _chk(coeffs, "coeffs")
+    if coeffs.shape[-1] != 3 or dirs.shape[-1] != 3:
+        raise ValueError("coeffs / dirs must have last dimension 3")
+    m8 = None
+    if masks is not None:
+        _chk(masks, "masks", torch.bool)
+        m8 = masks.view(torch.uint8)
+    n, K = dirs.numel() // 3, coeffs.shape[-2]
+    colors = torch.empty_like(dirs)
+    check(lib.lfs_spherical_harmonics_fwd(degrees_to_use, _p(dirs), _p(coeffs), _p(m8), n, K, _p(colors), _stream()))
+    return colors
+
+
+def spherical_harmonics_bwd(K: int, degrees_to_use: int, dirs, coeffs, masks, v_colors, compute_v_dirs: bool):
+    """gsplat::spherical_harmonics_bwd (gsplat/Ops.h:18-25) -> (v_coeffs, v_dirs or None)."""
+    lib = load()
+    _chk(dirs, "dirs"), _chk(coeffs, "coeffs"), _chk(v_colors, "v_colors")
+    m8 = None
+    if masks is not None:
+        _chk(masks, "masks", torch.bool)
+        m8 = masks.view(torch.uint8)
+    n = dirs.numel() // 3
+    v_coeffs = torch.empty_like(coeffs)
+    v_dirs = torch.empty_like(dirs) if compute_v_dirs else None
+    check(lib.lfs_spherical_harmonics_bwd(K, degrees_to_use, _p(dirs), _p(coeffs), _p(m8), _p(v_colors), n,
+                                          _p(v_coeffs), _p(v_dirs), _stream()))
+    return v_coeffs, v_dirs
+
+
+def intersect_tile(means2d, radii, depths, camera_ids, gaussian_ids, C_: int, tile_size: int, tile_width: int,
+                   tile_height: int, sort: bool = True):
+    """gsplat::intersect_tile (gsplat/Ops.h:28-38) -> (tiles_per_gauss, isect_ids, flatten_ids)."""
+    lib = load()
+    _chk(means2d, "means2d"), _chk(radii, "radii", torch.int32), _chk(depths, "depths")
+    if means2d.dim() == 2 or camera_ids is not None or gaussian_ids is not None:
+        raise _lib.LfsUnsupported(_lib.LFS_ERR_UNSUPPORTED, "intersect_tile: packed layout is not implemented")
+    N = means2d.shape[1]
+    dev = means2d.device
+    tiles_per_gauss = torch.empty(depths.shape, dtype=torch.int32, device=dev)
+    al = _Alloc(dev)
+    ids_p, flat_p, n_is = C.c_void_p(), C.c_void_p(), C.c_int64(0)
+    check(lib.lfs_intersect_tile(_p(means2d), _p(radii), _p(depths), C_, N, tile_size, tile_width, tile_height,
+                                 1 if sort else 0, _p(tiles_per_gauss), al.cb, None, C.byref(ids_p), C.byref(flat_p),
+                                 C.byref(n_is), _stream()))
+    n = int(n_is.value)
+    if n == 0:
+        return (tiles_per_gauss, torch.empty((0,), dtype=torch.int64, device=dev),
+                torch.empty((0,), dtype=torch.int32, device=dev))
+    isect_ids = al.tensor(_lib_tag("ISECT"), torch.int64, n)
+    flatten_ids = al.tensor(_lib_tag("FLAT"), torch.int32, n)
+    torch.cuda.current_stream().synchronize()  # scratch (tag 0) is dropped when `al` dies
+    return tiles_per_gauss, isect_ids, flatten_ids
+
+
+def _lib_tag(name: str) -> int:
+    return {"SCRATCH": 0, "ISECT": 1, "FLAT": 2}[name]
+
+
+def intersect_offset(isect_ids, C_: int, tile_width: int, tile_height: int):
+    """gsplat::intersect_offset (gsplat/Ops.h:39-43) -> offsets [C, tile_height, tile_width] int32."""
+    lib = load()
+    _chk(isect_ids, "isect_ids", torch.int64)
+    offsets = torch.empty((C_, tile_height, tile_width), dtype=torch.int32, device=isect_ids.device)
+    check(lib.lfs_intersect_offset(_p(isect_ids), isect_ids.numel(), C_, tile_width, tile_height, _p(offsets),
+                                   _stream()))
+    return offsets
+
+
+def rasterize_to_pixels_from_world_3dgs_fwd(means, quats, scales, colors, opacities, backgrounds, masks,
+                                            image_width, image_height, tile_size, viewmats0, viewmats1, Ks,
+                                            camera_model=PINHOLE, ut_params: Optional[UTParams] = None,
+                                            rs_type=SHUTTER_GLOBAL, radial_coeffs=None, tangential_coeffs=None,
+                                            thin_prism_coeffs=None, tile_offsets=None, flatten_ids=None):
+    """gsplat::rasterize_to_pixels_from_world_3dgs_fwd (gsplat/Ops.h:100-129) -> (renders, alphas, last_ids)."""
+    lib = load()
+    for t, nme in ((means, "means"), (quats, "quats"), (scales, "scales"), (colors, "colors"),
+                   (opacities, "opacities"), (viewmats0, "viewmats0"), (Ks, "Ks")):
+        _chk(t, nme)
+    _chk(tile_offsets, "tile_offsets", torch.int32), _chk(flatten_ids, "flatten_ids", torch.int32)
+    if backgrounds is not None:
+        _chk(backgrounds, "backgrounds")
+    m8 = None
+    if masks is not None:
+        _chk(masks, "masks", torch.bool)
+        m8 = masks.view(torch.uint8)
+    Cc, N, ch = tile_offsets.shape[0], means.shape[0], colors.shape[-1]
+    dev = means.device
+    renders = torch.empty((Cc, image_height, image_width, ch), dtype=torch.float32, device=dev)
+    alphas = torch.empty((Cc, image_height, image_width, 1), dtype=torch.float32, device=dev)
+    last_ids = torch.empty((Cc, image_height, image_width), dtype=torch.int32, device=dev)
+    ut = ut_params or UTParams.default()
+    al = _Alloc(dev)
+    check(lib.lfs_rasterize_to_pixels_from_world_3dgs_fwd(
+        _p(means), _p(quats), _p(scales), _p(colors), _p(opacities), _p(backgrounds), _p(m8), N, Cc, ch, image_width,
+        image_height, tile_size, _p(viewmats0), _p(viewmats1), _p(Ks), camera_model, C.byref(ut), rs_type,
+        _p(radial_coeffs), _p(tangential_coeffs), _p(thin_prism_coeffs), _p(tile_offsets), _p(flatten_ids),
+        flatten_ids.numel(), al.cb, None, _p(renders), _p(alphas), _p(last_ids), _stream()))
+    torch.cuda.current_stream().synchronize()
+    return renders, alphas, last_ids
+
+
+def rasterize_to_pixels_from_world_3dgs_bwd(means, quats, scales, colors, opacities, backgrounds, masks,
+                                            image_width, image_height, tile_size, viewmats0, viewmats1, Ks,
+                                            camera_model=PINHOLE, ut_params: Optional[UTParams] = None,
+                                            rs_type=SHUTTER_GLOBAL, radial_coeffs=None, tangential_coeffs=None,
+                                            thin_prism_coeffs=None, tile_offsets=None, flatten_ids=None,
+                                            render_alphas=None, last_ids=None, v_render_colors=None,
+                                            v_render_alphas=None):
+    """gsplat::rasterize_to_pixels_from_world_3dgs_bwd (gsplat/Ops.h:131-166)
+    -> (v_means, v_quats, v_scales, v_colors, v_opacities)."""
+    lib = load()
+    for t, nme in ((means, "means"), (quats, "quats"), (scales, "scales"), (colors, "colors"),
+                   (opacities, "opacities"), (viewmats0, "viewmats0"), (Ks, "Ks"), (render_alphas, "render_alphas"),
+                   (v_render_colors, "v_render_colors"), (v_render_alphas, "v_render_alphas")):
+        _chk(t, nme)
+    _chk(tile_offsets, "tile_offsets", torch.int32), _chk(flatten_ids, "flatten_ids", torch.int32)
+    _chk(last_ids, "last_ids", torch.int32)
+    if backgrounds is not None:
+        _chk(backgrounds, "backgrounds")
+    m8 = None
+    if masks is not None:
+        _chk(masks, "masks", torch.bool)
+        m8 = masks.view(torch.uint8)
+    Cc, N = tile_offsets.shape[0], means.shape[0]
+    dev = means.device
+    v_means = torch.empty_like(means)
+    v_quats = torch.empty_like(quats)
+    v_scales = torch.empty_like(scales)
+    v_colors = torch.empty_like(colors)
+    v_opacities = torch.empty_like(opacities)
+    ut = ut_params or UTParams.default()
+    al = _Alloc(dev)
+    check(lib.lfs_rasterize_to_pixels_from_world_3dgs_bwd(
+        _p(means), _p(quats), _p(scales), _p(colors), _p(opacities), _p(backgrounds), _p(m8), N, Cc, image_width,
+        image_height, tile_size, _p(viewmats0), _p(viewmats1), _p(Ks), camera_model, C.byref(ut), rs_type,
+        _p(radial_coeffs), _p(tangential_coeffs), _p(thin_prism_coeffs), _p(tile_offsets), _p(flatten_ids),
+        flatten_ids.numel(), _p(render_alphas), _p(last_ids), _p(v_render_colors), _p(v_render_alphas), al.cb, None,
+        _p(v_means), _p(v_quats), _p(v_scales), _p(v_colors), _p(v_opacities), _stream()))
+    torch.cuda.current_stream().synchronize()
+    return v_means, v_quats, v_scales, v_colors, v_opacities
+
+
+def adam_step(param, exp_avg, exp_avg_sq, param_grad, lr, beta1, beta2, eps, bias_correction1_rcp,
+              bias_correction2_sqrt_rcp):
+    """fast_gs::optimizer::adam_step_wrapper (fastgs/optimizer/include/adam_api.h:11-21); in place."""
+    lib = load()
+    for t, nme in ((param, "param"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq"), (param_grad, "param_grad")):
+        _chk(t, nme)
+    check(lib.lfs_adam_step(_p(param), _p(exp_avg), _p(exp_avg_sq), _p(param_grad), param.numel(), lr, beta1, beta2,
+                            eps, bias_correction1_rcp, bias_correction2_sqrt_rcp, _stream()))

@@ -1,0 +1,203 @@
+"""Training step of the B200-native rasterizer: view-sharded data parallel + fused Adam.
+
+Mirrors the reference's hot loop (src/training/trainer.cpp:579-757: render -> photometric loss -> backward ->
+strategy step -> FusedAdam::step, src/training/optimizers/fused_adam.cpp:22-95) for the steady state (no
+densification), generalised from the reference's batch of ONE view on ONE GPU to a batch of B views:
+gradients of the views are summed, then one Adam step is taken.  With world_size > 1 the views of a step are
+partitioned round-robin over the ranks (one process per GPU), the flat planar gradient arena is summed with a
+single NCCL all-reduce over NVLink, and every rank applies the identical Adam update (parameters stay
+replicated; no broadcast).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import IMG_U8_HWC, TrainerDesc, UTParams, check, load
+
+GROUPS = ("means", "sh0", "shN", "scaling", "rotation", "opacity")  # strategies/strategy_utils.cpp:35-40
+
+
+def default_lrs(scene_scale: float = 1.0) -> dict:
+    """eval/default_optimization_params.json (eval/, not parameter/)."""
+    return {"means": 0.00016 * scene_scale, "sh0": 0.0025, "shN": 0.0025 / 20.0, "scaling": 0.005,
+            "rotation": 0.001, "opacity": 0.05}
+
+
+class SplatTrainer:
+    def __init__(self, n_gaussians: int, width: int, height: int, sh_degree_max: int = 3, device="cuda:0",
+                 instance_capacity: int = 0, lrs: Optional[dict] = None, betas=(0.9, 0.999), eps: float = 1e-15,
+                 iterations: int = 30000, eps2d=0.3, near_plane=0.01, far_plane=1e4, radius_clip=0.0):
+        self.lib = load()
+        self.device = torch.device(device)
+        self.N, self.W, self.H, self.deg_max = n_gaussians, width, height, sh_degree_max
+        self.K = (sh_degree_max + 1) ** 2
+        self.Np = (n_gaussians + 3) // 4 * 4
+        self.desc = TrainerDesc(n_gaussians, sh_degree_max, width, height, eps2d, near_plane, far_plane, radius_clip,
+                                UTParams.default(), instance_capacity)
+        with torch.cuda.device(self.device):
+            self.h = self.lib.lfs_trainer_create(C.byref(self.desc))
+        if not self.h:
+            raise _lib.LfsError(-4, self.lib.lfs_last_error().decode())
+        n_floats = int(self.lib.lfs_trainer_arena_floats(C.byref(self.desc)))
+        assert n_floats == (11 + 3 * self.K) * self.Np
+        mk = lambda: torch.zeros(n_floats, dtype=torch.float32, device=self.device)
+        self.params, self.grads, self.exp_avg, self.exp_avg_sq = mk(), mk(), mk(), mk()
+        self.loss_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
+        # planar segment table in the reference's group order
+        planes = [3, 3, 3 * (self.K - 1), 3, 4, 1]
+        self.seg_begin = [0]
+        for p in planes:
+            self.seg_begin.append(self.seg_begin[-1] + p * self.Np)
+        self.lrs = dict(lrs or default_lrs())
+        self.betas, self.eps = betas, eps
+        self.step_count = [0] * 6
+        self.iteration = 0
+        self.means_gamma = math.pow(0.01, 1.0 / iterations)  # strategy_utils.cpp:47-55 (means group only)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self._tgt = [torch.empty((height, width, 3), dtype=torch.uint8, device=self.device) for _ in range(2)]
+        self._tgt_ready = [torch.cuda.Event() for _ in range(2)]
+        self._tgt_free = [torch.cuda.Event() for _ in range(2)]
+        self._loss_pinned = torch.zeros(1, dtype=torch.float32).pin_memory()
+
+    def __del__(self):
+        h, self.h = getattr(self, "h", None), None
+        if h:
+            self.lib.lfs_trainer_destroy(h)
+
+    # ---- parameters ------------------------------------------------------------------------------------
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def load_params(self, means, sh0, shN, scaling, rotation, opacity) -> None:
+        """AoS tensors in the reference's SplatData layout (include/core/splat_data.hpp:104-109)."""
+        ts = [torch.as_tensor(t, dtype=torch.float32).to(self.device).contiguous()
+              for t in (means, sh0, shN, scaling, rotation, opacity)]
+        if self.K == 1:
+            ts[2] = torch.zeros(1, device=self.device)
+        check(self.lib.lfs_trainer_pack(self.h, *[t.data_ptr() for t in ts], self.params.data_ptr(), self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def load_scene(self, scene) -> None:
+        self.load_params(scene.means, scene.sh0, scene.shN, scene.scaling, scene.rotation, scene.opacity)
+
+    def _unpack(self, arena: torch.Tensor) -> dict:
+        N, K, dev = self.N, self.K, self.device
+        out = {"means": torch.empty((N, 3), device=dev), "sh0": torch.empty((N, 1, 3), device=dev),
+               "shN": torch.empty((N, max(K - 1, 1), 3), device=dev), "scaling": torch.empty((N, 3), device=dev),
+               "rotation": torch.empty((N, 4), device=dev), "opacity": torch.empty((N, 1), device=dev)}
+        check(self.lib.lfs_trainer_unpack(self.h, arena.data_ptr(), *[out[k].data_ptr() for k in GROUPS],
+                                          self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()
+        if K == 1:
+            out["shN"] = out["shN"][:, :0]
+        return out
+
+    def export_params(self) -> dict:
+        return self._unpack(self.params)
+
+    def export_grads(self) -> dict:
+        return self._unpack(self.grads)
+
+    # ---- one view ----------------------------------------------------------------------------------------
+    def forward(self, viewmat: np.ndarray, K: np.ndarray, active_sh_degree: Optional[int] = None,
+                bg: Sequence[float] = (0.0, 0.0, 0.0), want_image: bool = False):
+        vm = np.ascontiguousarray(viewmat, dtype=np.float32).reshape(16)
+        kk = np.ascontiguousarray(K, dtype=np.float32).reshape(9)
+        bgc = (C.c_float * 3)(*[float(b) for b in bg])
+        deg = self.deg_max if active_sh_degree is None else active_sh_degree
+        image = alpha = None
+        if want_image:
+            image = torch.empty((self.H, self.W, 3), dtype=torch.float32, device=self.device)
+            alpha = torch.empty((self.H, self.W), dtype=torch.float32, device=self.device)
+        check(self.lib.lfs_trainer_view_forward(
+            self.h, self.params.data_ptr(), vm.ctypes.data_as(C.POINTER(C.c_float)),
+            kk.ctypes.data_as(C.POINTER(C.c_float)), deg, bgc, image.data_ptr() if want_image else None,
+            alpha.data_ptr() if want_image else None, self._stream()))
+        return image, alpha
+
+    def loss_l1(self, target: torch.Tensor, scale: Optional[float] = None, fmt: int = IMG_U8_HWC) -> None:
+        s = 1.0 / (3.0 * self.W * self.H) if scale is None else scale
+        check(self.lib.lfs_trainer_view_loss_l1(self.h, target.data_ptr(), fmt, s, self.loss_dev.data_ptr(),
+                                                self._stream()))
+
+    def set_grad(self, v_image: torch.Tensor, v_alpha: Optional[torch.Tensor] = None) -> None:
+        check(self.lib.lfs_trainer_view_set_grad(self.h, v_image.data_ptr(),
+                                                 None if v_alpha is None else v_alpha.data_ptr(), self._stream()))
+
+    def backward(self) -> None:
+        check(self.lib.lfs_trainer_view_backward(self.h, self.params.data_ptr(), self.grads.data_ptr(),
+                                                 self._stream()))
+
+    def stats(self):
+        n_inst, n_b = C.c_uint64(0), C.c_uint64(0)
+        check(self.lib.lfs_trainer_stats(self.h, C.byref(n_inst), C.byref(n_b), self._stream()))
+        return int(n_inst.value), int(n_b.value)
+
+    # ---- optimiser (FusedAdam::step mirror) -----------------------------------------------------------------
+    def adam_step(self) -> None:
+        self.iteration += 1
+        b1, b2 = self.betas
+        groups = []
+        for gi, name in enumerate(GROUPS):
+            self.step_count[gi] += 1
+            if name == "shN" and (self.iteration <= 1000 or self.K == 1):
+                continue  # fused_adam.cpp:68-70 (the counter is still incremented)
+            t = self.step_count[gi]
+            groups.append((gi, self.lrs[name], 1.0 / (1.0 - b1 ** t), 1.0 / math.sqrt(1.0 - b2 ** t)))
+        # consecutive groups share one launch
+        runs, cur = [], []
+        for g in groups:
+            if cur and g[0] != cur[-1][0] + 1:
+                runs.append(cur)
+                cur = []
+            cur.append(g)
+        if cur:
+            runs.append(cur)
+        for run in runs:
+            n = len(run)
+            seg = (C.c_int64 * (n + 1))(*([self.seg_begin[g[0]] for g in run] + [self.seg_begin[run[-1][0] + 1]]))
+            lr = (C.c_float * n)(*[g[1] for g in run])
+            bc1 = (C.c_float * n)(*[g[2] for g in run])
+            bc2 = (C.c_float * n)(*[g[3] for g in run])
+            check(self.lib.lfs_adam_step_multi(self.params.data_ptr(), self.exp_avg.data_ptr(),
+                                               self.exp_avg_sq.data_ptr(), self.grads.data_ptr(), n, seg, lr, bc1, bc2,
+                                               b1, b2, self.eps, 1, self._stream()))
+        if len(runs) != 1 or len(runs[0]) != 6:
+            self.grads.zero_()  # skipped segments still need their gradients cleared
+        self.lrs["means"] *= self.means_gamma  # ExponentialLR on group 0 only
+
+    # ---- full step: B views -> one Adam update --------------------------------------------------------------
+    def train_step(self, viewmats: np.ndarray, Ks: np.ndarray, targets_pinned: Sequence[torch.Tensor],
+                   bg=(0.0, 0.0, 0.0), active_sh_degree: Optional[int] = None, world_size: int = 1, rank: int = 0,
+                   read_loss: bool = True):
+        """targets_pinned: pinned host uint8 [H,W,3] tensors, one per view of the GLOBAL batch; this rank renders
+        views rank, rank + world_size, ...  Host->device copies run on a side stream, double buffered."""
+        main = torch.cuda.current_stream(self.device)
+        self.loss_dev.zero_()
+        my_views = list(range(rank, len(targets_pinned), world_size))
+        for i, v in enumerate(my_views):
+            slot = i & 1
+            with torch.cuda.stream(self.copy_stream):
+                if i >= 2:
+                    self.copy_stream.wait_event(self._tgt_free[slot])
+                self._tgt[slot].copy_(targets_pinned[v], non_blocking=True)
+                self._tgt_ready[slot].record(self.copy_stream)
+            self.forward(viewmats[v], Ks[v], active_sh_degree, bg)
+            main.wait_event(self._tgt_ready[slot])
+            self.loss_l1(self._tgt[slot])
+            self._tgt_free[slot].record(main)
+            self.backward()
+        if world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)
+            dist.all_reduce(self.loss_dev, op=dist.ReduceOp.SUM)
+        self.adam_step()
+        if read_loss:
+            self._loss_pinned.copy_(self.loss_dev, non_blocking=True)
+        return self._loss_pinned

@@ -1,0 +1,3 @@
+// TEST INFRASTRUCTURE ONLY: see ../glm.hpp (minimal glm-compatible shim).
+#pragma once
+#include "../glm.hpp"

@@ -1,0 +1,122 @@
+// TEST INFRASTRUCTURE ONLY -- not part of the product path.
+//
+// Thin extern "C" glue around the UNMODIFIED reference fastgs backend
+// (/root/reference/fastgs/rasterization/src/{forward,backward}.cu and
+// /root/reference/fastgs/optimizer/src/adam.cu, compiled in place by oracle/Makefile
+// into oracle/_ref/libfastgs_ref.so).  It calls the reference's own raw-pointer entry points
+//   fast_gs::rasterization::forward   (fastgs/rasterization/include/forward.h:13-38)
+//   fast_gs::rasterization::backward  (fastgs/rasterization/include/backward.h:13-50)
+//   fast_gs::optimizer::adam_step     (fastgs/optimizer/include/adam.h:9-20)
+// so tests / bench can run the reference CUDA path on the GPU box without libtorch.
+// Scratch blobs are owned here (cudaMalloc, grow-only) and play the role of the torch byte
+// tensors of fastgs/utils/torch_utils.h:10-17.
+#include "adam.h"
+#include "backward.h"
+#include "forward.h"
+
+#include <cstdio>
+#include <cuda_runtime.h>
+#include <functional>
+#include <tuple>
+
+namespace {
+    struct Blob {
+        char* ptr = nullptr;
+        size_t cap = 0;
+        char* resize(size_t n) {
+            if (n > cap) {
+                if (ptr)
+                    cudaFree(ptr);
+                size_t want = n + n / 4 + 256;
+                if (cudaMalloc(&ptr, want) != cudaSuccess) {
+                    ptr = nullptr;
+                    cap = 0;
+                    return nullptr;
+                }
+                cap = want;
+            }
+            return ptr;
+        }
+    };
+    struct Ctx {
+        Blob prim, tile, inst, bucket;
+        int n_visible = 0, n_instances = 0, n_buckets = 0, sel_prim = 0, sel_inst = 0;
+    };
+} // namespace
+
+extern "C" {
+
+void* ref_fastgs_create() { return new Ctx(); }
+
+void ref_fastgs_destroy(void* h) {
+    Ctx* c = static_cast<Ctx*>(h);
+    if (!c)
+        return;
+    for (Blob* b : {&c->prim, &c->tile, &c->inst, &c->bucket})
+        if (b->ptr)
+            cudaFree(b->ptr);
+    delete c;
+}
+
+// All pointers are device pointers. w2c: 16 floats row-major; cam_position: 3 floats.
+// image [3,H,W], alpha [1,H,W]. out_counts[3] (host) = n_visible, n_instances, n_buckets.
+int ref_fastgs_forward(void* h, const float* means, const float* scales_raw, const float* rotations_raw,
+                       const float* opacities_raw, const float* sh0, const float* shN, const float* w2c,
+                       const float* cam_position, float* image, float* alpha, int n_primitives,
+                       int active_sh_bases, int total_bases_sh_rest, int width, int height, float fx, float fy,
+                       float cx, float cy, float near_plane, float far_plane, int* out_counts) {
+    Ctx* c = static_cast<Ctx*>(h);
+    auto f_prim = [c](size_t n) { return c->prim.resize(n); };
+    auto f_tile = [c](size_t n) { return c->tile.resize(n); };
+    auto f_inst = [c](size_t n) { return c->inst.resize(n); };
+    auto f_bucket = [c](size_t n) { return c->bucket.resize(n); };
+    auto r = fast_gs::rasterization::forward(
+        f_prim, f_tile, f_inst, f_bucket, reinterpret_cast<const float3*>(means),
+        reinterpret_cast<const float3*>(scales_raw), reinterpret_cast<const float4*>(rotations_raw), opacities_raw,
+        reinterpret_cast<const float3*>(sh0), reinterpret_cast<const float3*>(shN),
+        reinterpret_cast<const float4*>(w2c), reinterpret_cast<const float3*>(cam_position), image, alpha,
+        n_primitives, active_sh_bases, total_bases_sh_rest, width, height, fx, fy, cx, cy, near_plane, far_plane);
+    c->n_visible = std::get<0>(r);
+    c->n_instances = std::get<1>(r);
+    c->n_buckets = std::get<2>(r);
+    c->sel_prim = std::get<3>(r);
+    c->sel_inst = std::get<4>(r);
+    if (out_counts) {
+        out_counts[0] = c->n_visible;
+        out_counts[1] = c->n_instances;
+        out_counts[2] = c->n_buckets;
+    }
+    return (int)cudaGetLastError();
+}
+
+// Gradient outputs must be zero-initialised by the caller exactly as backward_wrapper does
+// (fastgs/rasterization/src/rasterization_api.cu:125-132). grad_mean2d_helper [N,2],
+// grad_conic_helper [3,N]. densification_info may be null.
+int ref_fastgs_backward(void* h, const float* grad_image, const float* grad_alpha, const float* image,
+                        const float* alpha, const float* means, const float* scales_raw, const float* rotations_raw,
+                        const float* shN, const float* w2c, const float* cam_position, float* grad_means,
+                        float* grad_scales_raw, float* grad_rotations_raw, float* grad_opacities_raw, float* grad_sh0,
+                        float* grad_shN, float* grad_mean2d_helper, float* grad_conic_helper,
+                        float* densification_info, int n_primitives, int active_sh_bases, int total_bases_sh_rest,
+                        int width, int height, float fx, float fy, float cx, float cy) {
+    Ctx* c = static_cast<Ctx*>(h);
+    fast_gs::rasterization::backward(
+        grad_image, grad_alpha, image, alpha, reinterpret_cast<const float3*>(means),
+        reinterpret_cast<const float3*>(scales_raw), reinterpret_cast<const float4*>(rotations_raw),
+        reinterpret_cast<const float3*>(shN), reinterpret_cast<const float4*>(w2c),
+        reinterpret_cast<const float3*>(cam_position), c->prim.ptr, c->tile.ptr, c->inst.ptr, c->bucket.ptr,
+        reinterpret_cast<float3*>(grad_means), reinterpret_cast<float3*>(grad_scales_raw),
+        reinterpret_cast<float4*>(grad_rotations_raw), grad_opacities_raw, reinterpret_cast<float3*>(grad_sh0),
+        reinterpret_cast<float3*>(grad_shN), reinterpret_cast<float2*>(grad_mean2d_helper), grad_conic_helper,
+        nullptr, densification_info, n_primitives, c->n_visible, c->n_instances, c->n_buckets, c->sel_prim,
+        c->sel_inst, active_sh_bases, total_bases_sh_rest, width, height, fx, fy, cx, cy);
+    return (int)cudaGetLastError();
+}
+
+int ref_fastgs_adam_step(float* param, float* exp_avg, float* exp_avg_sq, const float* grad, int n, float lr,
+                         float beta1, float beta2, float eps, float bc1_rcp, float bc2_sqrt_rcp) {
+    fast_gs::optimizer::adam_step(param, exp_avg, exp_avg_sq, grad, n, lr, beta1, beta2, eps, bc1_rcp, bc2_sqrt_rcp);
+    return (int)cudaGetLastError();
+}
+
+} // extern "C"
