@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- training views/sec (fwd + bwd + Adam) of the B200-native 3DGS rasterizer.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path over one batch of synthetic views: every view is rendered (projection +
+SH + tile sort + blend forward), its L1 photometric gradient is back-propagated (blend backward + per-Gaussian
+backward), gradients of the batch are summed (NCCL all-reduce across ranks) and ONE fused Adam step is taken.
+Workload = BASELINE.json configs[2] ("C3": 1M Gaussians, 8 views of 1920x1080 per GPU, SH degree 3); with N GPUs
+the global batch is 8 N views (weak scaling; the views of a step are sharded round-robin over the ranks).
+
+One JSON line is printed by rank 0 (see the contract in the task statement): `value` = views/s with the target
+images already resident in HBM; `e2e` = the same through SplatTrainer.train_step with pinned HOST uint8 targets
+(H2D per view, D2H of the loss per step); `roofline` = blend-backward kernel, algorithmic bytes (172 I + 24 P per
+view) over its CUDA-event time against MEASURED_PEAKS.json; `cpu_baseline` = the CPU oracle
+port timed on a bounded crop of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "training views/sec (fwd+bwd+Adam) @1M Gaussians 1080p"
+UNIT = "views/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C3")
+    ap.add_argument("--n-gaussians", type=int, default=0, help="override N (testing only; invalidates the metric)")
+    ap.add_argument("--views-per-gpu", type=int, default=0)
+    ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / reference_gpu legs")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_reference_leg(scene_obj, seconds: float):
+    """The reference's path restated on the CPU (oracle port, OpenMP over all host cores) on a bounded crop of the
+    same workload: one view of the full Gaussian set, a centred crop window of the 1080p image, fwd + bwd."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+
+    import oracle as O
+
+    sc = scene_obj
+    cores = os.cpu_count() or 1
+    W, H = sc.width, sc.height
+    cw, ch = min(W, 256), min(H, 144)
+    x0, y0 = (W - cw) // 2 // 16 * 16, (H - ch) // 2 // 16 * 16
+    K = sc.Ks[0].copy()
+    K[0, 2] -= x0
+    K[1, 2] -= y0
+    raw = dict(means=sc.means, sh0=sc.sh0, shN=sc.shN, scaling=sc.scaling, rotation=sc.rotation, opacity=sc.opacity)
+    tgt = np.zeros((ch, cw, 3), np.uint8)
+    t0 = time.time()
+    reps = 0
+    while True:
+        O.view_loss_grads(raw, sc.viewmats[0], K, cw, ch, sc.sh_degree, (0.0, 0.0, 0.0), target=tgt, prec=32)
+        reps += 1
+        if time.time() - t0 > seconds or reps >= 3:
+            break
+    dt = (time.time() - t0) / reps
+    frac = (cw * ch) / float(W * H)
+    # per-Gaussian work (projection / SH) is paid in full by the crop; pixel work scales with the crop area:
+    # views/s is reported for the crop as if it were the image (an upper bound for the CPU path)
+    return {"value": frac / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"1 view, all {sc.n} Gaussians, centred {cw}x{ch} crop of {W}x{H} ({frac:.4f} of the pixels), "
+                      f"fwd+bwd, {reps} reps, {dt:.2f} s each; value = crop fraction / time"}
+
+
+def reference_gpu_leg(sc, steps: int, warmup: int, device):
+    """UNMODIFIED reference fastgs CUDA path (oracle/_ref/libfastgs_ref.so) on the same scene, cameras and loss:
+    per view forward -> L1 gradient (torch) -> backward, then its 6 Adam launches.  Reported beside our number as
+    the north_star asks; it is a baseline, never part of the product path."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import torch
+
+    import ref_libs as R
+    if not R.have_fastgs():
+        return {"unavailable": "oracle/_ref/libfastgs_ref.so not present"}
+    fg = R.FastGS()
+    T = lambda x: torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float32, device=device)
+    P = dict(means=T(sc.means), scales=T(sc.scaling), rot=T(sc.rotation), op=T(sc.opacity), sh0=T(sc.sh0),
+             shN=T(sc.shN))
+    state = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in P.items()}
+    lrs = dict(means=0.00016, sh0=0.0025, shN=0.0025 / 20, scales=0.005, rot=0.001, op=0.05)
+    W, H = sc.width, sc.height
+    V = sc.viewmats.shape[0]
+    from lichtfeld_studio_b200 import scene as S
+    tg = [torch.as_tensor(S.make_target(v, W, H)).to(device).permute(2, 0, 1).float().div_(255.0).contiguous()
+          for v in range(min(V, 8))]
+    cams = []
+    for v in range(V):
+        w2c = T(sc.viewmats[v])
+        campos = T(np.linalg.inv(sc.viewmats[v].astype(np.float64))[:3, 3])
+        cams.append((w2c, campos, float(sc.Ks[v, 0, 0]), float(sc.Ks[v, 1, 1]), float(sc.Ks[v, 0, 2]),
+                     float(sc.Ks[v, 1, 2])))
+    nb = (sc.sh_degree + 1) ** 2
+    scale = 1.0 / (3.0 * W * H)
+
+    def step(t):
+        acc = None
+        for v in range(V):
+            w2c, campos, fx, fy, cx, cy = cams[v]
+            img, alpha, _ = fg.forward(P["means"], P["scales"], P["rot"], P["op"], P["sh0"], P["shN"], w2c, campos, nb,
+                                       W, H, fx, fy, cx, cy)
+            gimg = torch.sign(img - tg[v % len(tg)]) * scale
+            galpha = torch.zeros_like(alpha)
+            g = fg.backward(gimg, galpha, img, alpha, P["means"], P["scales"], P["rot"], P["shN"], w2c, campos, nb, W,
+                            H, fx, fy, cx, cy)
+            if acc is None:
+                acc = g
+            else:
+                for k in ("means", "scales", "rot", "op", "sh0", "shN"):
+                    acc[k] += g[k]
+        bc1, bc2 = 1.0 / (1.0 - 0.9 ** t), 1.0 / (1.0 - 0.999 ** t) ** 0.5
+        for k in ("means", "sh0", "shN", "scales", "rot", "op"):
+            fg.adam_step(P[k], state[k][0], state[k][1], acc[k], lrs[k], 0.9, 0.999, 1e-15, bc1, bc2)
+
+    for i in range(warmup):
+        step(i + 1)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(warmup + i + 1)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"impl": "reference fastgs (EWA) CUDA build, unmodified, sm_100a, --use_fast_math", "value": V / ms * 1e3,
+            "unit": UNIT, "ms_per_step": ms, "views_per_step": V,
+            "note": "targets resident in HBM; loss gradient by torch elementwise ops; includes its 3 blocking D2H reads"}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def main():
+    a = parse()
+    import numpy as np
+    from lichtfeld_studio_b200 import scene as S
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg_n, cfg_v, W, H, deg = S.CONFIGS[a.config]
+    n = a.n_gaussians or cfg_n
+    vpg = a.views_per_gpu or (8 if a.config in ("C3", "C4") else cfg_v)
+    V = vpg * max(world, 1)
+
+    if a.impl == "reference":
+        # reference arm (tier rule): the reference's path on the box's host cores -- rank 0 only
+        if rank != 0:
+            return 0
+        sc = S.make_scene(n, 1, W, H, deg, seed=42)
+        t_all = time.time()
+        vals = []
+        for _ in range(max(1, min(a.steps, 3))):
+            vals.append(cpu_reference_leg(sc, max(5.0, min(a.cpu_seconds, 30.0)) / 3.0))
+        cb = dict(vals[-1])
+        cb["value"] = statistics.median(v["value"] for v in vals)
+        line = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "impl": "reference", "n_gpus": a.gpus,
+                "steps": len(vals), "warmup": 0, "ms_per_step": 1e3 / cb["value"] if cb["value"] else None,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{a.config}: {n} Gaussians, {W}x{H}, SH degree {deg}; CPU port of the "
+                                       "reference path (no CPU implementation of the blend exists in the reference: "
+                                       "tests/test_rasterization.cpp:96-98)", "gaussians": n},
+                "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0, "wall_s": round(time.time() - t_all, 1)}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from lichtfeld_studio_b200.trainer import SplatTrainer
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    sc = S.make_scene(n, V, W, H, deg, seed=42)
+    my_views = list(range(rank, V, world))
+
+    tr = SplatTrainer(n, W, H, deg, device)
+    tr.load_scene(sc)
+    # capacity calibration (one forward per local view, with sync) -- outside every timed region
+    need = 0
+    for v in my_views:
+        tr.forward(sc.viewmats[v], sc.Ks[v], deg)
+        try:
+            ni, _ = tr.stats()
+        except Exception:
+            ni = int(tr.lib.lfs_trainer_instance_capacity(tr.h)) * 2
+        need = max(need, ni)
+    cap = int(tr.lib.lfs_trainer_instance_capacity(tr.h))
+    if need > cap or cap > 2 * need + (1 << 20):
+        new_cap = int(need * 1.25) + (1 << 16)
+        del tr
+        torch.cuda.empty_cache()
+        tr = SplatTrainer(n, W, H, deg, device, instance_capacity=new_cap)
+        tr.load_scene(sc)
+    n_inst_per_view = []
+    for v in my_views:
+        tr.forward(sc.viewmats[v], sc.Ks[v], deg)
+        n_inst_per_view.append(tr.stats()[0])
+
+    targets_host = [torch.as_tensor(S.make_target(v, W, H)).pin_memory() for v in range(V)]
+    targets_dev = {v: targets_host[v].to(device) for v in my_views}
+    bg = (0.0, 0.0, 0.0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        tr.loss_dev.zero_()
+        for v in my_views:
+            tr.forward(sc.viewmats[v], sc.Ks[v], deg, bg)
+            tr.loss_l1(targets_dev[v])
+            tr.backward()
+        if world > 1:
+            dist.all_reduce(tr.grads, op=dist.ReduceOp.SUM)
+        tr.adam_step()
+
+    def step_e2e():
+        tr.train_step(sc.viewmats, sc.Ks, targets_host, bg, deg, world, rank, read_loss=True)
+        torch.cuda.current_stream().synchronize()  # the step's result (loss) is read on the host
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = tr.lib.lfs_launch_count()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        launches = tr.lib.lfs_launch_count() - l0
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return float(ms.item()), int(launches)
+
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ms_step, launches = timed(step_resident, a.steps, a.warmup)
+    clk = clocks.stop() if rank == 0 else {}
+    ms_e2e, _ = timed(step_e2e, a.steps, max(1, a.warmup))
+
+    # per-kernel timing for the roofline (profiling pass, outside the timed regions)
+    tr.set_profile(True)
+    for _ in range(2):
+        step_resident()
+    torch.cuda.synchronize()
+    prof = tr.get_profile()
+    tr.set_profile(False)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peak_gbs()
+    I = float(np.mean(n_inst_per_view)) if n_inst_per_view else 0.0
+    P = float(W * H)
+    bwd_bytes = 172.0 * I + 24.0 * P
+    fwd_bytes = 60.0 * I + 20.0 * P
+    bwd_ms = prof.get("blend_bwd", 0.0)
+    achieved = bwd_bytes / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 else 0.0
+    h2d = sum(int(targets_host[v].numel()) for v in my_views) + len(my_views) * (16 + 9) * 4
+    line = {
+        "metric": METRIC, "value": V / ms_step * 1e3, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{a.config}: {n} Gaussians, {vpg} views/GPU x {world} GPU of {W}x{H}, SH degree {deg}, "
+                               "3DGUT from-world rasterizer, L1 loss, eval/default_optimization_params.json lrs",
+                   "gaussians": n, "views_per_step": V, "width": W, "height": H, "sh_degree": deg,
+                   "parallelism": f"view-sharded dp{world} + NCCL all-reduce of the flat gradient arena",
+                   "instances_per_view": I, "l2": "per-step working set (params+grads+Adam state+records) >= 1 GB, "
+                                                  "larger than the 126 MB L2: no flush needed"},
+        "clocks": clk,
+        "e2e": {"value": V / ms_e2e * 1e3, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4,
+                "note": "SplatTrainer.train_step: pinned uint8 HWC targets copied per view on a side stream, "
+                        "loss scalar read back per step"},
+        "gpu_launches": launches,
+        "roofline": {"kernel": "k_blend_bwd", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes": bwd_bytes, "launch_ms": bwd_ms,
+                     "note": "algorithmic bytes = 172*I + 24*P per view (BASELINE.md s5); the kernel is FP32/SFU "
+                             "bound, not HBM bound (SURVEY s7 'roofline honesty')"},
+        "stage_ms_per_view": prof,
+        "stage_roofline": {"blend_fwd_GBps": fwd_bytes / (prof.get("blend_fwd", 0) * 1e-3) / 1e9
+                           if prof.get("blend_fwd", 0) > 0 else None},
+    }
+    if not a.no_extras and world == 1:
+        try:
+            line["cpu_baseline"] = cpu_reference_leg(S.make_scene(n, 1, W, H, deg, seed=42), a.cpu_seconds)
+        except Exception as e:
+            line["cpu_baseline"] = {"error": repr(e)}
+        try:
+            del tr
+            torch.cuda.empty_cache()
+            line["reference_gpu"] = reference_gpu_leg(sc, max(2, min(a.steps, 4)), 1, device)
+        except Exception as e:
+            line["reference_gpu"] = {"error": repr(e)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

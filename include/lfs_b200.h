@@ -225,6 +225,14 @@ int lfs_trainer_view_backward(void* trainer, const float* params_arena, float* g
 /* blocks on `stream`; returns LFS_ERR_CAPACITY if the last forward overflowed instance_capacity */
 int lfs_trainer_stats(void* trainer, uint64_t* n_instances, uint64_t* n_buckets, void* stream);
 
+/* Per-stage device timing of the view step with CUDA events on the launching stream (bench.py roofline).
+ * Stages: 0 preprocess_fwd | 1 depth sort + scan + emit + tile sort + offsets | 2 bucket offsets + expand |
+ *         3 blend_fwd | 4 (loss: caller side, always 0) | 5 blend_bwd | 6 preprocess_bwd.
+ * Enabling it makes lfs_trainer_view_backward block on the stream; never enable it inside a timed region. */
+#define LFS_PROF_STAGES 7
+int lfs_trainer_set_profile(void* trainer, int enable);
+int lfs_trainer_get_profile(void* trainer, float* mean_ms /* [LFS_PROF_STAGES] */, int* counts /* or NULL */);
+
 /* library options: "blend_tma" = 0/1 (stage per-tile records with cp.async.bulk + mbarrier; default 1) */
 int lfs_set_option(const char* name, int value);
 

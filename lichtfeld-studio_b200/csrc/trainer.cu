@@ -63,6 +63,17 @@ struct Trainer {
     float bg[3];
     uint32_t active_degree = 0;
     uint32_t* stats_host = nullptr; // pinned: n_inst, n_buckets
+    // optional per-stage CUDA-event timing (bench.py roofline): see lfs_trainer_set_profile
+    int profile = 0;
+    cudaEvent_t ev[LFS_PROF_STAGES + 2] = {};
+    bool ev_ok = false;
+    float acc_ms[LFS_PROF_STAGES] = {};
+    int acc_n[LFS_PROF_STAGES] = {};
+    int pending_from = -1, pending_to = -1;
+    void mark(int i, cudaStream_t st) {
+        if (profile && ev_ok)
+            cudaEventRecord(ev[i], st);
+    }
 };
 
 static size_t trainer_carve(Trainer& t, void* base) {
@@ -474,10 +485,12 @@ extern "C" int lfs_trainer_view_forward(void* h, const float* params_arena, cons
     LFS_CUDA_OK(cudaMemcpyAsync(t->cam_dev, &t->cam_host, sizeof(ViewCam), cudaMemcpyHostToDevice, stream));
 
     PreCfg cfg{t->d.eps2d, t->d.near_plane, t->d.far_plane, t->d.radius_clip, t->d.ut, (int)active_sh_degree};
+    t->mark(0, stream);
     k_preprocess_fwd<<<div_up(N, 256), 256, 0, stream>>>(params_arena, t->pl, N, t->cam_host, cfg, t->gauss, t->rects,
                                                          t->counts, t->dk_a, t->pm_a, t->act_means, t->act_quats,
                                                          t->act_scales);
     LFS_LAUNCH_OK("k_preprocess_fwd");
+    t->mark(1, stream);
     int in_b = 0;
     int rc = radix_sort_pairs(t->dk_a, t->pm_a, t->dk_b, t->pm_b, N, nullptr, 0, 32, t->sort_scr, &in_b, stream);
     if (rc)
@@ -512,6 +525,7 @@ extern "C" int lfs_trainer_view_forward(void* h, const float* params_arena, cons
     rb.tile_max_contrib = t->tile_max;
     rb.pix_state = t->pix_state;
     rb.n_contrib = t->n_contrib;
+    t->mark(2, stream);
     rc = launch_bucket_offsets(rb, t->n_tiles, t->n_inst + 1, t->scan_scr, t->bucket_counts, stream);
     if (rc)
         return rc;
@@ -519,10 +533,12 @@ extern "C" int lfs_trainer_view_forward(void* h, const float* params_arena, cons
                                  stream);
     if (rc)
         return rc;
+    t->mark(3, stream);
     rc = launch_blend_fwd(rb, 1, t->d.width, t->d.height, t->tile_w, t->tile_h, true, nullptr, nullptr, nullptr,
                           nullptr, nullptr, stream);
     if (rc)
         return rc;
+    t->mark(4, stream);
     if (image_out || alpha_out) {
         const uint32_t npix = t->d.width * t->d.height;
         k_export_image<<<div_up(npix, 256), 256, 0, stream>>>(t->pix_state, t->bg[0], t->bg[1], t->bg[2], npix,
@@ -579,15 +595,55 @@ extern "C" int lfs_trainer_view_backward(void* h, const float* params_arena, flo
     rb.tile_max_contrib = t->tile_max;
     rb.pix_state = t->pix_state;
     rb.n_contrib = t->n_contrib;
+    t->mark(5, stream);
     int rc = launch_blend_bwd(rb, t->cam_dev, t->v_pix, t->act_quats, t->act_scales, t->act_means, 1, N, t->d.width,
                               t->d.height, t->tile_w, t->tile_h, t->bucket_cap, t->n_inst + 1, t->v_means, t->v_quats,
                               t->v_scales, t->v_colors, t->v_opac, stream);
     if (rc)
         return rc;
+    t->mark(6, stream);
     k_preprocess_bwd<<<div_up(N, 256), 256, 0, stream>>>(params_arena, grads_arena, t->pl, N, t->cam_host,
                                                          (int)t->active_degree, t->counts, t->v_means, t->v_quats,
                                                          t->v_scales, t->v_colors, t->v_opac);
     LFS_LAUNCH_OK("k_preprocess_bwd");
+    t->mark(7, stream);
+    if (t->profile && t->ev_ok) { // fold this view's stage times into the running sums (blocks: profiling only)
+        cudaEventSynchronize(t->ev[7]);
+        for (int i = 0; i < LFS_PROF_STAGES; ++i) {
+            float ms = 0.f;
+            if (i == 4) // loss stage is not bracketed by library events
+                continue;
+            if (cudaEventElapsedTime(&ms, t->ev[i], t->ev[i + 1]) == cudaSuccess) {
+                t->acc_ms[i] += ms;
+                t->acc_n[i] += 1;
+            }
+        }
+    }
+    return LFS_OK;
+}
+
+extern "C" int lfs_trainer_set_profile(void* h, int enable) {
+    Trainer* t = static_cast<Trainer*>(h);
+    LFS_CHECK_ARG(t, "trainer_set_profile: null handle");
+    if (enable && !t->ev_ok) {
+        for (auto& e : t->ev)
+            LFS_CUDA_OK(cudaEventCreate(&e));
+        t->ev_ok = true;
+    }
+    t->profile = enable ? 1 : 0;
+    for (int i = 0; i < LFS_PROF_STAGES; ++i)
+        t->acc_ms[i] = 0.f, t->acc_n[i] = 0;
+    return LFS_OK;
+}
+
+extern "C" int lfs_trainer_get_profile(void* h, float* mean_ms, int* counts) {
+    Trainer* t = static_cast<Trainer*>(h);
+    LFS_CHECK_ARG(t && mean_ms, "trainer_get_profile: null pointer");
+    for (int i = 0; i < LFS_PROF_STAGES; ++i) {
+        mean_ms[i] = t->acc_n[i] ? t->acc_ms[i] / (float)t->acc_n[i] : 0.f;
+        if (counts)
+            counts[i] = t->acc_n[i];
+    }
     return LFS_OK;
 }
 

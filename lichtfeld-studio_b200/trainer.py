@@ -139,6 +139,17 @@ class SplatTrainer:
         check(self.lib.lfs_trainer_stats(self.h, C.byref(n_inst), C.byref(n_b), self._stream()))
         return int(n_inst.value), int(n_b.value)
 
+    PROF_STAGES = ("preprocess_fwd", "sort_intersect", "expand", "blend_fwd", "loss", "blend_bwd", "preprocess_bwd")
+
+    def set_profile(self, enable: bool) -> None:
+        check(self.lib.lfs_trainer_set_profile(self.h, 1 if enable else 0))
+
+    def get_profile(self) -> dict:
+        ms = (C.c_float * 7)()
+        cnt = (C.c_int * 7)()
+        check(self.lib.lfs_trainer_get_profile(self.h, ms, cnt))
+        return {k: float(ms[i]) for i, k in enumerate(self.PROF_STAGES)}
+
     # ---- optimiser (FusedAdam::step mirror) -----------------------------------------------------------------
     def adam_step(self) -> None:
         self.iteration += 1

@@ -1,0 +1,228 @@
+"""ctypes front-end of the CPU oracle (oracle/liblfs_oracle.so).  TEST INFRASTRUCTURE ONLY.
+
+numpy in, numpy out.  `prec` selects the float (orc32_) or double (orc64_) variant of the floating-point
+stages; integer stages (tile intersection) have a single bit-exact implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_ORACLE_DIR = os.path.join(_ROOT, "oracle")
+_LIB_PATH = os.path.join(_ORACLE_DIR, "liblfs_oracle.so")
+_lib = None
+
+
+def build():
+    r = subprocess.run(["make", "-C", _ORACLE_DIR, "oracle"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + r.stdout + r.stderr)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.orc_intersect_count.restype = C.c_int64
+    return _lib
+
+
+def _dt(prec):
+    return (np.float64, "orc64_", C.c_double) if prec == 64 else (np.float32, "orc32_", C.c_float)
+
+
+def _a(x, dtype):
+    return None if x is None else np.ascontiguousarray(x, dtype=dtype)
+
+
+def _p(x):
+    return None if x is None else x.ctypes.data_as(C.c_void_p)
+
+
+def projection_ut(means, quats, scales, opacities, viewmats, Ks, width, height, eps2d=0.3, near=0.01, far=1e4,
+                  radius_clip=0.0, ut=(0.1, 2.0, 0.0, 0.1, 1), calc_compensations=False, prec=64):
+    dt, pfx, cf = _dt(prec)
+    means, quats, scales = _a(means, dt), _a(quats, dt), _a(scales, dt)
+    opacities, viewmats, Ks = _a(opacities, dt), _a(viewmats, dt), _a(Ks, dt)
+    N, Cc = means.shape[0], Ks.shape[0]
+    radii = np.zeros((Cc, N, 2), np.int32)
+    means2d = np.zeros((Cc, N, 2), dt)
+    depths = np.zeros((Cc, N), dt)
+    conics = np.zeros((Cc, N, 3), dt)
+    comp = np.zeros((Cc, N), dt) if calc_compensations else None
+    getattr(lib(), pfx + "projection_ut")(
+        C.c_int(Cc), C.c_int(N), _p(means), _p(quats), _p(scales), _p(opacities), _p(viewmats), _p(Ks),
+        C.c_int(width), C.c_int(height), cf(eps2d), cf(near), cf(far), cf(radius_clip), cf(ut[0]), cf(ut[1]),
+        cf(ut[2]), cf(ut[3]), C.c_int(ut[4]), _p(radii), _p(means2d), _p(depths), _p(conics), _p(comp))
+    return radii, means2d, depths, conics, comp
+
+
+def sh_fwd(degree, dirs, coeffs, masks=None, prec=64):
+    dt, pfx, _ = _dt(prec)
+    dirs, coeffs = _a(dirs, dt), _a(coeffs, dt)
+    n, K = dirs.reshape(-1, 3).shape[0], coeffs.shape[-2]
+    m = None if masks is None else _a(masks, np.uint8)
+    colors = np.zeros((n, 3), dt)
+    getattr(lib(), pfx + "sh_fwd")(C.c_int(degree), C.c_int(n), C.c_int(K), _p(dirs), _p(coeffs), _p(m), _p(colors))
+    return colors.reshape(dirs.shape)
+
+
+def sh_bwd(degree, dirs, coeffs, v_colors, masks=None, compute_v_dirs=True, prec=64):
+    dt, pfx, _ = _dt(prec)
+    dirs, coeffs, v_colors = _a(dirs, dt), _a(coeffs, dt), _a(v_colors, dt)
+    n, K = dirs.reshape(-1, 3).shape[0], coeffs.shape[-2]
+    m = None if masks is None else _a(masks, np.uint8)
+    v_coeffs = np.zeros(coeffs.shape, dt)
+    v_dirs = np.zeros(dirs.shape, dt) if compute_v_dirs else None
+    getattr(lib(), pfx + "sh_bwd")(C.c_int(degree), C.c_int(n), C.c_int(K), _p(dirs), _p(coeffs), _p(m),
+                                   _p(v_colors), _p(v_coeffs), _p(v_dirs))
+    return v_coeffs, v_dirs
+
+
+def intersect_tile(means2d, radii, depths, tile_size, tile_width, tile_height, sort=True):
+    """-> (tiles_per_gauss [C,N] i32, isect_ids [n] i64, flatten_ids [n] i32); float32 arithmetic, bit exact."""
+    means2d, radii, depths = _a(means2d, np.float32), _a(radii, np.int32), _a(depths, np.float32)
+    Cc, N = depths.shape
+    tpg = np.zeros((Cc, N), np.int32)
+    n = lib().orc_intersect_count(C.c_int(Cc), C.c_int(N), _p(means2d), _p(radii), C.c_uint32(tile_size),
+                                  C.c_uint32(tile_width), C.c_uint32(tile_height), _p(tpg))
+    ids = np.zeros((n,), np.int64)
+    flat = np.zeros((n,), np.int32)
+    lib().orc_intersect_emit(C.c_int(Cc), C.c_int(N), _p(means2d), _p(radii), _p(depths), C.c_uint32(tile_size),
+                             C.c_uint32(tile_width), C.c_uint32(tile_height), C.c_int(1 if sort else 0), _p(ids),
+                             _p(flat))
+    return tpg, ids, flat
+
+
+def intersect_offset(isect_ids, Cc, tile_width, tile_height):
+    isect_ids = _a(isect_ids, np.int64)
+    off = np.zeros((Cc, tile_height, tile_width), np.int32)
+    lib().orc_intersect_offset(C.c_int64(isect_ids.shape[0]), _p(isect_ids), C.c_int(Cc), C.c_uint32(tile_width),
+                               C.c_uint32(tile_height), _p(off))
+    return off
+
+
+def raster_world_fwd(means, quats, scales, colors, opacities, backgrounds, tile_masks, width, height, tile_size,
+                     viewmats, Ks, tile_offsets, flatten_ids, prec=64):
+    dt, pfx, _ = _dt(prec)
+    means, quats, scales = _a(means, dt), _a(quats, dt), _a(scales, dt)
+    colors, opacities, viewmats, Ks = _a(colors, dt), _a(opacities, dt), _a(viewmats, dt), _a(Ks, dt)
+    backgrounds = _a(backgrounds, dt)
+    tile_masks = None if tile_masks is None else _a(tile_masks, np.uint8)
+    tile_offsets, flatten_ids = _a(tile_offsets, np.int32), _a(flatten_ids, np.int32)
+    Cc, N, CH = viewmats.shape[0], means.shape[0], colors.shape[-1]
+    renders = np.zeros((Cc, height, width, CH), dt)
+    alphas = np.zeros((Cc, height, width, 1), dt)
+    last_ids = np.zeros((Cc, height, width), np.int32)
+    getattr(lib(), pfx + "raster_world_fwd")(
+        C.c_int(Cc), C.c_int(N), C.c_int(CH), _p(means), _p(quats), _p(scales), _p(colors), _p(opacities),
+        _p(backgrounds), _p(tile_masks), C.c_int(width), C.c_int(height), C.c_int(tile_size), _p(viewmats), _p(Ks),
+        _p(tile_offsets), _p(flatten_ids), C.c_int64(flatten_ids.shape[0]), _p(renders), _p(alphas), _p(last_ids))
+    return renders, alphas, last_ids
+
+
+def raster_world_bwd(means, quats, scales, colors, opacities, backgrounds, tile_masks, width, height, tile_size,
+                     viewmats, Ks, tile_offsets, flatten_ids, render_alphas, last_ids, v_render_colors,
+                     v_render_alphas, prec=64):
+    dt, pfx, _ = _dt(prec)
+    means, quats, scales = _a(means, dt), _a(quats, dt), _a(scales, dt)
+    colors, opacities, viewmats, Ks = _a(colors, dt), _a(opacities, dt), _a(viewmats, dt), _a(Ks, dt)
+    backgrounds = _a(backgrounds, dt)
+    tile_masks = None if tile_masks is None else _a(tile_masks, np.uint8)
+    tile_offsets, flatten_ids = _a(tile_offsets, np.int32), _a(flatten_ids, np.int32)
+    render_alphas, last_ids = _a(render_alphas, dt), _a(last_ids, np.int32)
+    v_render_colors, v_render_alphas = _a(v_render_colors, dt), _a(v_render_alphas, dt)
+    Cc, N = viewmats.shape[0], means.shape[0]
+    v_means = np.zeros((N, 3), np.float64)
+    v_quats = np.zeros((N, 4), np.float64)
+    v_scales = np.zeros((N, 3), np.float64)
+    v_colors = np.zeros((Cc, N, 3), np.float64)
+    v_opac = np.zeros((Cc, N), np.float64)
+    getattr(lib(), pfx + "raster_world_bwd")(
+        C.c_int(Cc), C.c_int(N), _p(means), _p(quats), _p(scales), _p(colors), _p(opacities), _p(backgrounds),
+        _p(tile_masks), C.c_int(width), C.c_int(height), C.c_int(tile_size), _p(viewmats), _p(Ks), _p(tile_offsets),
+        _p(flatten_ids), C.c_int64(flatten_ids.shape[0]), _p(render_alphas), _p(last_ids), _p(v_render_colors),
+        _p(v_render_alphas), _p(v_means), _p(v_quats), _p(v_scales), _p(v_colors), _p(v_opac))
+    return v_means, v_quats, v_scales, v_colors, v_opac
+
+
+def adam_step(param, exp_avg, exp_avg_sq, grad, lr, beta1, beta2, eps, bc1_rcp, bc2_sqrt_rcp, prec=64):
+    """Returns updated copies (param, exp_avg, exp_avg_sq)."""
+    dt, pfx, cf = _dt(prec)
+    p, m, v, g = (np.array(x, dtype=dt, copy=True).reshape(-1) for x in (param, exp_avg, exp_avg_sq, grad))
+    getattr(lib(), pfx + "adam_step")(_p(p), _p(m), _p(v), _p(g), C.c_int64(p.shape[0]), cf(lr), cf(beta1),
+                                      cf(beta2), cf(eps), cf(bc1_rcp), cf(bc2_sqrt_rcp))
+    return p, m, v
+
+
+# ------------------------------------------------------------------------------------------------------------
+# composition of the oracle stages into the reference's per-view pipeline
+# (src/training/rasterization/rasterizer.cpp:208-360): activated params -> image (+ everything in between)
+# ------------------------------------------------------------------------------------------------------------
+def render_view(means, quats, scales, opacities, shs, sh_degree, viewmat, K, width, height, bg=None, tile_size=16,
+                prec=64):
+    vm, Kk = np.asarray(viewmat)[None], np.asarray(K)[None]
+    radii, means2d, depths, conics, _ = projection_ut(means, quats, scales, opacities, vm, Kk, width, height,
+                                                      prec=prec)
+    campos = np.linalg.inv(np.asarray(viewmat, np.float64))[:3, 3]
+    dirs = np.asarray(means, np.float64) - campos[None]
+    masks = (radii[0] > 0).all(-1)
+    cols = sh_fwd(sh_degree, dirs, shs, masks.astype(np.uint8), prec=prec)
+    colors = np.maximum(cols + 0.5, 0.0)
+    tw, th = (width + tile_size - 1) // tile_size, (height + tile_size - 1) // tile_size
+    tpg, ids, flat = intersect_tile(means2d, radii, depths, tile_size, tw, th, True)
+    offs = intersect_offset(ids, 1, tw, th)
+    bgs = None if bg is None else np.asarray(bg, np.float64)[None]
+    renders, alphas, last_ids = raster_world_fwd(means, quats, scales, colors[None], np.asarray(opacities)[None], bgs,
+                                                 None, width, height, tile_size, vm, Kk, offs, flat, prec=prec)
+    return dict(radii=radii, means2d=means2d, depths=depths, conics=conics, dirs=dirs, masks=masks, sh_colors=cols,
+                colors=colors, tiles_per_gauss=tpg, isect_ids=ids, flatten_ids=flat, offsets=offs, renders=renders,
+                alphas=alphas, last_ids=last_ids)
+
+
+def view_loss_grads(scene_raw, viewmat, K, width, height, sh_degree, bg, v_image=None, v_alpha=None, target=None,
+                    l1_scale=None, prec=64):
+    """Full per-view chain on raw parameters, as the reference composes it with torch autograd
+    (rasterizer.cpp:72-81 activations, :250-266 SH + clamp, rasterizer_autograd.cpp:329-392 blend bwd,
+    :84-130 SH bwd): returns (outputs dict, grads dict in the reference's AoS layout).
+    Either upstream grads (v_image [H,W,3], v_alpha [H,W]) or an L1 target (uint8/float [H,W,3]) is given."""
+    means = np.asarray(scene_raw["means"], np.float64)
+    rot = np.asarray(scene_raw["rotation"], np.float64)
+    nrm = np.maximum(np.linalg.norm(rot, axis=-1, keepdims=True), 1e-12)
+    q = rot / nrm
+    scales = np.exp(np.asarray(scene_raw["scaling"], np.float64))
+    op_raw = np.asarray(scene_raw["opacity"], np.float64)[:, 0]
+    op = 1.0 / (1.0 + np.exp(-op_raw))
+    sh0, shN = np.asarray(scene_raw["sh0"], np.float64), np.asarray(scene_raw["shN"], np.float64)
+    shs = np.concatenate([sh0, shN], axis=1)
+    r = render_view(means, q, scales, op, shs, sh_degree, viewmat, K, width, height, bg=bg, prec=prec)
+    image = r["renders"][0]
+    loss = None
+    if target is not None:
+        tgt = np.asarray(target, np.float64) / (255.0 if np.asarray(target).dtype == np.uint8 else 1.0)
+        s = 1.0 / (3.0 * width * height) if l1_scale is None else l1_scale
+        diff = image - tgt
+        loss = s * np.abs(diff).sum()
+        v_image = s * np.sign(diff)
+        v_alpha = np.zeros((height, width))
+    v_alpha = np.zeros((height, width)) if v_alpha is None else v_alpha
+    vm, Kk = np.asarray(viewmat)[None], np.asarray(K)[None]
+    bgs = None if bg is None else np.asarray(bg, np.float64)[None]
+    g = raster_world_bwd(means, q, scales, r["colors"][None], op[None], bgs, None, width, height, 16, vm, Kk,
+                         r["offsets"], r["flatten_ids"], r["alphas"], r["last_ids"], np.asarray(v_image)[None],
+                         np.asarray(v_alpha)[None, :, :, None], prec=prec)
+    v_means, v_quats, v_scales, v_colors, v_opac = g[0], g[1], g[2], g[3][0], g[4][0]
+    v_colors = v_colors * (r["sh_colors"] + 0.5 >= 0.0)  # clamp_min backward
+    v_coeffs, v_dirs = sh_bwd(sh_degree, r["dirs"], shs, v_colors, r["masks"].astype(np.uint8), True, prec=prec)
+    v_means = v_means + v_dirs
+    dq = (v_quats * q).sum(-1, keepdims=True)
+    grads = dict(means=v_means, sh0=v_coeffs[:, :1], shN=v_coeffs[:, 1:], scaling=v_scales * scales,
+                 rotation=(v_quats - dq * q) / nrm, opacity=(v_opac * op * (1.0 - op))[:, None])
+    r["loss"] = loss
+    return r, grads
