@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--views-per-gpu", type=int, default=0)
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / reference_gpu legs")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    ap.add_argument("--ref-gpu-leg", action="store_true", help=argparse.SUPPRESS)
     return ap.parse_args()
 
 
@@ -209,6 +210,12 @@ def main():
     vpg = a.views_per_gpu or (8 if a.config in ("C3", "C4") else cfg_v)
     V = vpg * max(world, 1)
 
+    if a.ref_gpu_leg:  # child process: time the unmodified reference CUDA build and print one JSON object
+        import torch
+        sc = S.make_scene(n, vpg, W, H, deg, seed=42)
+        print("REFGPU " + json.dumps(reference_gpu_leg(sc, max(2, min(a.steps, 4)), 1, torch.device("cuda:0"))))
+        return 0
+
     if a.impl == "reference":
         # reference arm (tier rule): the reference's path on the box's host cores -- rank 0 only
         if rank != 0:
@@ -365,10 +372,14 @@ def main():
             line["cpu_baseline"] = cpu_reference_leg(S.make_scene(n, 1, W, H, deg, seed=42), a.cpu_seconds)
         except Exception as e:
             line["cpu_baseline"] = {"error": repr(e)}
-        try:
+        try:  # separate process: a fault inside the reference build must not take the bench down
             del tr
             torch.cuda.empty_cache()
-            line["reference_gpu"] = reference_gpu_leg(sc, max(2, min(a.steps, 4)), 1, device)
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--ref-gpu-leg", "--config", a.config,
+                                "--n-gaussians", str(a.n_gaussians), "--views-per-gpu", str(vpg), "--steps",
+                                str(a.steps)], capture_output=True, text=True, timeout=600)
+            got = [l for l in r.stdout.splitlines() if l.startswith("REFGPU ")]
+            line["reference_gpu"] = json.loads(got[-1][7:]) if got else {"error": (r.stderr or r.stdout)[-400:]}
         except Exception as e:
             line["reference_gpu"] = {"error": repr(e)}
     print(json.dumps(line))

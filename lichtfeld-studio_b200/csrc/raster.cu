@@ -152,60 +152,40 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
                  : "memory");
 }
 
-struct PixAcc {
-    float r, g, b, T;
-    uint32_t ncon;
-    bool done;
-};
+// Forward blend with ACTIVE-PIXEL COMPACTION.
+// A 16x16 tile is served by 64 threads; every thread works on up to 4 pixels taken from a compact list of the
+// tile's still-active pixels that is rebuilt in shared memory after every staged batch of 64 records.  Pixels
+// that saturate (T <= 1e-4) or lie outside the image drop out of the list, so the few pixels of a tile that never
+// saturate (silhouettes, sky) no longer drag 32-wide warps through the whole instance list with 1-2 live lanes
+// (measured before: 2.0 active threads per warp instruction on the C3 scene, profiles/r01_*).  One staged record
+// (4 x LDS.128) serves 4 pixel evaluations.  The polynomial nesting is mirrored exactly by the backward so a pair
+// gets the same alpha bits in both passes.
+constexpr int kFwdThreads = kTilePix / 4;
 
-// evaluate `nrec` records of one staged batch for this pixel
-__device__ __forceinline__ void blend_batch(const float4* __restrict__ s, const int nrec, const uint32_t first_li,
-                                            const float dx, const float dy, const bool write_ckpt,
-                                            float4* __restrict__ ckpt_px /* + bucket*256 stride */, PixAcc& a) {
-    for (int t = 0; t < nrec; ++t) {
-        const uint32_t li = first_li + t;
-        if (write_ckpt && (li & (kBucket - 1)) == 0)
-            ckpt_px[(size_t)(li >> 5) * kTilePix] = make_float4(a.r, a.g, a.b, a.T);
-        const float4 A = s[4 * t], B = s[4 * t + 1], Cc = s[4 * t + 2], E = s[4 * t + 3];
-        const float Nv = fmaf(dy, fmaf(dy, B.y, A.z), fmaf(dx, fmaf(dy, B.x, fmaf(dx, A.w, A.y)), A.x));
-        const float Dv = fmaf(dy, fmaf(dy, Cc.w, Cc.x), fmaf(dx, fmaf(dy, Cc.z, fmaf(dx, Cc.y, B.w)), B.z));
-        const float vis = ex2_approx(Nv * rcp_approx(Dv));
-        const float alpha = fminf(kAlphaMax, E.x * vis);
-        if (alpha < kAlphaMin)
-            continue;
-        const float next_T = a.T * (1.0f - alpha);
-        if (next_T <= kTMin) {
-            a.done = true;
-            break;
-        }
-        const float w = alpha * a.T;
-        a.r = fmaf(w, E.y, a.r);
-        a.g = fmaf(w, E.z, a.g);
-        a.b = fmaf(w, E.w, a.b);
-        a.T = next_T;
-        a.ncon = li + 1;
-    }
+__device__ __forceinline__ float poly2(const float dx, const float dy, const float c0, const float cx,
+                                       const float cy, const float cxx, const float cxy, const float cyy) {
+    return fmaf(dx, fmaf(dx, cxx, fmaf(dy, cxy, cx)), fmaf(dy, fmaf(dy, cyy, cy), c0));
 }
 
 template <bool USE_TMA>
-__global__ void __launch_bounds__(kTilePix)
+__global__ void __launch_bounds__(kFwdThreads)
     k_blend_fwd(const RasterBuffers rb, const uint32_t width, const uint32_t height, const uint32_t tile_w,
                 const uint32_t tile_h, const bool write_ckpt, const float* __restrict__ backgrounds,
                 const uint8_t* __restrict__ masks, float* __restrict__ renders, float* __restrict__ alphas,
                 int32_t* __restrict__ last_ids) {
     __shared__ __align__(128) float4 s_rec[2][kBatch * 4];
+    __shared__ __align__(16) float4 s_state[kTilePix]; // (r, g, b, T) per pixel
+    __shared__ uint32_t s_ncon[kTilePix];
+    __shared__ uint8_t s_list[2][kTilePix];
     __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ uint32_t s_max[kTilePix / 32];
+    __shared__ uint32_t s_warp_tot[kFwdThreads / 32];
+    __shared__ uint32_t s_nact[2];
 
     const uint32_t tile = blockIdx.x, cam = blockIdx.y;
     const uint32_t n_tiles = tile_w * tile_h;
     const uint32_t ft = cam * n_tiles + tile;
     const uint32_t ty = tile / tile_w, tx = tile - ty * tile_w;
-    const uint32_t tid = threadIdx.x;
-    const uint32_t lx = tid & (kTile - 1), ly = tid >> 4;
-    const uint32_t px = tx * kTile + lx, py = ty * kTile + ly;
-    const bool inside = px < width && py < height;
-    const float dx = (float)lx - 7.5f, dy = (float)ly - 7.5f;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
     const int32_t start = rb.tile_off[ft];
     int32_t end = rb.tile_off[ft + 1];
@@ -216,16 +196,50 @@ __global__ void __launch_bounds__(kTilePix)
     const uint32_t boff = rb.bucket_off ? rb.bucket_off[ft] : 0u;
     if (write_ckpt) { // bucket -> tile map for the backward (unmasked count: bucket_off is mask-agnostic)
         const uint32_t nb = (uint32_t)(cnt_raw + kBucket - 1) / kBucket;
-        for (uint32_t k = tid; k < nb; k += kTilePix)
+        for (uint32_t k = tid; k < nb; k += kFwdThreads)
             rb.bucket_tile[boff + k] = ft;
     }
-    float4* ckpt_px = write_ckpt ? rb.ckpt + (size_t)boff * kTilePix + tid : nullptr;
+    float4* ckpt_tile = write_ckpt ? rb.ckpt + (size_t)boff * kTilePix : nullptr;
 
-    PixAcc a;
-    a.r = a.g = a.b = 0.f;
-    a.T = 1.f;
-    a.ncon = 0;
-    a.done = !inside;
+    // ---- initial state + initial active list (pixels inside the image, row-major order)
+    uint32_t keep = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t p = tid * 4 + k;
+        s_state[p] = make_float4(0.f, 0.f, 0.f, 1.f);
+        s_ncon[p] = 0;
+        const uint32_t px = tx * kTile + (p & 15u), py = ty * kTile + (p >> 4);
+        keep |= (px < width && py < height ? 1u : 0u) << k;
+    }
+    int cur = 0;
+    auto compact = [&](const uint32_t keep_mask, const uint8_t ids[4], const int dst) {
+        // block-wide exclusive scan of popc(keep_mask) over 64 threads, then scatter the kept ids
+        const uint32_t c = __popc(keep_mask);
+        uint32_t x = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= (uint32_t)o)
+                x += y;
+        }
+        if (lane == 31)
+            s_warp_tot[warp] = x;
+        __syncthreads();
+        uint32_t base = x - c;
+        if (warp == 1)
+            base += s_warp_tot[0];
+        if (tid == kFwdThreads - 1)
+            s_nact[dst] = base + c;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if ((keep_mask >> k) & 1u)
+                s_list[dst][base++] = ids[k];
+        __syncthreads();
+    };
+    {
+        const uint8_t ids[4] = {(uint8_t)(tid * 4), (uint8_t)(tid * 4 + 1), (uint8_t)(tid * 4 + 2), (uint8_t)(tid * 4 + 3)};
+        compact(keep, ids, cur);
+    }
 
     const float4* gsrc = reinterpret_cast<const float4*>(rb.inst + start);
     const int nbatch = (cnt + kBatch - 1) / kBatch;
@@ -244,85 +258,169 @@ __global__ void __launch_bounds__(kTilePix)
                 tma_load_1d(&s_rec[k][0], gsrc + (size_t)k * kBatch * 4, nrec * (uint32_t)sizeof(InstRec), &s_bar[k]);
             }
         }
-        int consumed = 0; // batches whose barrier has been waited on
-        for (int k = 0; k < nbatch; ++k) {
-            const int buf = k & 1;
-            mbar_wait(&s_bar[buf], (uint32_t)((k >> 1) & 1));
-            consumed = k + 1;
-            const int nrec = min(kBatch, cnt - k * kBatch);
-            if (!a.done)
-                blend_batch(&s_rec[buf][0], nrec, (uint32_t)(k * kBatch), dx, dy, write_ckpt, ckpt_px, a);
-            const int ndone = __syncthreads_count(a.done);
-            if (ndone == kTilePix)
-                break;
-            if (tid == 0 && k + 2 < nbatch) {
-                const uint32_t nr2 = (uint32_t)min(kBatch, cnt - (k + 2) * kBatch);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(&s_bar[buf], nr2 * (uint32_t)sizeof(InstRec));
-                tma_load_1d(&s_rec[buf][0], gsrc + (size_t)(k + 2) * kBatch * 4, nr2 * (uint32_t)sizeof(InstRec),
-                            &s_bar[buf]);
-            }
-        }
-        // early exit: one more batch may still be in flight into this CTA's shared memory -- drain it
-        if (tid == 0 && consumed < nbatch)
-            mbar_wait(&s_bar[consumed & 1], (uint32_t)((consumed >> 1) & 1));
-    } else {
-        if (nbatch > 0) {
-            if ((int)tid < min(kBatch, cnt) * 4)
-                s_rec[0][tid] = ld_nc4(gsrc + tid);
-            __syncthreads();
-        }
-        for (int k = 0; k < nbatch; ++k) {
-            const int buf = k & 1;
-            const bool has_next = k + 1 < nbatch;
-            float4 pre = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int next_f4 = has_next ? min(kBatch, cnt - (k + 1) * kBatch) * 4 : 0;
-            if ((int)tid < next_f4)
-                pre = ld_nc4(gsrc + (size_t)(k + 1) * kBatch * 4 + tid);
-            const int nrec = min(kBatch, cnt - k * kBatch);
-            if (!a.done)
-                blend_batch(&s_rec[buf][0], nrec, (uint32_t)(k * kBatch), dx, dy, write_ckpt, ckpt_px, a);
-            if ((int)tid < next_f4)
-                s_rec[buf ^ 1][tid] = pre;
-            const int ndone = __syncthreads_count(a.done);
-            if (ndone == kTilePix)
-                break;
-        }
+    } else if (nbatch > 0) {
+        const int nf4 = min(kBatch, cnt) * 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if ((int)(tid + q * kFwdThreads) < nf4)
+                s_rec[0][tid + q * kFwdThreads] = ld_nc4(gsrc + tid + q * kFwdThreads);
+        __syncthreads();
     }
 
-    if (inside) {
+    int consumed = 0;
+    for (int kb = 0; kb < nbatch; ++kb) {
+        const int buf = kb & 1;
+        const uint32_t n_act = s_nact[cur];
+        if (n_act == 0)
+            break;
+        // this thread's slice of the active list
+        uint8_t pid[4];
+        float r[4], g[4], b[4], T[4], dx[4], dy[4];
+        uint32_t ncon[4];
+        uint32_t live = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t j = tid * 4 + k;
+            pid[k] = 0;
+            if (j < n_act) {
+                pid[k] = s_list[cur][j];
+                const float4 st = s_state[pid[k]];
+                r[k] = st.x, g[k] = st.y, b[k] = st.z, T[k] = st.w;
+                ncon[k] = s_ncon[pid[k]];
+                dx[k] = (float)(pid[k] & 15u) - 7.5f;
+                dy[k] = (float)(pid[k] >> 4) - 7.5f;
+                live |= 1u << k;
+            } else {
+                r[k] = g[k] = b[k] = 0.f, T[k] = 1.f, ncon[k] = 0, dx[k] = dy[k] = 0.f;
+            }
+        }
+        const uint32_t mine = live;
+
+        float4 pre[4];
+        int next_f4 = 0;
+        if (USE_TMA) {
+            mbar_wait(&s_bar[buf], (uint32_t)((kb >> 1) & 1));
+            consumed = kb + 1;
+        } else {
+            next_f4 = (kb + 1 < nbatch) ? min(kBatch, cnt - (kb + 1) * kBatch) * 4 : 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if ((int)(tid + q * kFwdThreads) < next_f4)
+                    pre[q] = ld_nc4(gsrc + (size_t)(kb + 1) * kBatch * 4 + tid + q * kFwdThreads);
+        }
+
+        if (live) {
+            const float4* s = &s_rec[buf][0];
+            const int nrec = min(kBatch, cnt - kb * kBatch);
+            const uint32_t first_li = (uint32_t)(kb * kBatch);
+            for (int t = 0; t < nrec; ++t) {
+                const uint32_t li = first_li + t;
+                if (write_ckpt && (li & (kBucket - 1)) == 0) {
+                    float4* c = ckpt_tile + (size_t)(li >> 5) * kTilePix;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if ((live >> k) & 1u)
+                            c[pid[k]] = make_float4(r[k], g[k], b[k], T[k]);
+                }
+                const float4 A = s[4 * t], B = s[4 * t + 1], Cc = s[4 * t + 2], E = s[4 * t + 3];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float Nv = poly2(dx[k], dy[k], A.x, A.y, A.z, A.w, B.x, B.y);
+                    const float Dv = poly2(dx[k], dy[k], B.z, B.w, Cc.x, Cc.y, Cc.z, Cc.w);
+                    const float vis = ex2_approx(Nv * rcp_approx(Dv));
+                    const float alpha = fminf(kAlphaMax, E.x * vis);
+                    if (((live >> k) & 1u) && alpha >= kAlphaMin) {
+                        const float next_T = T[k] * (1.0f - alpha);
+                        if (next_T <= kTMin) {
+                            live &= ~(1u << k);
+                        } else {
+                            const float w = alpha * T[k];
+                            r[k] = fmaf(w, E.y, r[k]);
+                            g[k] = fmaf(w, E.z, g[k]);
+                            b[k] = fmaf(w, E.w, b[k]);
+                            T[k] = next_T;
+                            ncon[k] = li + 1;
+                        }
+                    }
+                }
+                if (live == 0)
+                    break;
+            }
+        }
+        // write back the pixels this thread owned in this batch
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if ((mine >> k) & 1u) {
+                s_state[pid[k]] = make_float4(r[k], g[k], b[k], T[k]);
+                s_ncon[pid[k]] = ncon[k];
+            }
+        if (!USE_TMA) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if ((int)(tid + q * kFwdThreads) < next_f4)
+                    s_rec[buf ^ 1][tid + q * kFwdThreads] = pre[q];
+        }
+        // rebuild the active list only when some pixel finished in this batch (compact() syncs the block)
+        const int changed = __syncthreads_or((int)(live != mine));
+        if (changed) {
+            compact(live, pid, cur ^ 1);
+            cur ^= 1;
+        }
+        if (USE_TMA && tid == 0 && kb + 2 < nbatch && s_nact[cur] != 0) {
+            const uint32_t nr2 = (uint32_t)min(kBatch, cnt - (kb + 2) * kBatch);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&s_bar[buf], nr2 * (uint32_t)sizeof(InstRec));
+            tma_load_1d(&s_rec[buf][0], gsrc + (size_t)(kb + 2) * kBatch * 4, nr2 * (uint32_t)sizeof(InstRec),
+                        &s_bar[buf]);
+        }
+    }
+    // early exit: one more batch may still be in flight into this CTA's shared memory -- drain it
+    if (USE_TMA && tid == 0 && consumed < nbatch && consumed >= 1)
+        mbar_wait(&s_bar[consumed & 1], (uint32_t)((consumed >> 1) & 1));
+    if (USE_TMA && tid == 0 && consumed == 0 && nbatch > 0) { // loop never ran (no active pixel): drain both
+        mbar_wait(&s_bar[0], 0u);
+        if (nbatch > 1)
+            mbar_wait(&s_bar[1], 0u);
+    }
+    __syncthreads();
+
+    // ---- outputs: thread t writes its 4 row-adjacent pixels (64 B contiguous per thread)
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t p = tid * 4 + k;
+        const uint32_t px = tx * kTile + (p & 15u), py = ty * kTile + (p >> 4);
+        if (!(px < width && py < height))
+            continue;
+        const float4 st = s_state[p];
+        const uint32_t nc = s_ncon[p];
+        m = max(m, nc);
         const size_t pix = ((size_t)cam * height + py) * width + px;
-        rb.pix_state[pix] = make_float4(a.r, a.g, a.b, a.T);
-        rb.n_contrib[pix] = (int32_t)a.ncon;
+        rb.pix_state[pix] = st;
+        rb.n_contrib[pix] = (int32_t)nc;
         if (renders) {
             float br = 0.f, bgc = 0.f, bb = 0.f;
             if (backgrounds) {
                 br = backgrounds[cam * 3], bgc = backgrounds[cam * 3 + 1], bb = backgrounds[cam * 3 + 2];
             }
-            renders[pix * 3] = fmaf(a.T, br, a.r);
-            renders[pix * 3 + 1] = fmaf(a.T, bgc, a.g);
-            renders[pix * 3 + 2] = fmaf(a.T, bb, a.b);
+            renders[pix * 3] = fmaf(st.w, br, st.x);
+            renders[pix * 3 + 1] = fmaf(st.w, bgc, st.y);
+            renders[pix * 3 + 2] = fmaf(st.w, bb, st.z);
         }
         if (alphas)
-            alphas[pix] = 1.0f - a.T;
+            alphas[pix] = 1.0f - st.w;
         if (last_ids)
-            last_ids[pix] = a.ncon > 0 ? start + (int32_t)a.ncon - 1 : 0;
+            last_ids[pix] = nc > 0 ? start + (int32_t)nc - 1 : 0;
     }
     // per-tile maximum contributor count (lets the backward skip whole buckets)
-    uint32_t m = a.ncon;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
         m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((tid & 31) == 0)
-        s_max[tid >> 5] = m;
+    if (lane == 0)
+        s_warp_tot[warp] = m;
     __syncthreads();
-    if (tid == 0) {
-        uint32_t mm = 0;
-#pragma unroll
-        for (int w = 0; w < kTilePix / 32; ++w)
-            mm = max(mm, s_max[w]);
-        rb.tile_max_contrib[ft] = mm;
-    }
+    if (tid == 0)
+        rb.tile_max_contrib[ft] = max(s_warp_tot[0], s_warp_tot[1]);
 }
 
 int launch_blend_fwd(const RasterBuffers& rb, uint32_t C, uint32_t width, uint32_t height, uint32_t tile_w,
@@ -332,10 +430,10 @@ int launch_blend_fwd(const RasterBuffers& rb, uint32_t C, uint32_t width, uint32
         return LFS_OK;
     dim3 grid(tile_w * tile_h, C);
     if (raster_options().use_tma)
-        k_blend_fwd<true><<<grid, kTilePix, 0, stream>>>(rb, width, height, tile_w, tile_h, write_ckpt, backgrounds,
+        k_blend_fwd<true><<<grid, kFwdThreads, 0, stream>>>(rb, width, height, tile_w, tile_h, write_ckpt, backgrounds,
                                                          masks, renders, alphas, last_ids);
     else
-        k_blend_fwd<false><<<grid, kTilePix, 0, stream>>>(rb, width, height, tile_w, tile_h, write_ckpt, backgrounds,
+        k_blend_fwd<false><<<grid, kFwdThreads, 0, stream>>>(rb, width, height, tile_w, tile_h, write_ckpt, backgrounds,
                                                           masks, renders, alphas, last_ids);
     LFS_LAUNCH_OK("k_blend_fwd");
     return LFS_OK;
@@ -405,24 +503,41 @@ __global__ void __launch_bounds__(kBwdWarps * 32)
 
     const float4* ck = rb.ckpt + (size_t)b * kTilePix;
 
-    for (int i = 0; i < kTilePix + 31; ++i) {
-        if ((i & 31) == 0 && i < kTilePix) {
-            __syncwarp();
-            const int p = i + lane;
+    // compact list of the tile's pixels that reach this bucket (n_contrib > first instance of the bucket):
+    // late buckets are reached by few pixels, so the rotation below runs m + 31 instead of 256 + 31 steps
+    __shared__ uint8_t s_pix[kBwdWarps][kTilePix];
+    int m = 0;
+    {
+        const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+        for (int rr = 0; rr < kTilePix / 32; ++rr) {
+            const int p = rr * 32 + lane;
             const uint32_t px = tx * kTile + (p & 15), py = ty * kTile + (p >> 4);
+            bool kp = false;
+            if (px < width && py < height)
+                kp = (uint32_t)__ldg(rb.n_contrib + ((size_t)cam * height + py) * width + px) > local_b * kBucket;
+            const uint32_t mask = __ballot_sync(0xffffffffu, kp);
+            if (kp)
+                s_pix[warp][m + __popc(mask & lt)] = (uint8_t)p;
+            m += __popc(mask);
+        }
+        __syncwarp();
+    }
+
+    for (int i = 0; i < m + 31; ++i) {
+        if ((i & 31) == 0 && i < m) {
+            __syncwarp();
             float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a4;
             int32_t nc = 0;
-            if (px < width && py < height) {
+            if (i + lane < m) {
+                const int p = s_pix[warp][i + lane];
+                const uint32_t px = tx * kTile + (p & 15), py = ty * kTile + (p >> 4);
                 const size_t pix = ((size_t)cam * height + py) * width + px;
-                nc = __ldg(rb.n_contrib + pix);
-                if ((uint32_t)nc > local_b * kBucket) { // this pixel reaches the bucket: checkpoint is valid
-                    const float4 c4 = ld_nc4(ck + p);
-                    const float4 f4 = __ldg(rb.pix_state + pix);
-                    a4 = make_float4(f4.x - c4.x, f4.y - c4.y, f4.z - c4.z, c4.w);
-                    b4 = __ldg(v_pix + pix);
-                } else {
-                    nc = 0;
-                }
+                nc = (int32_t)((uint32_t)__ldg(rb.n_contrib + pix) | ((uint32_t)p << 24)); // pixel id rides in the top byte (n_contrib < 2^24)
+                const float4 c4 = ld_nc4(ck + p);
+                const float4 f4 = __ldg(rb.pix_state + pix);
+                a4 = make_float4(f4.x - c4.x, f4.y - c4.y, f4.z - c4.z, c4.w);
+                b4 = __ldg(v_pix + pix);
             }
             sA[warp][lane] = a4;
             sB[warp][lane] = b4;
@@ -441,7 +556,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32)
             ga = __shfl_up_sync(0xffffffffu, ga, 1);
         }
         if (lane == 0) {
-            if (i < kTilePix) {
+            if (i < m) {
                 const float4 a4 = sA[warp][i & 31], b4 = sB[warp][i & 31];
                 ncon = sN[warp][i & 31];
                 car = a4.x, cag = a4.y, cab = a4.z, T = a4.w;
@@ -450,13 +565,15 @@ __global__ void __launch_bounds__(kBwdWarps * 32)
                 ncon = 0;
             }
         }
-        const int idx = i - lane;
-        const bool active = valid && idx >= 0 && idx < kTilePix && (int32_t)li < ncon;
+        const int idx = i - lane; // position in the compact list of the pixel currently at this lane
+        const uint32_t ucode = (uint32_t)ncon;
+        const int pcode = (int)(ucode >> 24), nc_px = (int)(ucode & 0xFFFFFFu);
+        const bool active = valid && idx >= 0 && idx < m && (int32_t)li < nc_px;
         if (!active)
             continue;
-        const float dx = (float)(idx & 15) - 7.5f, dy = (float)(idx >> 4) - 7.5f;
-        const float Nv = fmaf(dy, fmaf(dy, B.y, A.z), fmaf(dx, fmaf(dy, B.x, fmaf(dx, A.w, A.y)), A.x));
-        const float Dv = fmaf(dy, fmaf(dy, Cc.w, Cc.x), fmaf(dx, fmaf(dy, Cc.z, fmaf(dx, Cc.y, B.w)), B.z));
+        const float dx = (float)(pcode & 15) - 7.5f, dy = (float)(pcode >> 4) - 7.5f;
+        const float Nv = poly2(dx, dy, A.x, A.y, A.z, A.w, B.x, B.y);
+        const float Dv = poly2(dx, dy, B.z, B.w, Cc.x, Cc.y, Cc.z, Cc.w);
         const float rD = rcp_approx(Dv);
         const float p2 = Nv * rD;
         const float vis = ex2_approx(p2);

@@ -15,6 +15,7 @@
 #include "forward.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <functional>
 #include <tuple>
@@ -24,11 +25,15 @@ namespace {
         char* ptr = nullptr;
         size_t cap = 0;
         char* resize(size_t n) {
+            if (getenv("REF_FASTGS_DEBUG"))
+                fprintf(stderr, "[ref_fastgs] resize request %zu bytes (cap %zu)\n", n, cap);
             if (n > cap) {
                 if (ptr)
                     cudaFree(ptr);
                 size_t want = n + n / 4 + 256;
-                if (cudaMalloc(&ptr, want) != cudaSuccess) {
+                cudaError_t e = cudaMalloc(&ptr, want);
+                if (e != cudaSuccess) {
+                    fprintf(stderr, "[ref_fastgs] cudaMalloc(%zu) failed: %s\n", want, cudaGetErrorString(e));
                     ptr = nullptr;
                     cap = 0;
                     return nullptr;
@@ -66,6 +71,11 @@ int ref_fastgs_forward(void* h, const float* means, const float* scales_raw, con
                        int active_sh_bases, int total_bases_sh_rest, int width, int height, float fx, float fy,
                        float cx, float cy, float near_plane, float far_plane, int* out_counts) {
     Ctx* c = static_cast<Ctx*>(h);
+    {
+        cudaError_t pre = cudaGetLastError(); // do not inherit a stale error from the caller
+        if (pre != cudaSuccess)
+            fprintf(stderr, "[ref_fastgs] stale CUDA error before forward: %s\n", cudaGetErrorString(pre));
+    }
     auto f_prim = [c](size_t n) { return c->prim.resize(n); };
     auto f_tile = [c](size_t n) { return c->tile.resize(n); };
     auto f_inst = [c](size_t n) { return c->inst.resize(n); };

@@ -194,7 +194,8 @@ def diag_adam(n=100003):
     tp, tm, tv, tg = T(p), T(m), T(v), T(g)
     args = (1e-3, 0.9, 0.999, 1e-15, 1.0 / (1 - 0.9 ** 3), 1.0 / np.sqrt(1 - 0.999 ** 3))
     ops.adam_step(tp, tm, tv, tg, *args)
-    op_, om, ov = O.adam_step(p, m, v, g, *args)
+    f32 = lambda x: float(np.float32(x))  # the kernel (like the reference's) receives fp32-rounded scalars
+    op_, om, ov = O.adam_step(p, m, v, g, *[f32(x) for x in args])
     out = {"param_rel": relerr(tp.cpu().numpy(), op_), "m_rel": relerr(tm.cpu().numpy(), om),
            "v_rel": relerr(tv.cpu().numpy(), ov),
            "update_rel": relerr(tp.cpu().numpy() - p, op_ - p)}
@@ -232,6 +233,27 @@ def diag_trainer(n=3000, w=240, h=160, deg=3, views=2, seed=21, tma=1):
         out[f"v{v}_n_inst_oracle"] = int(len(r["flatten_ids"]))
         out[f"v{v}_image_rel"] = relerr(img.cpu().numpy(), r["renders"][0])
         out[f"v{v}_alpha_rel"] = relerr(alpha.cpu().numpy(), r["alphas"][0, :, :, 0])
+        # the same view through the gsplat-surface ops (same device code, composed by the caller as
+        # rasterizer.cpp:208-360 does) must agree with the fused step to rounding
+        pm, pq, ps, po, pshs = sc.activated()
+        tm_, tq_, ts_, to_ = T(pm), T(pq), T(ps), T(po)
+        tvm, tK = T(sc.viewmats[v:v + 1]), T(sc.Ks[v:v + 1])
+        rad, m2d, dep, con, _ = ops.projection_ut_3dgs_fused(tm_, tq_, ts_, to_, tvm, None, tK, w, h, 0.3, 0.01, 1e4,
+                                                            0.0, False)
+        campos = torch.linalg.inv(tvm[0])[:3, 3]
+        dirs = (tm_ - campos[None]).contiguous()
+        msk = (rad[0] > 0).all(-1).contiguous()
+        cols = ops.spherical_harmonics_fwd(deg, dirs, T(pshs), msk)
+        cols = torch.where(msk[:, None], torch.clamp_min(cols + 0.5, 0.0), torch.zeros_like(cols))
+        tw_, th_ = (w + 15) // 16, (h + 15) // 16
+        _, ids_, flat_ = ops.intersect_tile(m2d, rad, dep, None, None, 1, 16, tw_, th_, True)
+        offs_ = ops.intersect_offset(ids_, 1, tw_, th_)
+        ren_, al_, _ = ops.rasterize_to_pixels_from_world_3dgs_fwd(
+            tm_, tq_, ts_, cols[None].contiguous(), to_[None].contiguous(), T(np.array([bg])), None, w, h, 16, tvm,
+            None, tK, tile_offsets=offs_, flatten_ids=flat_)
+        out[f"v{v}_n_inst_ops"] = int(flat_.numel())
+        out[f"v{v}_image_vs_ops_rel"] = relerr(img.cpu().numpy(), ren_[0].cpu().numpy())
+        out[f"v{v}_alpha_vs_ops_rel"] = relerr(alpha.cpu().numpy(), al_[0, :, :, 0].cpu().numpy())
         for k in tot:
             tot[k] += g[k]
     grads = tr.export_grads()
@@ -248,11 +270,43 @@ def diag_trainer(n=3000, w=240, h=160, deg=3, views=2, seed=21, tma=1):
     p1 = tr.export_params()
     worst = 0.0
     for k in p0:
-        want, _, _ = O.adam_step(p0[k], np.zeros_like(p0[k]), np.zeros_like(p0[k]), g0[k], lrs[k], 0.9, 0.999, 1e-15,
-                                 1.0 / (1 - 0.9), 1.0 / np.sqrt(1 - 0.999))
+        f32 = lambda x: float(np.float32(x))
+        want, _, _ = O.adam_step(p0[k], np.zeros_like(p0[k]), np.zeros_like(p0[k]), g0[k], f32(lrs[k]), f32(0.9),
+                                 f32(0.999), f32(1e-15), f32(1.0 / (1 - 0.9)), f32(1.0 / np.sqrt(1 - 0.999)))
         worst = max(worst, relerr(p1[k].cpu().numpy().reshape(-1) - p0[k].reshape(-1), want - p0[k].reshape(-1)))
     out["adam_update_rel"] = worst
     out["grads_cleared"] = bool(float(tr.grads.abs().max().item()) == 0.0)
+    return out
+
+
+def diag_ref_fastgs(n=5000, w=320, h=240, deg=3):
+    """Runs the UNMODIFIED reference fastgs CUDA path (EWA) on a small scene: sanity of oracle/_ref/libfastgs_ref.so
+    and of its glue, and a coarse cross-check of the two algorithms (EWA vs 3DGUT render the same scene alike)."""
+    out = {}
+    if not R.have_fastgs():
+        return {"unavailable": True}
+    sc = scene.make_scene(n, 1, w, h, deg, seed=8, sigma_px=3.5)
+    fg = R.FastGS()
+    w2c = T(sc.viewmats[0])
+    campos = T(np.linalg.inv(sc.viewmats[0].astype(np.float64))[:3, 3])
+    fx, fy, cx, cy = [float(x) for x in (sc.Ks[0, 0, 0], sc.Ks[0, 1, 1], sc.Ks[0, 0, 2], sc.Ks[0, 1, 2])]
+    P = dict(means=T(sc.means), scales=T(sc.scaling), rot=T(sc.rotation), op=T(sc.opacity), sh0=T(sc.sh0), shN=T(sc.shN))
+    img, alpha, counts = fg.forward(P["means"], P["scales"], P["rot"], P["op"], P["sh0"], P["shN"], w2c, campos,
+                                    (deg + 1) ** 2, w, h, fx, fy, cx, cy)
+    torch.cuda.synchronize()
+    out["counts"] = list(counts)
+    out["image_finite"] = bool(torch.isfinite(img).all())
+    gimg = torch.randn_like(img)
+    g = fg.backward(gimg, torch.zeros_like(alpha), img, alpha, P["means"], P["scales"], P["rot"], P["shN"], w2c, campos,
+                    (deg + 1) ** 2, w, h, fx, fy, cx, cy)
+    torch.cuda.synchronize()
+    out["grads_finite"] = bool(all(torch.isfinite(v).all() for v in g.values()))
+    out["grad_means_absmax"] = float(g["means"].abs().max())
+    tr = SplatTrainer(n, w, h, deg, DEV)
+    tr.load_scene(sc)
+    ours, oa = tr.forward(sc.viewmats[0], sc.Ks[0], deg, (0, 0, 0), want_image=True)
+    out["ewa_vs_gut_image_mean_abs_diff"] = float((ours.permute(2, 0, 1) - img).abs().mean())
+    out["ewa_vs_gut_alpha_mean_abs_diff"] = float((oa - alpha[0]).abs().mean())
     return out
 
 
@@ -262,7 +316,7 @@ def run_all(fast=False):
     for name, fn in (("projection", diag_projection), ("sh", diag_sh), ("intersect", diag_intersect),
                      ("raster_tma0", lambda: diag_raster(tma=0)), ("raster_tma1", lambda: diag_raster(tma=1)),
                      ("raster_nobg_dense", lambda: diag_raster(n=4000, w=96, h=80, seed=4, sigma_px=7.0, with_bg=False)),
-                     ("adam", diag_adam), ("trainer", diag_trainer),
+                     ("adam", diag_adam), ("trainer", diag_trainer), ("ref_fastgs", diag_ref_fastgs),
                      ("trainer_tma0", lambda: diag_trainer(n=1200, w=100, h=84, deg=2, views=1, seed=2, tma=0))):
         try:
             t = time.time()

@@ -1,0 +1,27 @@
+"""Runs a few fused view steps of the C3 workload (for ncu / nsight captures):
+   ncu --set full --clock-control none --import-source on -k regex:k_blend -s 4 -c 4 -o gpurun_out/prof python tools/profile_view.py
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from lichtfeld_studio_b200 import scene as S  # noqa: E402
+from lichtfeld_studio_b200.trainer import SplatTrainer  # noqa: E402
+
+cfg = sys.argv[1] if len(sys.argv) > 1 else "C3"
+views = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+n, _, W, H, deg = S.CONFIGS[cfg]
+sc = S.make_scene(n, views, W, H, deg, seed=42)
+tr = SplatTrainer(n, W, H, deg, "cuda:0", instance_capacity=int(os.environ.get("LFS_INST_CAP", "12000000")))
+tr.load_scene(sc)
+tg = [torch.as_tensor(S.make_target(v, W, H)).cuda() for v in range(views)]
+for it in range(2):
+    for v in range(views):
+        tr.forward(sc.viewmats[v], sc.Ks[v], deg)
+        tr.loss_l1(tg[v])
+        tr.backward()
+    tr.adam_step()
+torch.cuda.synchronize()
+print("instances", tr.stats())
