@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--views-per-gpu", type=int, default=0)
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / reference_gpu legs")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
-    ap.add_argument("--ref-gpu-leg", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--ref-gpu-leg", default="", choices=["", "fastgs", "gsplat"], help=argparse.SUPPRESS)
     return ap.parse_args()
 
 
@@ -196,6 +196,90 @@ def reference_gpu_leg(sc, steps: int, warmup: int, device):
             "note": "targets resident in HBM; loss gradient by torch elementwise ops; includes its 3 blocking D2H reads"}
 
 
+def reference_gsplat_gpu_leg(sc, steps: int, warmup: int, device):
+    """UNMODIFIED reference gsplat (3DGUT) CUDA path (oracle/_ref/libgsplat_ref.so, built against oracle/glm_shim):
+    per view projection_ut -> SH fwd -> intersect_tile (+CUB sort) -> intersect_offset -> rasterize fwd -> L1
+    gradient -> rasterize bwd -> SH bwd, i.e. the kernel sequence of src/training/rasterization/rasterizer.cpp:208-360
+    and its autograd backward, with the SplatData activations done by torch as the reference does; then the
+    reference's 6 fused-Adam launches.  The torch autograd bookkeeping of the reference is NOT included (this is a
+    lower bound of the reference's step time)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import torch
+
+    import ref_libs as R
+    if not R.have_gsplat():
+        return {"unavailable": "oracle/_ref/libgsplat_ref.so not present"}
+    T = lambda x: torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float32, device=device)
+    P = dict(means=T(sc.means), sh0=T(sc.sh0), shN=T(sc.shN), scales=T(sc.scaling), rot=T(sc.rotation), op=T(sc.opacity))
+    W, H, deg = sc.width, sc.height, sc.sh_degree
+    V = sc.viewmats.shape[0]
+    tw, th = (W + 15) // 16, (H + 15) // 16
+    from lichtfeld_studio_b200 import scene as S
+    tg = [torch.as_tensor(S.make_target(v, W, H)).to(device).float().div_(255.0).contiguous() for v in range(min(V, 8))]
+    cams = [(T(sc.viewmats[v:v + 1]), T(sc.Ks[v:v + 1]),
+             T(np.linalg.inv(sc.viewmats[v].astype(np.float64))[:3, 3])) for v in range(V)]
+    scale = 1.0 / (3.0 * W * H)
+    fg = R.FastGS() if R.have_fastgs() else None
+    state = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in P.items()}
+    lrs = dict(means=0.00016, sh0=0.0025, shN=0.0025 / 20, scales=0.005, rot=0.001, op=0.05)
+    n_isects = []
+
+    def step(t):
+        acc = {k: torch.zeros_like(v) for k, v in P.items()}
+        for v in range(V):
+            vm, K, campos = cams[v]
+            # SplatData getters (src/core/splat_data.cpp:267-286)
+            opac = torch.sigmoid(P["op"]).squeeze(-1)
+            scl = torch.exp(P["scales"])
+            quat = torch.nn.functional.normalize(P["rot"], dim=-1)
+            shs = torch.cat([P["sh0"], P["shN"]], dim=1).contiguous()
+            radii, m2d, dep, con, _ = R.projection_ut(P["means"], quat, scl, opac, vm, K, W, H)
+            dirs = (P["means"] - campos[None]).contiguous()
+            masks = (radii[0] > 0).all(-1).contiguous()
+            cols = R.sh_fwd(deg, dirs, shs, masks)
+            colors = torch.clamp_min(cols + 0.5, 0.0)
+            _, ids, flat = R.intersect_tile(m2d, radii, dep, 16, tw, th, True)
+            offs = R.intersect_offset(ids, 1, tw, th)
+            if len(n_isects) < V:
+                n_isects.append(int(flat.numel()))
+            ren, al, li = R.raster_fwd(P["means"], quat, scl, colors[None].contiguous(), opac[None].contiguous(), None,
+                                       W, H, 16, vm, K, offs, flat)
+            v_ren = (torch.sign(ren[0] - tg[v % len(tg)]) * scale)[None].contiguous()
+            v_al = torch.zeros_like(al)
+            vmn, vq, vs, vc, vo = R.raster_bwd(P["means"], quat, scl, colors[None].contiguous(), opac[None].contiguous(),
+                                               None, W, H, 16, vm, K, offs, flat, al, li, v_ren, v_al)
+            vcol = vc[0] * (cols + 0.5 >= 0)
+            v_shs, v_dirs = R.sh_bwd(deg, dirs, shs, vcol.contiguous(), masks, True)
+            # activation VJPs (what torch autograd does for the reference)
+            acc["means"] += vmn + v_dirs
+            acc["sh0"] += v_shs[:, :1]
+            acc["shN"] += v_shs[:, 1:]
+            acc["scales"] += vs * scl
+            dq = (vq * quat).sum(-1, keepdim=True)
+            acc["rot"] += (vq - dq * quat) / P["rot"].norm(dim=-1, keepdim=True).clamp_min(1e-12)
+            acc["op"] += (vo[0] * opac * (1 - opac))[:, None]
+        bc1, bc2 = 1.0 / (1.0 - 0.9 ** t), 1.0 / (1.0 - 0.999 ** t) ** 0.5
+        for k in ("means", "sh0", "shN", "scales", "rot", "op"):
+            if fg is not None:
+                fg.adam_step(P[k], state[k][0], state[k][1], acc[k].contiguous(), lrs[k], 0.9, 0.999, 1e-15, bc1, bc2)
+
+    for i in range(warmup):
+        step(i + 1)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(warmup + i + 1)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"impl": "reference gsplat (3DGUT) CUDA kernels, unmodified, built against oracle/glm_shim, sm_100a, "
+                    "--use_fast_math; kernel sequence of rasterizer.cpp without the autograd bookkeeping",
+            "value": V / ms * 1e3, "unit": UNIT, "ms_per_step": ms, "views_per_step": V,
+            "instances_per_view": float(np.mean(n_isects)) if n_isects else None}
+
+
 # ------------------------------------------------------------------------------------------------------------------
 def main():
     a = parse()
@@ -213,7 +297,8 @@ def main():
     if a.ref_gpu_leg:  # child process: time the unmodified reference CUDA build and print one JSON object
         import torch
         sc = S.make_scene(n, vpg, W, H, deg, seed=42)
-        print("REFGPU " + json.dumps(reference_gpu_leg(sc, max(2, min(a.steps, 4)), 1, torch.device("cuda:0"))))
+        fn = reference_gpu_leg if a.ref_gpu_leg == "fastgs" else reference_gsplat_gpu_leg
+        print("REFGPU " + json.dumps(fn(sc, max(2, min(a.steps, 4)), 1, torch.device("cuda:0"))))
         return 0
 
     if a.impl == "reference":
@@ -252,6 +337,7 @@ def main():
 
     tr = SplatTrainer(n, W, H, deg, device)
     tr.load_scene(sc)
+    tr.iteration = 1000  # steady state: the reference skips the shN group only for iteration <= 1000
     # capacity calibration (one forward per local view, with sync) -- outside every timed region
     need = 0
     for v in my_views:
@@ -268,6 +354,7 @@ def main():
         torch.cuda.empty_cache()
         tr = SplatTrainer(n, W, H, deg, device, instance_capacity=new_cap)
         tr.load_scene(sc)
+        tr.iteration = 1000
     n_inst_per_view = []
     for v in my_views:
         tr.forward(sc.viewmats[v], sc.Ks[v], deg)
@@ -375,11 +462,14 @@ def main():
         try:  # separate process: a fault inside the reference build must not take the bench down
             del tr
             torch.cuda.empty_cache()
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--ref-gpu-leg", "--config", a.config,
-                                "--n-gaussians", str(a.n_gaussians), "--views-per-gpu", str(vpg), "--steps",
-                                str(a.steps)], capture_output=True, text=True, timeout=600)
-            got = [l for l in r.stdout.splitlines() if l.startswith("REFGPU ")]
-            line["reference_gpu"] = json.loads(got[-1][7:]) if got else {"error": (r.stderr or r.stdout)[-400:]}
+            line["reference_gpu"] = {}
+            for which in ("gsplat", "fastgs"):
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--ref-gpu-leg", which, "--config",
+                                    a.config, "--n-gaussians", str(a.n_gaussians), "--views-per-gpu", str(vpg),
+                                    "--steps", str(a.steps)], capture_output=True, text=True, timeout=600)
+                got = [l for l in r.stdout.splitlines() if l.startswith("REFGPU ")]
+                line["reference_gpu"][which] = (json.loads(got[-1][7:]) if got
+                                                else {"error": (r.stderr or r.stdout).strip().splitlines()[-1][:300]})
         except Exception as e:
             line["reference_gpu"] = {"error": repr(e)}
     print(json.dumps(line))

@@ -77,7 +77,17 @@ int ref_fastgs_forward(void* h, const float* means, const float* scales_raw, con
             fprintf(stderr, "[ref_fastgs] stale CUDA error before forward: %s\n", cudaGetErrorString(pre));
     }
     auto f_prim = [c](size_t n) { return c->prim.resize(n); };
-    auto f_tile = [c](size_t n) { return c->tile.resize(n); };
+    // The reference zeroes PerTileBuffers::instance_ranges with cudaMemsetAsync on a private static stream
+    // (fastgs/rasterization/src/forward.cu:48-55).  On this image (CUDA 12.9 runtime inside a torch process)
+    // that call returns cudaErrorInvalidValue (compute-sanitizer, profiles/r01_ref_fastgs_memset.txt), the ranges of
+    // empty tiles stay uninitialised and n_buckets becomes garbage.  Zeroing the whole per-tile blob here, right
+    // before the reference carves it, gives the state the reference intends without touching its sources.
+    auto f_tile = [c](size_t n) {
+        char* p = c->tile.resize(n);
+        if (p)
+            cudaMemset(p, 0, n);
+        return p;
+    };
     auto f_inst = [c](size_t n) { return c->inst.resize(n); };
     auto f_bucket = [c](size_t n) { return c->bucket.resize(n); };
     auto r = fast_gs::rasterization::forward(
@@ -86,6 +96,11 @@ int ref_fastgs_forward(void* h, const float* means, const float* scales_raw, con
         reinterpret_cast<const float3*>(sh0), reinterpret_cast<const float3*>(shN),
         reinterpret_cast<const float4*>(w2c), reinterpret_cast<const float3*>(cam_position), image, alpha,
         n_primitives, active_sh_bases, total_bases_sh_rest, width, height, fx, fy, cx, cy, near_plane, far_plane);
+    {
+        cudaError_t e = cudaGetLastError(); // swallow the reference's failed cudaMemsetAsync (see above)
+        if (e != cudaSuccess && e != cudaErrorInvalidValue)
+            return (int)e;
+    }
     c->n_visible = std::get<0>(r);
     c->n_instances = std::get<1>(r);
     c->n_buckets = std::get<2>(r);
@@ -96,7 +111,7 @@ int ref_fastgs_forward(void* h, const float* means, const float* scales_raw, con
         out_counts[1] = c->n_instances;
         out_counts[2] = c->n_buckets;
     }
-    return (int)cudaGetLastError();
+    return (int)cudaDeviceSynchronize();
 }
 
 // Gradient outputs must be zero-initialised by the caller exactly as backward_wrapper does
