@@ -10,4 +10,4 @@ All compute goes through liblfs_b200.so (C ABI: include/lfs_b200.h); there is no
 from . import _lib  # noqa: F401
 from ._lib import LfsError, LfsUnsupported, UTParams, build, load  # noqa: F401
 
-__all__ = ["_lib", "ops", "trainer", "scene", "LfsError", "LfsUnsupported", "UTParams", "build", "load"]
+__all__ = ["_lib", "ops", "trainer", "scene", "dp", "LfsError", "LfsUnsupported", "UTParams", "build", "load"]

@@ -17,7 +17,7 @@ from typing import Optional, Sequence
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, dp
 from ._lib import IMG_U8_HWC, TrainerDesc, UTParams, check, load
 
 GROUPS = ("means", "sh0", "shN", "scaling", "rotation", "opacity")  # strategies/strategy_utils.cpp:35-40
@@ -191,7 +191,7 @@ class SplatTrainer:
         views rank, rank + world_size, ...  Host->device copies run on a side stream, double buffered."""
         main = torch.cuda.current_stream(self.device)
         self.loss_dev.zero_()
-        my_views = list(range(rank, len(targets_pinned), world_size))
+        my_views = dp.shard_views(len(targets_pinned), world_size, rank)
         for i, v in enumerate(my_views):
             slot = i & 1
             with torch.cuda.stream(self.copy_stream):
@@ -205,9 +205,8 @@ class SplatTrainer:
             self._tgt_free[slot].record(main)
             self.backward()
         if world_size > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)
-            dist.all_reduce(self.loss_dev, op=dist.ReduceOp.SUM)
+            dp.allreduce_sum_(self.grads)  # ONE collective over the flat planar gradient arena
+            dp.allreduce_sum_(self.loss_dev)
         self.adam_step()
         if read_loss:
             self._loss_pinned.copy_(self.loss_dev, non_blocking=True)
