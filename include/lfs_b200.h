@@ -171,6 +171,18 @@ int lfs_adam_step_multi(float* params, float* exp_avg, float* exp_avg_sq, float*
                         void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * small per-Gaussian ops of the densification strategies (off the steady-state hot path)
+ * ------------------------------------------------------------------------------------------------------- */
+/* gsplat::quats_to_rotmats (gsplat/Ops.h:46-48): quats [N,4] wxyz -> rotmats [N,3,3] row-major */
+int lfs_quats_to_rotmats(const float* quats, uint32_t n, float* rotmats, void* stream);
+/* gsplat::relocation (gsplat/Ops.h:52-57): opacities [N], scales [N,3], ratios [N] i32, binoms [n_max,n_max] */
+int lfs_relocation(const float* opacities, const float* scales, const int32_t* ratios, const float* binoms,
+                   int n_max, uint32_t n, float* new_opacities, float* new_scales, void* stream);
+/* gsplat::add_noise (gsplat/Ops.h:59-65): means [N,3] updated in place */
+int lfs_add_noise(const float* raw_opacities, const float* raw_scales, const float* raw_quats, const float* noise,
+                  float* means, float current_lr, uint32_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * fused training step (the fast path; what bench.py times)
  *
  * Plays the role of gs::training::rasterize + GUTRasterizationFunction / SphericalHarmonicsFunction forward

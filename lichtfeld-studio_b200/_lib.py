@@ -103,6 +103,9 @@ SIGNATURES = {
         [_vp, _vp, _vp, _vp, C.c_int, C.POINTER(_i64), C.POINTER(_f), C.POINTER(_f), C.POINTER(_f), _f, _f, _f,
          C.c_int, _vp],
     ),
+    "lfs_quats_to_rotmats": (C.c_int, [_vp, _u32, _vp, _vp]),
+    "lfs_relocation": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _u32, _vp, _vp, _vp]),
+    "lfs_add_noise": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _f, _u32, _vp]),
     "lfs_trainer_arena_floats": (C.c_uint64, [C.POINTER(TrainerDesc)]),
     "lfs_trainer_create": (_vp, [C.POINTER(TrainerDesc)]),
     "lfs_trainer_destroy": (None, [_vp]),

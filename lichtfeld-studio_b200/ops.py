@@ -235,3 +235,32 @@ def adam_step(param, exp_avg, exp_avg_sq, param_grad, lr, beta1, beta2, eps, bia
         _chk(t, nme)
     check(lib.lfs_adam_step(_p(param), _p(exp_avg), _p(exp_avg_sq), _p(param_grad), param.numel(), lr, beta1, beta2,
                             eps, bias_correction1_rcp, bias_correction2_sqrt_rcp, _stream()))
+
+
+def quats_to_rotmats(quats):
+    """gsplat::quats_to_rotmats (gsplat/Ops.h:46-48): [N,4] -> [N,3,3]."""
+    lib = load()
+    _chk(quats, "quats")
+    out = torch.empty((quats.shape[0], 3, 3), dtype=torch.float32, device=quats.device)
+    check(lib.lfs_quats_to_rotmats(_p(quats), quats.shape[0], _p(out), _stream()))
+    return out
+
+
+def relocation(opacities, scales, ratios, binoms, n_max: int):
+    """gsplat::relocation (gsplat/Ops.h:52-57) -> (new_opacities [N], new_scales [N,3])."""
+    lib = load()
+    _chk(opacities, "opacities"), _chk(scales, "scales"), _chk(ratios, "ratios", torch.int32), _chk(binoms, "binoms")
+    new_op, new_sc = torch.empty_like(opacities), torch.empty_like(scales)
+    check(lib.lfs_relocation(_p(opacities), _p(scales), _p(ratios), _p(binoms), n_max, opacities.shape[0], _p(new_op),
+                             _p(new_sc), _stream()))
+    return new_op, new_sc
+
+
+def add_noise(raw_opacities, raw_scales, raw_quats, noise, means, current_lr: float) -> None:
+    """gsplat::add_noise (gsplat/Ops.h:59-65); means updated in place."""
+    lib = load()
+    for t, nme in ((raw_opacities, "raw_opacities"), (raw_scales, "raw_scales"), (raw_quats, "raw_quats"),
+                   (noise, "noise"), (means, "means")):
+        _chk(t, nme)
+    check(lib.lfs_add_noise(_p(raw_opacities), _p(raw_scales), _p(raw_quats), _p(noise), _p(means), current_lr,
+                            raw_opacities.shape[0], _stream()))
