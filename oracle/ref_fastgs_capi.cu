@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <functional>
 #include <tuple>
+#include <vector>
 
 namespace {
     struct Blob {
@@ -46,6 +47,7 @@ namespace {
     struct Ctx {
         Blob prim, tile, inst, bucket;
         int n_visible = 0, n_instances = 0, n_buckets = 0, sel_prim = 0, sel_inst = 0;
+        size_t inst_req = 0, inst_n = 0;
     };
 } // namespace
 
@@ -76,7 +78,19 @@ int ref_fastgs_forward(void* h, const float* means, const float* scales_raw, con
         if (pre != cudaSuccess)
             fprintf(stderr, "[ref_fastgs] stale CUDA error before forward: %s\n", cudaGetErrorString(pre));
     }
-    auto f_prim = [c](size_t n) { return c->prim.resize(n); };
+    const bool dbg = getenv("REF_FASTGS_DEBUG") != nullptr;
+    const int n_tiles_dbg = ((width + 15) / 16) * ((height + 15) / 16);
+    auto stage = [dbg](const char* where) {
+        if (!dbg)
+            return;
+        cudaError_t e1 = cudaDeviceSynchronize();
+        cudaError_t e2 = cudaGetLastError();
+        fprintf(stderr, "[ref_fastgs] at %s: sync=%s last=%s\n", where, cudaGetErrorString(e1), cudaGetErrorString(e2));
+    };
+    auto f_prim = [c, stage](size_t n) {
+        stage("per_primitive alloc (after per-tile memset)");
+        return c->prim.resize(n);
+    };
     // The reference zeroes PerTileBuffers::instance_ranges with cudaMemsetAsync on a private static stream
     // (fastgs/rasterization/src/forward.cu:48-55).  On this image (CUDA 12.9 runtime inside a torch process)
     // that call returns cudaErrorInvalidValue (compute-sanitizer, profiles/r01_ref_fastgs_memset.txt), the ranges of
@@ -88,8 +102,61 @@ int ref_fastgs_forward(void* h, const float* means, const float* scales_raw, con
             cudaMemset(p, 0, n);
         return p;
     };
-    auto f_inst = [c](size_t n) { return c->inst.resize(n); };
-    auto f_bucket = [c](size_t n) { return c->bucket.resize(n); };
+    auto f_inst = [c, stage](size_t n) {
+        stage("per_instance alloc (after preprocess + depth sort + scan)");
+        // On sm_100a the reference's two copies of the exact tile test (preprocess_cu counts, create_instances_cu
+        // emits; kernel_utils.cuh:108-210) do not always agree under --use_fast_math, so a few instance slots are
+        // never written.  Their uninitialised u16 tile keys can exceed n_tiles and extract_instance_ranges_cu then
+        // writes out of bounds (observed: garbage bucket counts at 1080p).  Zero-filling the blob makes such slots
+        // harmless duplicates in tile 0; it does not change anything the reference writes itself.
+        char* p = c->inst.resize(n);
+        if (p)
+            cudaMemset(p, 0, n);
+        c->inst_req = n;
+        return p;
+    };
+    auto f_bucket = [c, stage, dbg, n_tiles_dbg](size_t n) {
+        stage("per_bucket alloc (after create_instances + tile sort + ranges + bucket scan)");
+        if (dbg && c->tile.ptr) { // PerTileBuffers layout (buffer_utils.h:114-137): ranges | n_buckets | bucket_offsets
+            const size_t o_nb = ((size_t)n_tiles_dbg * 8 + 127) / 128 * 128;
+            const size_t o_bo = (o_nb + (size_t)n_tiles_dbg * 4 + 127) / 128 * 128;
+            std::vector<unsigned> rng(2 * (size_t)n_tiles_dbg), nb(n_tiles_dbg), bo(n_tiles_dbg);
+            cudaMemcpy(rng.data(), c->tile.ptr, rng.size() * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(nb.data(), c->tile.ptr + o_nb, nb.size() * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(bo.data(), c->tile.ptr + o_bo, bo.size() * 4, cudaMemcpyDeviceToHost);
+            unsigned long long snb = 0, maxy = 0, bad = 0;
+            for (int t = 0; t < n_tiles_dbg; ++t) {
+                snb += nb[t];
+                if (rng[2 * t + 1] > maxy)
+                    maxy = rng[2 * t + 1];
+                if (rng[2 * t + 1] < rng[2 * t])
+                    ++bad;
+            }
+            c->inst_n = (size_t)maxy;
+            fprintf(stderr, "[ref_fastgs] tiles=%d sum(n_buckets)=%llu last(bucket_offsets)=%u max(range.y)=%llu "
+                            "ranges with y<x=%llu first ranges (%u,%u) (%u,%u)\n",
+                    n_tiles_dbg, snb, bo[n_tiles_dbg - 1], maxy, bad, rng[0], rng[1], rng[2], rng[3]);
+        }
+        if (dbg && c->inst.ptr && c->inst_n > 0) { // PerInstanceBuffers: keys cur | keys alt | idx cur | idx alt
+            const size_t ni = c->inst_n;
+            const size_t o_alt = (ni * 2 + 127) / 128 * 128;
+            for (int which = 0; which < 2; ++which) {
+                std::vector<unsigned short> k(ni);
+                cudaMemcpy(k.data(), c->inst.ptr + (which ? o_alt : 0), ni * 2, cudaMemcpyDeviceToHost);
+                size_t inv = 0;
+                unsigned mx = 0;
+                for (size_t i = 0; i < ni; ++i) {
+                    if (i && k[i] < k[i - 1])
+                        ++inv;
+                    if (k[i] > mx)
+                        mx = k[i];
+                }
+                fprintf(stderr, "[ref_fastgs] key buffer %d: n=%zu inversions=%zu max_key=%u first=%u last=%u\n", which,
+                        ni, inv, mx, (unsigned)k[0], (unsigned)k[ni - 1]);
+            }
+        }
+        return c->bucket.resize(n);
+    };
     auto r = fast_gs::rasterization::forward(
         f_prim, f_tile, f_inst, f_bucket, reinterpret_cast<const float3*>(means),
         reinterpret_cast<const float3*>(scales_raw), reinterpret_cast<const float4*>(rotations_raw), opacities_raw,
