@@ -139,27 +139,37 @@ int exclusive_scan_u32(const uint32_t* in, const uint32_t* gather, uint32_t* out
 __global__ void __launch_bounds__(kRsThreads)
     k_rs_hist(const uint32_t* __restrict__ keys, uint32_t n_cap, const uint32_t* __restrict__ n_dev, int shift,
               int ndig, uint32_t nblk, uint32_t* __restrict__ table) {
-    extern __shared__ uint32_t sh[];
+    extern __shared__ uint32_t sh[]; // [kHistCopies][ndig] privatised copies (fewer same-address conflicts)
+    constexpr int kHistCopies = 4;
     const uint32_t n = resolve_n(n_cap, n_dev);
-    for (int d = threadIdx.x; d < ndig; d += kRsThreads)
+    for (int d = threadIdx.x; d < kHistCopies * ndig; d += kRsThreads)
         sh[d] = 0;
     __syncthreads();
     const uint32_t base = blockIdx.x * kRsTile;
     if (base < n) {
-        const int lane = threadIdx.x & 31;
-#pragma unroll 4
-        for (int r = 0; r < kRsItems; ++r) {
-            const uint32_t i = base + r * kRsThreads + threadIdx.x;
-            const bool valid = i < n;
-            const uint32_t d = valid ? ((__ldg(keys + i) >> shift) & (uint32_t)(ndig - 1)) : (uint32_t)ndig;
-            const uint32_t peers = __match_any_sync(0xffffffffu, d);
-            if (valid && (__ffs(peers) - 1) == lane)
-                atomicAdd(&sh[d], (uint32_t)__popc(peers));
+        uint32_t* mine = sh + ((threadIdx.x >> 5) & (kHistCopies - 1)) * ndig;
+        const uint32_t mask = (uint32_t)(ndig - 1);
+        if (base + kRsTile <= n && (reinterpret_cast<uintptr_t>(keys + base) & 15u) == 0) { // full tile: 128-bit loads
+            const uint4* k4 = reinterpret_cast<const uint4*>(keys + base);
+#pragma unroll
+            for (int r = 0; r < kRsItems / 4; ++r) {
+                const uint4 v = __ldg(k4 + r * kRsThreads + threadIdx.x);
+                atomicAdd(&mine[(v.x >> shift) & mask], 1u);
+                atomicAdd(&mine[(v.y >> shift) & mask], 1u);
+                atomicAdd(&mine[(v.z >> shift) & mask], 1u);
+                atomicAdd(&mine[(v.w >> shift) & mask], 1u);
+            }
+        } else {
+            for (int r = 0; r < kRsItems; ++r) {
+                const uint32_t i = base + r * kRsThreads + threadIdx.x;
+                if (i < n)
+                    atomicAdd(&mine[(__ldg(keys + i) >> shift) & mask], 1u);
+            }
         }
     }
     __syncthreads();
     for (int d = threadIdx.x; d < ndig; d += kRsThreads)
-        table[(size_t)d * nblk + blockIdx.x] = sh[d];
+        table[(size_t)d * nblk + blockIdx.x] = sh[d] + sh[ndig + d] + sh[2 * ndig + d] + sh[3 * ndig + d];
 }
 
 // grid = ndig CTAs: exclusive scan of row d over the blocks, totals[d] = row sum
@@ -227,11 +237,11 @@ __global__ void __launch_bounds__(kRsThreads)
         const uint32_t d = valid ? ((key[r] >> shift) & (uint32_t)(ndig - 1)) : (uint32_t)ndig;
         const uint32_t peers = __match_any_sync(0xffffffffu, d);
         const uint32_t rank = __popc(peers & lt_mask);
-        const uint32_t before = valid ? wh[d] : 0u;
-        __syncwarp();
-        if (valid && rank == 0)
-            wh[d] = before + (uint32_t)__popc(peers);
-        __syncwarp();
+        const int leader = __ffs(peers) - 1;
+        uint32_t before = 0;
+        if (valid && rank == 0) // one shared atomic per distinct digit; same-address atomics of one warp retire in
+            before = atomicAdd(&wh[d], (uint32_t)__popc(peers)); // program order -> ranks stay stable across rounds
+        before = __shfl_sync(0xffffffffu, before, leader);
         lrank[r] = before + rank;
     }
     __syncthreads();
@@ -275,7 +285,7 @@ int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint3
     uint32_t *kin = keys_a, *vin = vals_a, *kout = keys_b, *vout = vals_b;
     for (int p = 0; p < plan.n_pass; ++p) {
         const int ndig = 1 << plan.bits[p];
-        k_rs_hist<<<nblk, kRsThreads, sizeof(uint32_t) * ndig, stream>>>(kin, n_cap, n_dev, plan.shift[p], ndig, nblk,
+        k_rs_hist<<<nblk, kRsThreads, sizeof(uint32_t) * 4 * ndig, stream>>>(kin, n_cap, n_dev, plan.shift[p], ndig, nblk,
                                                                          table);
         LFS_LAUNCH_OK("k_rs_hist");
         k_rs_scan_rows<<<ndig, 256, 0, stream>>>(table, nblk, totals);
