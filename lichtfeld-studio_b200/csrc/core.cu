@@ -31,6 +31,18 @@ extern "C" int lfs_set_option(const char* name, int value) {
         lfs::raster_options().use_tma = value ? 1 : 0;
         return LFS_OK;
     }
+    if (name && std::string(name) == "bwd_variant") {
+        lfs::raster_options().bwd_variant = value;
+        return LFS_OK;
+    }
+    if (name && std::string(name) == "pre_bwd_split") {
+        lfs::raster_options().pre_bwd_split = value;
+        return LFS_OK;
+    }
+    if (name && std::string(name) == "blend_fused") {
+        lfs::raster_options().fuse_expand = value ? 1 : 0;
+        return LFS_OK;
+    }
     lfs::set_error("set_option: unknown option '%s'", name ? name : "(null)");
     return LFS_ERR_INVALID_ARG;
 }

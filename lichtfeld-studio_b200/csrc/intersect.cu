@@ -61,6 +61,10 @@ __device__ __forceinline__ uint32_t upper_slot(const uint32_t* __restrict__ off,
     return lo;
 }
 
+// Warp-cooperative emission: a warp owns 32 consecutive slots of the depth order; for every slot with a non-empty
+// tile rectangle the whole warp writes that Gaussian's run of instances (coalesced: the run is contiguous at
+// off[slot]).  Replaces the instance-parallel version whose 20-step binary search over `off` per instance was
+// latency bound (ncu r01c: 0.150 ms, 28 long-scoreboard stall cycles per issue).
 __global__ void __launch_bounds__(kIsThreads)
     k_emit_instances(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ off, const uint32_t n_gauss,
                      const TileRect* __restrict__ rects, const uint32_t tile_w, const uint32_t id_offset,
@@ -71,15 +75,35 @@ __global__ void __launch_bounds__(kIsThreads)
         const uint32_t nd = *n_dev;
         n = nd < n_cap ? nd : n_cap;
     }
-    for (uint32_t j = blockIdx.x * kIsThreads + threadIdx.x; j < n; j += gridDim.x * kIsThreads) {
-        const uint32_t slot = upper_slot(off, n_gauss, j);
-        const uint32_t g = perm ? __ldg(perm + slot) : slot;
-        const uint32_t k = j - __ldg(off + slot);
-        const TileRect r = rects[g];
-        const uint32_t w = (uint32_t)r.x1 - (uint32_t)r.x0;
-        const uint32_t ty = r.y0 + k / w, tx = r.x0 + k % w;
-        tile_keys[j] = ty * tile_w + tx;
-        vals[j] = g + id_offset;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warps = (gridDim.x * kIsThreads) >> 5;
+    for (uint32_t base = ((blockIdx.x * kIsThreads + threadIdx.x) >> 5) * 32u; base < n_gauss; base += warps * 32u) {
+        const uint32_t slot = base + lane;
+        uint32_t g = 0, o = 0, xy0 = 0, w = 0, c = 0;
+        if (slot < n_gauss) {
+            g = perm ? __ldg(perm + slot) : slot;
+            const TileRect r = rects[g];
+            w = (uint32_t)r.x1 - (uint32_t)r.x0;
+            c = w * ((uint32_t)r.y1 - (uint32_t)r.y0);
+            xy0 = (uint32_t)r.x0 | ((uint32_t)r.y0 << 16);
+            o = __ldg(off + slot);
+        }
+        uint32_t todo = __ballot_sync(0xffffffffu, c > 0);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t bo = __shfl_sync(0xffffffffu, o, src), bc = __shfl_sync(0xffffffffu, c, src);
+            const uint32_t bw = __shfl_sync(0xffffffffu, w, src), bxy = __shfl_sync(0xffffffffu, xy0, src);
+            const uint32_t bg = __shfl_sync(0xffffffffu, g, src) + id_offset;
+            for (uint32_t k = lane; k < bc; k += 32u) {
+                const uint32_t j = bo + k;
+                if (j < n) {
+                    const uint32_t q = k / bw;
+                    tile_keys[j] = ((bxy >> 16) + q) * tile_w + (bxy & 0xffffu) + (k - q * bw);
+                    vals[j] = bg;
+                }
+            }
+        }
     }
 }
 
@@ -88,7 +112,7 @@ int launch_emit_instances(const uint32_t* perm, const uint32_t* off, uint32_t n_
                           uint32_t* tile_keys, uint32_t* vals, cudaStream_t stream) {
     if (n_cap == 0 || n_gauss == 0)
         return LFS_OK;
-    const unsigned want = div_up(n_cap, kIsThreads);
+    const unsigned want = div_up(n_gauss, kIsThreads);
     const unsigned grid = want < (unsigned)(kNumSMs * 16) ? want : (unsigned)(kNumSMs * 16);
     k_emit_instances<<<grid, kIsThreads, 0, stream>>>(perm, off, n_gauss, rects, tile_w, id_offset, n_cap, n_dev,
                                                       tile_keys, vals);

@@ -29,6 +29,40 @@ __device__ __forceinline__ uint32_t find_tile(const int32_t* __restrict__ off, u
     return lo;
 }
 
+
+// Tile-local expansion of one GaussRec into the 12 rational-quadratic coefficients (see raster.cuh).  Used by the
+// stand-alone expand kernel AND inlined into the fused forward / backward blends, so every operation is spelled with
+// explicit fmaf / __fmul_rn: the three call sites must produce the same coefficient BITS (a pair has to get the same
+// alpha in the forward and in the backward), which rules out leaving FMA contraction to the optimiser.
+__device__ __forceinline__ float dot_rn(const f3 a, const f3 b) {
+    return fmaf(a.z, b.z, fmaf(a.y, b.y, __fmul_rn(a.x, b.x)));
+}
+__device__ __forceinline__ f3 cross_rn(const f3 a, const f3 b) {
+    return mk3(fmaf(a.y, b.z, -__fmul_rn(a.z, b.y)), fmaf(a.z, b.x, -__fmul_rn(a.x, b.z)),
+               fmaf(a.x, b.y, -__fmul_rn(a.y, b.x)));
+}
+__device__ __forceinline__ void expand_record(const float4 g0, const float4 g1, const float4 g2, const float Xo,
+                                              const float Yo, float4& A, float4& B, float4& Cc) {
+    const f3 vx = mk3(g0.x, g0.y, g0.z), vy = mk3(g0.w, g1.x, g1.y), w2 = mk3(g1.z, g1.w, g2.x);
+    const f3 gro = mk3(g2.y, g2.z, g2.w);
+    const f3 v0 = mk3(fmaf(vy.x, Yo, fmaf(vx.x, Xo, w2.x)), fmaf(vy.y, Yo, fmaf(vx.y, Xo, w2.y)),
+                      fmaf(vy.z, Yo, fmaf(vx.z, Xo, w2.z)));
+    const f3 c0 = cross_rn(v0, gro), cxv = cross_rn(vx, gro), cyv = cross_rn(vy, gro);
+    constexpr float k2 = 2.f * kNScale;
+    A.x = __fmul_rn(kNScale, dot_rn(c0, c0));
+    A.y = __fmul_rn(k2, dot_rn(c0, cxv));
+    A.z = __fmul_rn(k2, dot_rn(c0, cyv));
+    A.w = __fmul_rn(kNScale, dot_rn(cxv, cxv));
+    B.x = __fmul_rn(k2, dot_rn(cxv, cyv));
+    B.y = __fmul_rn(kNScale, dot_rn(cyv, cyv));
+    B.z = dot_rn(v0, v0);
+    B.w = __fmul_rn(2.f, dot_rn(v0, vx));
+    Cc.x = __fmul_rn(2.f, dot_rn(v0, vy));
+    Cc.y = dot_rn(vx, vx);
+    Cc.z = __fmul_rn(2.f, dot_rn(vx, vy));
+    Cc.w = dot_rn(vy, vy);
+}
+
 __global__ void __launch_bounds__(kExThreads)
     k_expand_instances(const GaussRec* __restrict__ gauss, const int32_t* __restrict__ inst_gid,
                        const int32_t* __restrict__ tile_off, const uint32_t* __restrict__ sorted_tile_keys,
@@ -52,24 +86,8 @@ __global__ void __launch_bounds__(kExThreads)
 
         const float4* gp = reinterpret_cast<const float4*>(gauss + g);
         const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1), g2 = __ldg(gp + 2), g3 = __ldg(gp + 3);
-        const f3 vx = mk3(g0.x, g0.y, g0.z), vy = mk3(g0.w, g1.x, g1.y), w2 = mk3(g1.z, g1.w, g2.x);
-        const f3 gro = mk3(g2.y, g2.z, g2.w);
-
-        const f3 v0 = w2 + vx * Xo + vy * Yo;
-        const f3 c0 = cross(v0, gro), cxv = cross(vx, gro), cyv = cross(vy, gro);
         float4 A, B, Cc;
-        A.x = kNScale * dot(c0, c0);
-        A.y = kNScale * 2.f * dot(c0, cxv);
-        A.z = kNScale * 2.f * dot(c0, cyv);
-        A.w = kNScale * dot(cxv, cxv);
-        B.x = kNScale * 2.f * dot(cxv, cyv);
-        B.y = kNScale * dot(cyv, cyv);
-        B.z = dot(v0, v0);
-        B.w = 2.f * dot(v0, vx);
-        Cc.x = 2.f * dot(v0, vy);
-        Cc.y = dot(vx, vx);
-        Cc.z = 2.f * dot(vx, vy);
-        Cc.w = dot(vy, vy);
+        expand_record(g0, g1, g2, Xo, Yo, A, B, Cc);
         float4* out = reinterpret_cast<float4*>(inst + j);
         out[0] = A;
         out[1] = B;
@@ -167,12 +185,14 @@ __device__ __forceinline__ float poly2(const float dx, const float dy, const flo
     return fmaf(dx, fmaf(dx, cxx, fmaf(dy, cxy, cx)), fmaf(dy, fmaf(dy, cyy, cy), c0));
 }
 
-template <bool USE_TMA>
+template <int MODE> // 0: register-staged InstRec, 1: TMA-staged InstRec, 2: fused expansion (GaussRec gather)
 __global__ void __launch_bounds__(kFwdThreads)
-    k_blend_fwd(const RasterBuffers rb, const uint32_t width, const uint32_t height, const uint32_t tile_w,
+    k_blend_fwd(const RasterBuffers rb, const ViewCam* __restrict__ cams, const uint32_t width, const uint32_t height, const uint32_t tile_w,
                 const uint32_t tile_h, const bool write_ckpt, const float* __restrict__ backgrounds,
                 const uint8_t* __restrict__ masks, float* __restrict__ renders, float* __restrict__ alphas,
                 int32_t* __restrict__ last_ids) {
+    constexpr bool USE_TMA = (MODE == 1);
+    constexpr bool FUSED = (MODE == 2);
     __shared__ __align__(128) float4 s_rec[2][kBatch * 4];
     __shared__ __align__(16) float4 s_state[kTilePix]; // (r, g, b, T) per pixel
     __shared__ uint32_t s_ncon[kTilePix];
@@ -242,6 +262,12 @@ __global__ void __launch_bounds__(kFwdThreads)
     }
 
     const float4* gsrc = reinterpret_cast<const float4*>(rb.inst + start);
+    float Xo = 0.f, Yo = 0.f;
+    uint32_t gid_next = 0; // FUSED: flattened Gaussian id this thread expands for the NEXT batch
+    if (FUSED) {
+        Xo = (float)(tx * kTile + kTile / 2) - cams[cam].cx;
+        Yo = (float)(ty * kTile + kTile / 2) - cams[cam].cy;
+    }
     const int nbatch = (cnt + kBatch - 1) / kBatch;
 
     if (USE_TMA) {
@@ -257,6 +283,19 @@ __global__ void __launch_bounds__(kFwdThreads)
                 mbar_expect_tx(&s_bar[k], nrec * (uint32_t)sizeof(InstRec));
                 tma_load_1d(&s_rec[k][0], gsrc + (size_t)k * kBatch * 4, nrec * (uint32_t)sizeof(InstRec), &s_bar[k]);
             }
+        }
+    } else if (FUSED) {
+        if (nbatch > 0) {
+            if ((int)tid < min(kBatch, cnt)) {
+                const float4* gp = reinterpret_cast<const float4*>(rb.gauss + (uint32_t)__ldg(rb.inst_gid + start + tid));
+                float4 A, B, Cc;
+                expand_record(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), Xo, Yo, A, B, Cc);
+                s_rec[0][4 * tid] = A, s_rec[0][4 * tid + 1] = B, s_rec[0][4 * tid + 2] = Cc;
+                s_rec[0][4 * tid + 3] = __ldg(gp + 3);
+            }
+            if ((int)tid < cnt - kBatch)
+                gid_next = (uint32_t)__ldg(rb.inst_gid + start + kBatch + tid);
+            __syncthreads();
         }
     } else if (nbatch > 0) {
         const int nf4 = min(kBatch, cnt) * 4;
@@ -301,6 +340,15 @@ __global__ void __launch_bounds__(kFwdThreads)
         if (USE_TMA) {
             mbar_wait(&s_bar[buf], (uint32_t)((kb >> 1) & 1));
             consumed = kb + 1;
+        } else if (FUSED) {
+            // gather the next batch's GaussRec (this thread's record) now; it is expanded after the blend below
+            next_f4 = (kb + 1 < nbatch) ? min(kBatch, cnt - (kb + 1) * kBatch) : 0;
+            if ((int)tid < next_f4) {
+                const float4* gp = reinterpret_cast<const float4*>(rb.gauss + gid_next);
+                pre[0] = __ldg(gp), pre[1] = __ldg(gp + 1), pre[2] = __ldg(gp + 2), pre[3] = __ldg(gp + 3);
+            }
+            if ((int)tid < cnt - (kb + 2) * kBatch)
+                gid_next = (uint32_t)__ldg(rb.inst_gid + start + (kb + 2) * kBatch + tid);
         } else {
             next_f4 = (kb + 1 < nbatch) ? min(kBatch, cnt - (kb + 1) * kBatch) * 4 : 0;
 #pragma unroll
@@ -354,7 +402,14 @@ __global__ void __launch_bounds__(kFwdThreads)
                 s_state[pid[k]] = make_float4(r[k], g[k], b[k], T[k]);
                 s_ncon[pid[k]] = ncon[k];
             }
-        if (!USE_TMA) {
+        if (FUSED) {
+            if ((int)tid < next_f4) {
+                float4 A, B, Cc;
+                expand_record(pre[0], pre[1], pre[2], Xo, Yo, A, B, Cc);
+                float4* d = &s_rec[buf ^ 1][4 * tid];
+                d[0] = A, d[1] = B, d[2] = Cc, d[3] = pre[3];
+            }
+        } else if (!USE_TMA) {
 #pragma unroll
             for (int q = 0; q < 4; ++q)
                 if ((int)(tid + q * kFwdThreads) < next_f4)
@@ -423,18 +478,21 @@ __global__ void __launch_bounds__(kFwdThreads)
         rb.tile_max_contrib[ft] = max(s_warp_tot[0], s_warp_tot[1]);
 }
 
-int launch_blend_fwd(const RasterBuffers& rb, uint32_t C, uint32_t width, uint32_t height, uint32_t tile_w,
-                     uint32_t tile_h, bool write_ckpt, const float* backgrounds, const uint8_t* masks, float* renders,
-                     float* alphas, int32_t* last_ids, cudaStream_t stream) {
+int launch_blend_fwd(const RasterBuffers& rb, const ViewCam* cams_dev, uint32_t C, uint32_t width, uint32_t height,
+                     uint32_t tile_w, uint32_t tile_h, bool write_ckpt, const float* backgrounds, const uint8_t* masks,
+                     float* renders, float* alphas, int32_t* last_ids, cudaStream_t stream) {
     if (C == 0 || tile_w == 0 || tile_h == 0)
         return LFS_OK;
     dim3 grid(tile_w * tile_h, C);
-    if (raster_options().use_tma)
-        k_blend_fwd<true><<<grid, kFwdThreads, 0, stream>>>(rb, width, height, tile_w, tile_h, write_ckpt, backgrounds,
-                                                         masks, renders, alphas, last_ids);
+    if (raster_options().fuse_expand)
+        k_blend_fwd<2><<<grid, kFwdThreads, 0, stream>>>(rb, cams_dev, width, height, tile_w, tile_h, write_ckpt,
+                                                      backgrounds, masks, renders, alphas, last_ids);
+    else if (raster_options().use_tma)
+        k_blend_fwd<1><<<grid, kFwdThreads, 0, stream>>>(rb, cams_dev, width, height, tile_w, tile_h, write_ckpt,
+                                                      backgrounds, masks, renders, alphas, last_ids);
     else
-        k_blend_fwd<false><<<grid, kFwdThreads, 0, stream>>>(rb, width, height, tile_w, tile_h, write_ckpt, backgrounds,
-                                                          masks, renders, alphas, last_ids);
+        k_blend_fwd<0><<<grid, kFwdThreads, 0, stream>>>(rb, cams_dev, width, height, tile_w, tile_h, write_ckpt,
+                                                      backgrounds, masks, renders, alphas, last_ids);
     LFS_LAUNCH_OK("k_blend_fwd");
     return LFS_OK;
 }
@@ -442,7 +500,6 @@ int launch_blend_fwd(const RasterBuffers& rb, uint32_t C, uint32_t width, uint32
 // ------------------------------------------------------------------------------------------------------
 // backward blend: one warp per 32-instance bucket
 // ------------------------------------------------------------------------------------------------------
-constexpr int kBwdWarps = 4;
 
 __device__ __forceinline__ void quat_to_rotmat_dev(const float4 q_wxyz, float R[9], float& inv_norm, float qn[4]) {
     float w = q_wxyz.x, x = q_wxyz.y, y = q_wxyz.z, z = q_wxyz.w;
@@ -456,16 +513,21 @@ __device__ __forceinline__ void quat_to_rotmat_dev(const float4 q_wxyz, float R[
     R[6] = 2.f * (xz - wy), R[7] = 2.f * (yz + wx), R[8] = 1.f - 2.f * (x2 + y2);
 }
 
-__global__ void __launch_bounds__(kBwdWarps * 32)
+template <bool FUSED, int kBwdWarps, int kMinBlocks>
+__global__ void __launch_bounds__(kBwdWarps * 32, kMinBlocks)
     k_blend_bwd(const RasterBuffers rb, const ViewCam* __restrict__ cams, const float4* __restrict__ v_pix,
                 const float* __restrict__ quats, const float* __restrict__ scales, const float* __restrict__ means,
                 const uint32_t N, const uint32_t width, const uint32_t height, const uint32_t tile_w,
                 const uint32_t tile_h, const uint32_t n_bucket_cap, const uint32_t* __restrict__ n_buckets_dev,
                 float* __restrict__ v_means, float* __restrict__ v_quats, float* __restrict__ v_scales,
                 float* __restrict__ v_colors, float* __restrict__ v_opacities) {
-    __shared__ float4 sA[kBwdWarps][32];
-    __shared__ float4 sB[kBwdWarps][32];
-    __shared__ int32_t sN[kBwdWarps][32];
+    // ring of per-pixel records the lanes read directly (no 9-register rotation): two float4 per pixel,
+    //   ringA = (v_r, v_g, v_b, dx)   ringB = (dy, bits(n_rel), T0, u0)
+    // n_rel = how many instances of THIS bucket the pixel consumed (lane < n_rel <=> the forward evaluated the pair);
+    // T0 = transmittance at the bucket start; u0 = <colour accumulated from this bucket on, v_rgb> - v_alpha term.
+    __shared__ float4 ringA[kBwdWarps][64];
+    __shared__ float4 ringB[kBwdWarps][64];
+    __shared__ uint8_t s_pix[kBwdWarps][kTilePix];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t b = blockIdx.x * kBwdWarps + warp;
     uint32_t nbk = *n_buckets_dev;
@@ -483,19 +545,27 @@ __global__ void __launch_bounds__(kBwdWarps * 32)
     const uint32_t li = local_b * kBucket + lane; // tile-local instance index of this lane
     const int32_t inst = tstart + (int32_t)li;
     const bool valid = inst < tend;
+    const ViewCam& cm = cams[cam];
+    const float Xo = (float)(tx * kTile + kTile / 2) - cm.cx;
+    const float Yo = (float)(ty * kTile + kTile / 2) - cm.cy;
 
     float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A, Cc = A, E = A;
     uint32_t g = 0;
     if (valid) {
-        const float4* rp = reinterpret_cast<const float4*>(rb.inst + inst);
-        A = ld_nc4(rp), B = ld_nc4(rp + 1), Cc = ld_nc4(rp + 2), E = ld_nc4(rp + 3);
         g = (uint32_t)__ldg(rb.inst_gid + inst);
+        if (FUSED) {
+            const float4* gp = reinterpret_cast<const float4*>(rb.gauss + g);
+            expand_record(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), Xo, Yo, A, B, Cc);
+            E = __ldg(gp + 3);
+        } else {
+            const float4* rp = reinterpret_cast<const float4*>(rb.inst + inst);
+            A = ld_nc4(rp), B = ld_nc4(rp + 1), Cc = ld_nc4(rp + 2), E = ld_nc4(rp + 3);
+        }
     }
 
-    // rotating pixel state
-    int32_t ncon = 0;
-    float car = 0.f, cag = 0.f, cab = 0.f, T = 0.f;
-    float vr = 0.f, vg = 0.f, vb = 0.f, ga = 0.f;
+    // state that still rotates through the lanes: transmittance before this lane's instance, and
+    // u = <sum_{j >= this instance} c_j alpha_j T_j, v_rgb> - v_alpha_term   (one scalar instead of 3 + 1)
+    float T = 0.f, u = 0.f;
     // per-instance accumulators
     float an0 = 0.f, an1 = 0.f, an2 = 0.f, an3 = 0.f, an4 = 0.f, an5 = 0.f;
     float ad0 = 0.f, ad1 = 0.f, ad2 = 0.f, ad3 = 0.f, ad4 = 0.f, ad5 = 0.f;
@@ -505,7 +575,6 @@ __global__ void __launch_bounds__(kBwdWarps * 32)
 
     // compact list of the tile's pixels that reach this bucket (n_contrib > first instance of the bucket):
     // late buckets are reached by few pixels, so the rotation below runs m + 31 instead of 256 + 31 steps
-    __shared__ uint8_t s_pix[kBwdWarps][kTilePix];
     int m = 0;
     {
         const uint32_t lt = (1u << lane) - 1u;
@@ -524,54 +593,39 @@ __global__ void __launch_bounds__(kBwdWarps * 32)
         __syncwarp();
     }
 
+    const int ilane = lane;
     for (int i = 0; i < m + 31; ++i) {
-        if ((i & 31) == 0 && i < m) {
+        if ((i & 31) == 0 && i < m) { // stage the next 32 pixels of the list into the ring half (i & 32)
             __syncwarp();
             float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a4;
-            int32_t nc = 0;
             if (i + lane < m) {
                 const int p = s_pix[warp][i + lane];
                 const uint32_t px = tx * kTile + (p & 15), py = ty * kTile + (p >> 4);
                 const size_t pix = ((size_t)cam * height + py) * width + px;
-                nc = (int32_t)((uint32_t)__ldg(rb.n_contrib + pix) | ((uint32_t)p << 24)); // pixel id rides in the top byte (n_contrib < 2^24)
+                const int32_t nrel = __ldg(rb.n_contrib + pix) - (int32_t)(local_b * kBucket);
                 const float4 c4 = ld_nc4(ck + p);
                 const float4 f4 = __ldg(rb.pix_state + pix);
-                a4 = make_float4(f4.x - c4.x, f4.y - c4.y, f4.z - c4.z, c4.w);
-                b4 = __ldg(v_pix + pix);
+                const float4 v4 = __ldg(v_pix + pix);
+                const float u0 = fmaf(f4.x - c4.x, v4.x, fmaf(f4.y - c4.y, v4.y, fmaf(f4.z - c4.z, v4.z, -v4.w)));
+                a4 = make_float4(v4.x, v4.y, v4.z, (float)(p & 15) - 7.5f);
+                b4 = make_float4((float)(p >> 4) - 7.5f, __int_as_float(nrel), c4.w, u0);
             }
-            sA[warp][lane] = a4;
-            sB[warp][lane] = b4;
-            sN[warp][lane] = nc;
+            ringA[warp][(i + lane) & 63] = a4;
+            ringB[warp][(i + lane) & 63] = b4;
             __syncwarp();
         }
-        if (i > 0) {
-            ncon = __shfl_up_sync(0xffffffffu, ncon, 1);
-            car = __shfl_up_sync(0xffffffffu, car, 1);
-            cag = __shfl_up_sync(0xffffffffu, cag, 1);
-            cab = __shfl_up_sync(0xffffffffu, cab, 1);
-            T = __shfl_up_sync(0xffffffffu, T, 1);
-            vr = __shfl_up_sync(0xffffffffu, vr, 1);
-            vg = __shfl_up_sync(0xffffffffu, vg, 1);
-            vb = __shfl_up_sync(0xffffffffu, vb, 1);
-            ga = __shfl_up_sync(0xffffffffu, ga, 1);
-        }
+        const int idx = i - ilane; // position in the compact list of the pixel currently at this lane
+        const float4 ea = ringA[warp][idx & 63], eb = ringB[warp][idx & 63];
+        T = __shfl_up_sync(0xffffffffu, T, 1);
+        u = __shfl_up_sync(0xffffffffu, u, 1);
         if (lane == 0) {
-            if (i < m) {
-                const float4 a4 = sA[warp][i & 31], b4 = sB[warp][i & 31];
-                ncon = sN[warp][i & 31];
-                car = a4.x, cag = a4.y, cab = a4.z, T = a4.w;
-                vr = b4.x, vg = b4.y, vb = b4.z, ga = b4.w;
-            } else {
-                ncon = 0;
-            }
+            T = eb.z;
+            u = eb.w;
         }
-        const int idx = i - lane; // position in the compact list of the pixel currently at this lane
-        const uint32_t ucode = (uint32_t)ncon;
-        const int pcode = (int)(ucode >> 24), nc_px = (int)(ucode & 0xFFFFFFu);
-        const bool active = valid && idx >= 0 && idx < m && (int32_t)li < nc_px;
+        const bool active = valid && (uint32_t)idx < (uint32_t)m && ilane < __float_as_int(eb.y);
         if (!active)
             continue;
-        const float dx = (float)(pcode & 15) - 7.5f, dy = (float)(pcode >> 4) - 7.5f;
+        const float dx = ea.w, dy = eb.x;
         const float Nv = poly2(dx, dy, A.x, A.y, A.z, A.w, B.x, B.y);
         const float Dv = poly2(dx, dy, B.z, B.w, Cc.x, Cc.y, Cc.z, Cc.w);
         const float rD = rcp_approx(Dv);
@@ -582,19 +636,16 @@ __global__ void __launch_bounds__(kBwdWarps * 32)
         if (alpha < kAlphaMin)
             continue;
         const float w = T * alpha;
-        acr = fmaf(w, vr, acr);
-        acg = fmaf(w, vg, acg);
-        acb = fmaf(w, vb, acb);
-        car = fmaf(-w, E.y, car);
-        cag = fmaf(-w, E.z, cag);
-        cab = fmaf(-w, E.w, cab);
-        const float om = 1.0f - alpha;
-        const float ra = __fdividef(1.0f, om);
-        const float v_alpha = (T * E.y - car * ra) * vr + (T * E.z - cag * ra) * vg + (T * E.w - cab * ra) * vb + ga * ra;
+        acr = fmaf(w, ea.x, acr);
+        acg = fmaf(w, ea.y, acg);
+        acb = fmaf(w, ea.z, acb);
+        const float Ev = fmaf(E.y, ea.x, fmaf(E.z, ea.y, E.w * ea.z)); // <c_i, v_rgb>
+        u = fmaf(-w, Ev, u);                                           // now the sum over j > i
+        const float om = 1.0f - alpha;                                 // >= 0.001: plain rcp is safe
+        const float v_alpha = fmaf(T, Ev, -u * rcp_approx(om));
         if (a_raw <= kAlphaMax) {
             aop = fmaf(vis, v_alpha, aop);
-            const float v_p2 = v_alpha * a_raw * kLn2;
-            const float vN = v_p2 * rD;
+            const float vN = v_alpha * a_raw * kLn2 * rD;
             const float vD = -vN * p2;
             const float dxx = dx * dx, dxy = dx * dy, dyy = dy * dy;
             an0 += vN;
@@ -616,14 +667,11 @@ __global__ void __launch_bounds__(kBwdWarps * 32)
     if (!valid)
         return;
     // ---- per-instance chain rule: polynomial coefficients -> (vx, vy, w2, gro) -> (mean, quat, scale)
-    const ViewCam& cm = cams[cam];
     const uint32_t gid = g % N;
     const float4* gp = reinterpret_cast<const float4*>(rb.gauss + g);
     const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1), g2 = __ldg(gp + 2);
     const f3 vx = mk3(g0.x, g0.y, g0.z), vy = mk3(g0.w, g1.x, g1.y), w2 = mk3(g1.z, g1.w, g2.x);
     const f3 gro = mk3(g2.y, g2.z, g2.w);
-    const float Xo = (float)(tx * kTile + kTile / 2) - cm.cx;
-    const float Yo = (float)(ty * kTile + kTile / 2) - cm.cy;
     const f3 v0 = w2 + vx * Xo + vy * Yo;
     const f3 c0 = cross(v0, gro), cxv = cross(vx, gro), cyv = cross(vy, gro);
     // un-scale the N' coefficient gradients
@@ -718,9 +766,25 @@ int launch_blend_bwd(const RasterBuffers& rb, const ViewCam* cams_dev, const flo
     (void)C;
     if (n_bucket_cap == 0)
         return LFS_OK;
-    k_blend_bwd<<<div_up(n_bucket_cap, kBwdWarps), kBwdWarps * 32, 0, stream>>>(
-        rb, cams_dev, v_pix, quats, scales, means, N, width, height, tile_w, tile_h, n_bucket_cap, n_buckets_dev,
-        v_means, v_quats, v_scales, v_colors, v_opacities);
+#define LFS_BWD_LAUNCH(F, W, MB)                                                                                      \
+    k_blend_bwd<F, W, MB><<<div_up(n_bucket_cap, W), W * 32, 0, stream>>>(                                            \
+        rb, cams_dev, v_pix, quats, scales, means, N, width, height, tile_w, tile_h, n_bucket_cap, n_buckets_dev,      \
+        v_means, v_quats, v_scales, v_colors, v_opacities)
+    const int variant = raster_options().bwd_variant;
+    if (!raster_options().fuse_expand) {
+        LFS_BWD_LAUNCH(false, 4, 1);
+    } else if (variant == 1) {
+        LFS_BWD_LAUNCH(true, 4, 8);
+    } else if (variant == 2) {
+        LFS_BWD_LAUNCH(true, 2, 16);
+    } else if (variant == 3) {
+        LFS_BWD_LAUNCH(true, 1, 32);
+    } else if (variant == 4) {
+        LFS_BWD_LAUNCH(true, 2, 1);
+    } else {
+        LFS_BWD_LAUNCH(true, 4, 1);
+    }
+#undef LFS_BWD_LAUNCH
     LFS_LAUNCH_OK("k_blend_bwd");
     return LFS_OK;
 }

@@ -65,6 +65,9 @@ struct RasterBuffers {
 // Tunables (process-wide; set through lfs_set_option).
 struct RasterOptions {
     int use_tma = 1; // stage InstRec batches with cp.async.bulk + mbarrier (1) or register-staged loads (0)
+    int bwd_variant = 0; // backward blend launch shape under test (warps per CTA / register cap), see launch_blend_bwd
+    int pre_bwd_split = 1; // trainer: SH / geometry halves of the per-Gaussian backward as two launches (A/B switch)
+    int fuse_expand = 1; // blends gather GaussRec and expand in-kernel (no InstRec array, no expand launch)
 };
 RasterOptions& raster_options();
 
@@ -77,8 +80,8 @@ int launch_bucket_offsets(const RasterBuffers& rb, uint32_t n_tiles_total, uint3
                           uint32_t* counts_tmp, cudaStream_t stream);
 
 // forward blend. renders/alphas/last_ids (gsplat layouts) are optional; backgrounds [C,3] / masks optional.
-int launch_blend_fwd(const RasterBuffers& rb, uint32_t C, uint32_t width, uint32_t height, uint32_t tile_w,
-                     uint32_t tile_h, bool write_ckpt, const float* backgrounds, const uint8_t* masks, float* renders,
+int launch_blend_fwd(const RasterBuffers& rb, const ViewCam* cams_dev, uint32_t C, uint32_t width, uint32_t height,
+                     uint32_t tile_w, uint32_t tile_h, bool write_ckpt, const float* backgrounds, const uint8_t* masks, float* renders,
                      float* alphas, int32_t* last_ids, cudaStream_t stream);
 
 // backward blend: v_pix [C*H*W] = (dL/d rgb, T_final * (dL/d alpha - <bg, dL/d rgb>)).

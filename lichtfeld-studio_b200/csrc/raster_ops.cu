@@ -162,9 +162,12 @@ static int raster_front(const RasterScratch& s, RasterBuffers& rb, const float* 
     rb.tile_max_contrib = s.tile_max;
     rb.pix_state = s.pix_state;
     rb.n_contrib = s.n_contrib;
-    int rc = launch_expand_instances(rb, s.cams, n_tiles, tile_w, (uint32_t)n_isects, nullptr, nullptr, C, N, stream);
-    if (rc)
-        return rc;
+    int rc = LFS_OK;
+    if (!raster_options().fuse_expand) {
+        rc = launch_expand_instances(rb, s.cams, n_tiles, tile_w, (uint32_t)n_isects, nullptr, nullptr, C, N, stream);
+        if (rc)
+            return rc;
+    }
     if (bwd) {
         rc = launch_bucket_offsets(rb, n_tiles_total, s.n_buckets, s.scan_scratch, s.counts_tmp, stream);
         if (rc)
@@ -215,7 +218,7 @@ extern "C" int lfs_rasterize_to_pixels_from_world_3dgs_fwd(
                       tile_offsets, flatten_ids, n_isects, false, stream);
     if (rc)
         return rc;
-    return launch_blend_fwd(rb, C, image_width, image_height, tile_w, tile_h, false, backgrounds, masks, renders, alphas,
+    return launch_blend_fwd(rb, s.cams, C, image_width, image_height, tile_w, tile_h, false, backgrounds, masks, renders, alphas,
                             last_ids, stream);
 }
 
@@ -264,7 +267,7 @@ extern "C" int lfs_rasterize_to_pixels_from_world_3dgs_bwd(
                       tile_offsets, flatten_ids, n_isects, true, stream);
     if (rc)
         return rc;
-    rc = launch_blend_fwd(rb, C, image_width, image_height, tile_w, tile_h, true, nullptr, masks, nullptr, nullptr,
+    rc = launch_blend_fwd(rb, s.cams, C, image_width, image_height, tile_w, tile_h, true, nullptr, masks, nullptr, nullptr,
                           nullptr, stream);
     if (rc)
         return rc;

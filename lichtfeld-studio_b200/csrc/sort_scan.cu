@@ -214,8 +214,12 @@ __global__ void __launch_bounds__(kRsThreads)
                  const uint32_t* __restrict__ table, const uint32_t* __restrict__ base) {
     extern __shared__ uint32_t sh[];
     constexpr int kWarps = kRsThreads / 32;
+    __shared__ uint32_t s_scan[33];
     uint32_t* whist = sh;                 // [kWarps][ndig]
-    uint32_t* sbase = sh + kWarps * ndig; // [ndig]
+    uint32_t* sbase = sh + kWarps * ndig; // [ndig] global start of this block's run of digit d
+    uint32_t* dstart = sbase + ndig;      // [ndig] block-local start of digit d
+    uint32_t* skey = dstart + ndig;       // [kRsTile]
+    uint32_t* sval = skey + kRsTile;      // [kRsTile]
     const uint32_t n = resolve_n(n_cap, n_dev);
     const uint32_t blk_base = blockIdx.x * kRsTile;
     if (blk_base >= n)
@@ -245,6 +249,7 @@ __global__ void __launch_bounds__(kRsThreads)
         lrank[r] = before + rank;
     }
     __syncthreads();
+    // warp-private counts -> exclusive prefix over the warps; digit totals of this block into dtot
     for (int d = threadIdx.x; d < ndig; d += kRsThreads) {
         uint32_t run = 0;
 #pragma unroll
@@ -253,19 +258,53 @@ __global__ void __launch_bounds__(kRsThreads)
             whist[w * ndig + d] = run;
             run += t;
         }
+        dstart[d] = run;
         sbase[d] = base[d] + table[(size_t)d * nblk + blockIdx.x];
     }
     __syncthreads();
+    { // exclusive scan of the digit totals (block-local start of every digit's run)
+        const int per = ndig > kRsThreads ? ndig / kRsThreads : 1;
+        const int d0 = threadIdx.x * per;
+        uint32_t sum = 0;
+        for (int k = 0; k < per; ++k)
+            if (d0 + k < ndig)
+                sum += dstart[d0 + k];
+        uint32_t total;
+        const uint32_t incl = block_inclusive_scan(sum, s_scan, &total);
+        uint32_t run = incl - sum;
+        for (int k = 0; k < per; ++k)
+            if (d0 + k < ndig) {
+                const uint32_t t = dstart[d0 + k];
+                dstart[d0 + k] = run;
+                run += t;
+            }
+    }
+    __syncthreads();
+    // block-local reorder through shared memory, then every digit's run leaves as one contiguous, coalesced segment
+    // (before: 32 lanes of a store hit up to 32 different runs -> one 32-B sector per 4-B element)
 #pragma unroll
     for (int r = 0; r < kRsItems; ++r) {
         const uint32_t i = wbase + r * 32 + lane;
         if (i < n) {
             const uint32_t d = (key[r] >> shift) & (uint32_t)(ndig - 1);
-            const uint32_t pos = sbase[d] + wh[d] + lrank[r];
-            keys_out[pos] = key[r];
-            vals_out[pos] = val[r];
+            const uint32_t lp = dstart[d] + wh[d] + lrank[r];
+            skey[lp] = key[r];
+            sval[lp] = val[r];
         }
     }
+    __syncthreads();
+    const uint32_t n_here = n - blk_base < (uint32_t)kRsTile ? n - blk_base : (uint32_t)kRsTile;
+    for (uint32_t t = threadIdx.x; t < n_here; t += kRsThreads) {
+        const uint32_t k = skey[t];
+        const uint32_t d = (k >> shift) & (uint32_t)(ndig - 1);
+        const uint32_t pos = sbase[d] + (t - dstart[d]);
+        keys_out[pos] = k;
+        vals_out[pos] = sval[t];
+    }
+}
+
+static size_t rs_scatter_smem(int ndig) {
+    return sizeof(uint32_t) * ((size_t)(kRsThreads / 32 + 2) * ndig + 2 * (size_t)kRsTile);
 }
 
 int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t n_cap,
@@ -276,7 +315,7 @@ int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint3
         return LFS_OK;
     // per-device attribute; cheap enough to set on every call (one process may drive several devices)
     LFS_CUDA_OK(cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)(sizeof(uint32_t) * (kRsThreads / 32 + 1) * (1 << kRsMaxBits))));
+                                     (int)rs_scatter_smem(1 << kRsMaxBits)));
     const RadixPlan plan = make_radix_plan(begin_bit, n_bits);
     const uint32_t nblk = div_up(n_cap, kRsTile);
     uint32_t* table = static_cast<uint32_t*>(scratch);
@@ -292,7 +331,7 @@ int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint3
         LFS_LAUNCH_OK("k_rs_scan_rows");
         k_rs_scan_totals<<<1, 1024, 0, stream>>>(totals, base, ndig);
         LFS_LAUNCH_OK("k_rs_scan_totals");
-        k_rs_scatter<<<nblk, kRsThreads, sizeof(uint32_t) * (kRsThreads / 32 + 1) * ndig, stream>>>(
+        k_rs_scatter<<<nblk, kRsThreads, rs_scatter_smem(ndig), stream>>>(
             kin, vin, kout, vout, n_cap, n_dev, plan.shift[p], ndig, nblk, table, base);
         LFS_LAUNCH_OK("k_rs_scatter");
         uint32_t* t = kin;

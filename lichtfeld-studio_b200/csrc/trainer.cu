@@ -171,6 +171,15 @@ __global__ void __launch_bounds__(256)
         return;
     const size_t Np = pl.Np;
     auto P = [&](uint32_t plane) { return __ldg(arena + (size_t)plane * Np + g); };
+    // The SH planes are only needed after the (long) projection and only for visible Gaussians; pull them towards
+    // L2 now so that second phase does not pay a full DRAM round trip (costs no registers, unlike early loads).
+    {
+        const int nb = (cfg.degree + 1) * (cfg.degree + 1);
+        for (int k = 0; k < nb; ++k)
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(arena + (size_t)pl.sh(k, ch) * Np + g));
+    }
     const f3 mean = mk3(P(pl.mean(0)), P(pl.mean(1)), P(pl.mean(2)));
     const f3 scale = mk3(__expf(P(pl.scaling(0))), __expf(P(pl.scaling(1))), __expf(P(pl.scaling(2))));
     float qw = P(pl.rotation(0)), qx = P(pl.rotation(1)), qy = P(pl.rotation(2)), qz = P(pl.rotation(3));
@@ -252,12 +261,6 @@ __global__ void __launch_bounds__(256)
     const f3 vs = mk3(v_scales[3 * (size_t)g], v_scales[3 * (size_t)g + 1], v_scales[3 * (size_t)g + 2]);
     f3 vc = mk3(v_colors[3 * (size_t)g], v_colors[3 * (size_t)g + 1], v_colors[3 * (size_t)g + 2]);
     const float vo = v_opac[g];
-    v_means[3 * (size_t)g] = v_means[3 * (size_t)g + 1] = v_means[3 * (size_t)g + 2] = 0.f;
-    reinterpret_cast<float4*>(v_quats)[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-    v_scales[3 * (size_t)g] = v_scales[3 * (size_t)g + 1] = v_scales[3 * (size_t)g + 2] = 0.f;
-    v_colors[3 * (size_t)g] = v_colors[3 * (size_t)g + 1] = v_colors[3 * (size_t)g + 2] = 0.f;
-    v_opac[g] = 0.f;
-
     // ---- all loads first (independent, coalesced plane reads): parameters, SH coefficients, old gradients.
     // The read-modify-write of the gradient planes must not be written as `g[i] += v` one after the other:
     // the compiler then serialises 59 dependent DRAM round trips per thread (measured 1.03 ms per view).
@@ -352,6 +355,120 @@ __global__ void __launch_bounds__(256)
     grads[(size_t)pl.rotation(1) * Np + g] = gq[1] + (vq.y - dq * nx) * inv;
     grads[(size_t)pl.rotation(2) * Np + g] = gq[2] + (vq.z - dq * ny) * inv;
     grads[(size_t)pl.rotation(3) * Np + g] = gq[3] + (vq.w - dq * nz) * inv;
+    // clear the per-view accumulators LAST: a store issued right behind a load of the same address holds back every
+    // later load of the thread for one DRAM round trip (tools/micro/planar_rmw_variants.cu: 0.20 ms vs 0.13 ms)
+    v_means[3 * (size_t)g] = v_means[3 * (size_t)g + 1] = v_means[3 * (size_t)g + 2] = 0.f;
+    reinterpret_cast<float4*>(v_quats)[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    v_scales[3 * (size_t)g] = v_scales[3 * (size_t)g + 1] = v_scales[3 * (size_t)g + 2] = 0.f;
+    v_colors[3 * (size_t)g] = v_colors[3 * (size_t)g + 1] = v_colors[3 * (size_t)g + 2] = 0.f;
+    v_opac[g] = 0.f;
+}
+
+// Two launches instead of one 255-register kernel (ncu r01c: 12 % occupancy, 2.1 TB/s):
+//  k_preprocess_bwd_sh  -- one thread per (Gaussian, colour channel): 16 coefficient planes read-modify-written per
+//                          thread, the channel's share of dL/d(dir) goes to the mean-gradient planes with 3 RED atomics;
+//  k_preprocess_bwd_geo -- one thread per Gaussian: activation VJPs of mean / scale / quat / opacity, and clears the
+//                          per-view activated-space accumulators for the next view.
+template <int DEG>
+__global__ void __launch_bounds__(256)
+    k_preprocess_bwd_sh(const float* __restrict__ arena, float* __restrict__ grads, const Planes pl, const uint32_t N,
+                        const ViewCam cam, const int32_t* __restrict__ counts, float* __restrict__ v_colors) {
+    constexpr int NB = (DEG + 1) * (DEG + 1);
+    const uint32_t g = blockIdx.x * 256 + threadIdx.x;
+    const int ch = blockIdx.y;
+    if (g >= N || counts[g] <= 0)
+        return;
+    const size_t Np = pl.Np;
+    float vc = v_colors[3 * (size_t)g + ch];
+    float cf[NB], go[NB];
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        cf[k] = __ldg(arena + (size_t)pl.sh(k, ch) * Np + g);
+        go[k] = grads[(size_t)pl.sh(k, ch) * Np + g];
+    }
+    float x = 0.f, y = 0.f, z = 0.f, inorm = 0.f;
+    if (DEG >= 1) {
+        const f3 dir = mk3(__ldg(arena + (size_t)pl.mean(0) * Np + g) - cam.org[0],
+                           __ldg(arena + (size_t)pl.mean(1) * Np + g) - cam.org[1],
+                           __ldg(arena + (size_t)pl.mean(2) * Np + g) - cam.org[2]);
+        inorm = rsqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
+        x = dir.x * inorm, y = dir.y * inorm, z = dir.z * inorm;
+    }
+    ShBasis B;
+    sh_bases(DEG, x, y, z, B);
+    float col = 0.f;
+#pragma unroll
+    for (int k = 0; k < NB; ++k)
+        col += B.b[k] * cf[k];
+    if (col + 0.5f < 0.f) // clamp_min(c + 0.5, 0) passes the gradient where c + 0.5 >= 0
+        vc = 0.f;
+    float sdot[25];
+#pragma unroll
+    for (int k = 0; k < 25; ++k)
+        sdot[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        grads[(size_t)pl.sh(k, ch) * Np + g] = fmaf(B.b[k], vc, go[k]);
+        if (k >= 1)
+            sdot[k] = cf[k] * vc;
+    }
+    if (DEG >= 1 && vc != 0.f) {
+        const f3 vdn = sh_bases_vjp(DEG, x, y, z, sdot);
+        const float dt = vdn.x * x + vdn.y * y + vdn.z * z;
+        atomicAdd(grads + (size_t)pl.mean(0) * Np + g, (vdn.x - dt * x) * inorm);
+        atomicAdd(grads + (size_t)pl.mean(1) * Np + g, (vdn.y - dt * y) * inorm);
+        atomicAdd(grads + (size_t)pl.mean(2) * Np + g, (vdn.z - dt * z) * inorm);
+    }
+    v_colors[3 * (size_t)g + ch] = 0.f; // cleared last, see k_preprocess_bwd
+}
+
+__global__ void __launch_bounds__(256)
+    k_preprocess_bwd_geo(const float* __restrict__ arena, float* __restrict__ grads, const Planes pl, const uint32_t N,
+                         const int32_t* __restrict__ counts, float* __restrict__ v_means, float* __restrict__ v_quats,
+                         float* __restrict__ v_scales, float* __restrict__ v_opac) {
+    const uint32_t g = blockIdx.x * 256 + threadIdx.x;
+    if (g >= N || counts[g] <= 0)
+        return;
+    const size_t Np = pl.Np;
+    auto P = [&](uint32_t plane) { return __ldg(arena + (size_t)plane * Np + g); };
+    const f3 vm = mk3(v_means[3 * (size_t)g], v_means[3 * (size_t)g + 1], v_means[3 * (size_t)g + 2]);
+    const float4 vq = reinterpret_cast<float4*>(v_quats)[g];
+    const f3 vs = mk3(v_scales[3 * (size_t)g], v_scales[3 * (size_t)g + 1], v_scales[3 * (size_t)g + 2]);
+    const float vo = v_opac[g];
+    // loads first, stores last (independent DRAM round trips overlap)
+    const float sraw[3] = {P(pl.scaling(0)), P(pl.scaling(1)), P(pl.scaling(2))};
+    const float qraw[4] = {P(pl.rotation(0)), P(pl.rotation(1)), P(pl.rotation(2)), P(pl.rotation(3))};
+    const float oraw = P(pl.opacity());
+    float gs[3], gq[4], gop;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        gs[c] = grads[(size_t)pl.scaling(c) * Np + g];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        gq[c] = grads[(size_t)pl.rotation(c) * Np + g];
+    gop = grads[(size_t)pl.opacity() * Np + g];
+
+    const float op = sigmoidf_(oraw);
+    const float nrm = fmaxf(sqrtf(qraw[0] * qraw[0] + qraw[1] * qraw[1] + qraw[2] * qraw[2] + qraw[3] * qraw[3]), 1e-12f);
+    const float inv = 1.0f / nrm;
+    const float nw = qraw[0] * inv, nx = qraw[1] * inv, ny = qraw[2] * inv, nz = qraw[3] * inv;
+    const float dq = vq.x * nw + vq.y * nx + vq.z * ny + vq.w * nz;
+    // the SH kernel adds its dL/d(dir) share to the same planes with atomics -> RED here as well (no ordering needed)
+    atomicAdd(grads + (size_t)pl.mean(0) * Np + g, vm.x);
+    atomicAdd(grads + (size_t)pl.mean(1) * Np + g, vm.y);
+    atomicAdd(grads + (size_t)pl.mean(2) * Np + g, vm.z);
+    grads[(size_t)pl.scaling(0) * Np + g] = fmaf(vs.x, __expf(sraw[0]), gs[0]); // scale = exp(raw)
+    grads[(size_t)pl.scaling(1) * Np + g] = fmaf(vs.y, __expf(sraw[1]), gs[1]);
+    grads[(size_t)pl.scaling(2) * Np + g] = fmaf(vs.z, __expf(sraw[2]), gs[2]);
+    grads[(size_t)pl.opacity() * Np + g] = fmaf(vo, op * (1.0f - op), gop); // opacity = sigmoid(raw)
+    grads[(size_t)pl.rotation(0) * Np + g] = gq[0] + (vq.x - dq * nw) * inv; // q_n = q / max(|q|, eps)
+    grads[(size_t)pl.rotation(1) * Np + g] = gq[1] + (vq.y - dq * nx) * inv;
+    grads[(size_t)pl.rotation(2) * Np + g] = gq[2] + (vq.z - dq * ny) * inv;
+    grads[(size_t)pl.rotation(3) * Np + g] = gq[3] + (vq.w - dq * nz) * inv;
+    v_means[3 * (size_t)g] = v_means[3 * (size_t)g + 1] = v_means[3 * (size_t)g + 2] = 0.f;
+    reinterpret_cast<float4*>(v_quats)[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    v_scales[3 * (size_t)g] = v_scales[3 * (size_t)g + 1] = v_scales[3 * (size_t)g + 2] = 0.f;
+    v_opac[g] = 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -596,12 +713,14 @@ extern "C" int lfs_trainer_view_forward(void* h, const float* params_arena, cons
     rc = launch_bucket_offsets(rb, t->n_tiles, t->n_inst + 1, t->scan_scr, t->bucket_counts, stream);
     if (rc)
         return rc;
-    rc = launch_expand_instances(rb, t->cam_dev, t->n_tiles, t->tile_w, t->inst_cap, t->n_inst, t->sorted_keys, 1, N,
-                                 stream);
-    if (rc)
-        return rc;
+    if (!raster_options().fuse_expand) {
+        rc = launch_expand_instances(rb, t->cam_dev, t->n_tiles, t->tile_w, t->inst_cap, t->n_inst, t->sorted_keys, 1,
+                                     N, stream);
+        if (rc)
+            return rc;
+    }
     t->mark(3, stream);
-    rc = launch_blend_fwd(rb, 1, t->d.width, t->d.height, t->tile_w, t->tile_h, true, nullptr, nullptr, nullptr,
+    rc = launch_blend_fwd(rb, t->cam_dev, 1, t->d.width, t->d.height, t->tile_w, t->tile_h, true, nullptr, nullptr, nullptr,
                           nullptr, nullptr, stream);
     if (rc)
         return rc;
@@ -669,10 +788,29 @@ extern "C" int lfs_trainer_view_backward(void* h, const float* params_arena, flo
     if (rc)
         return rc;
     t->mark(6, stream);
-    k_preprocess_bwd<<<div_up(N, 256), 256, 0, stream>>>(params_arena, grads_arena, t->pl, N, t->cam_host,
-                                                         (int)t->active_degree, t->counts, t->v_means, t->v_quats,
-                                                         t->v_scales, t->v_colors, t->v_opac);
-    LFS_LAUNCH_OK("k_preprocess_bwd");
+    if (!raster_options().pre_bwd_split) {
+        k_preprocess_bwd<<<div_up(N, 256), 256, 0, stream>>>(params_arena, grads_arena, t->pl, N, t->cam_host,
+                                                             (int)t->active_degree, t->counts, t->v_means, t->v_quats,
+                                                             t->v_scales, t->v_colors, t->v_opac);
+        LFS_LAUNCH_OK("k_preprocess_bwd");
+    } else {
+        const dim3 grid_sh(div_up(N, 256), 3);
+#define LFS_SH_BWD(D)                                                                                                  \
+    k_preprocess_bwd_sh<D><<<grid_sh, 256, 0, stream>>>(params_arena, grads_arena, t->pl, N, t->cam_host, t->counts,     \
+                                                        t->v_colors)
+        switch ((int)t->active_degree) {
+        case 0: LFS_SH_BWD(0); break;
+        case 1: LFS_SH_BWD(1); break;
+        case 2: LFS_SH_BWD(2); break;
+        case 3: LFS_SH_BWD(3); break;
+        default: LFS_SH_BWD(4); break;
+        }
+#undef LFS_SH_BWD
+        LFS_LAUNCH_OK("k_preprocess_bwd_sh");
+        k_preprocess_bwd_geo<<<div_up(N, 256), 256, 0, stream>>>(params_arena, grads_arena, t->pl, N, t->counts,
+                                                                 t->v_means, t->v_quats, t->v_scales, t->v_opac);
+        LFS_LAUNCH_OK("k_preprocess_bwd_geo");
+    }
     t->mark(7, stream);
     if (t->profile && t->ev_ok) { // fold this view's stage times into the running sums (blocks: profiling only)
         cudaEventSynchronize(t->ev[7]);

@@ -48,9 +48,12 @@ def test_intersect_bit_exact():
     assert r["big_sorted_n"] > 100000 and r["empty_sorted_n"] == 0
 
 
-@pytest.mark.parametrize("tma", [0, 1])
-def test_rasterize_fwd_bwd(tma):
-    r = D.diag_raster(tma=tma)
+BLEND_MODES = [(0, 0), (1, 0), (1, 1)]  # (blend_tma, blend_fused): register-staged, TMA-staged, fused expansion
+
+
+@pytest.mark.parametrize("tma,fused", BLEND_MODES)
+def test_rasterize_fwd_bwd(tma, fused):
+    r = D.diag_raster(tma=tma, fused=fused)
     assert r["n_isects"] > 5000
     assert r["fwd_rgb_rel"] <= 1e-4 and r["fwd_alpha_rel"] <= 1e-4, r
     assert r["fwd_last_ids_mismatch"] <= r["n_pixels"] // 500, r
@@ -76,11 +79,11 @@ def test_adam():
         assert r["ref_update_rel"] <= 1e-5, r
 
 
-@pytest.mark.parametrize("tma", [0, 1])
-def test_fused_trainer_step(tma):
-    r = D.diag_trainer(tma=tma)
-    if tma == 0:
-        D.L.load().lfs_set_option(b"blend_tma", 1)
+@pytest.mark.parametrize("tma,fused", BLEND_MODES)
+def test_fused_trainer_step(tma, fused):
+    r = D.diag_trainer(tma=tma, fused=fused)
+    D.L.load().lfs_set_option(b"blend_tma", 1)
+    D.L.load().lfs_set_option(b"blend_fused", 1)
     assert r["pack_roundtrip_exact"]
     for v in (0, 1):
         # fused step vs the same device code composed op by op (strict) ...
