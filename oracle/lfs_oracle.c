@@ -15,12 +15,14 @@
 #define REAL float
 #define PFX orc32_
 #include "lfs_oracle_impl.h"
+#include "lfs_oracle_fastgs_impl.h"
 #undef REAL
 #undef PFX
 
 #define REAL double
 #define PFX orc64_
 #include "lfs_oracle_impl.h"
+#include "lfs_oracle_fastgs_impl.h"
 #undef REAL
 #undef PFX
 

@@ -226,3 +226,51 @@ def view_loss_grads(scene_raw, viewmat, K, width, height, sh_degree, bg, v_image
                  rotation=(v_quats - dq * q) / nrm, opacity=(v_opac * op * (1.0 - op))[:, None])
     r["loss"] = loss
     return r, grads
+
+
+def fastgs(means, scales_raw, rotations_raw, opacities_raw, sh0, shN, w2c, cam_pos, active_sh_bases, width, height,
+           fx, fy, cx, cy, near=0.01, far=1e10, grad_image=None, grad_alpha=None, want_w2c_grad=False,
+           densification_info=None, prec=64):
+    """Reference fastgs (EWA) forward [+ backward when grad_image is given]; reference tensor layouts
+    (fastgs/rasterization/include/rasterization_api.h:26-75). Returns a dict."""
+    dt, pfx, cf = _dt(prec)
+    means, scales_raw, rotations_raw = _a(means, dt), _a(scales_raw, dt), _a(rotations_raw, dt)
+    opacities_raw = _a(np.asarray(opacities_raw).reshape(-1), dt)
+    N = means.shape[0]
+    sh0 = _a(np.asarray(sh0).reshape(N, 3), dt)
+    shN = _a(np.asarray(shN).reshape(N, -1, 3), dt)
+    total_rest = shN.shape[1]
+    w2c, cam_pos = _a(np.asarray(w2c).reshape(4, 4), dt), _a(np.asarray(cam_pos).reshape(3), dt)
+    image = np.zeros((3, height, width), dt)
+    alpha = np.zeros((1, height, width), dt)
+    n_touched = np.zeros(N, np.int32)
+    out = {}
+    bwd = grad_image is not None
+    if bwd:
+        gi, ga = _a(grad_image, dt), _a(np.asarray(grad_alpha).reshape(height, width), dt)
+        g = dict(means=np.zeros((N, 3), dt), scales_raw=np.zeros((N, 3), dt), rotations_raw=np.zeros((N, 4), dt),
+                 opacities_raw=np.zeros((N, 1), dt), sh0=np.zeros((N, 1, 3), dt), shN=np.zeros((N, total_rest, 3), dt))
+        gw = np.zeros((4, 4), dt) if want_w2c_grad else None
+        dens = None if densification_info is None else _a(densification_info, dt).copy()
+    else:
+        gi = ga = gw = dens = None
+        g = dict(means=None, scales_raw=None, rotations_raw=None, opacities_raw=None, sh0=None, shN=None)
+    fn = getattr(lib(), pfx + "fastgs")
+    fn.restype = C.c_int64
+    n_inst = fn(C.c_int(N), _p(means), _p(scales_raw), _p(rotations_raw), _p(opacities_raw), _p(sh0), _p(shN),
+                C.c_int(total_rest), _p(w2c), _p(cam_pos), C.c_int(active_sh_bases), C.c_int(width), C.c_int(height),
+                cf(fx), cf(fy), cf(cx), cf(cy), cf(near), cf(far), _p(image), _p(alpha), _p(n_touched), _p(gi), _p(ga),
+                _p(g["means"]), _p(g["scales_raw"]), _p(g["rotations_raw"]), _p(g["opacities_raw"]), _p(g["sh0"]),
+                _p(g["shN"]), _p(gw), _p(dens))
+    out.update(image=image, alpha=alpha, n_touched=n_touched, n_instances=int(n_inst))
+    if bwd:
+        out.update(grads=g, grad_w2c=gw, densification_info=dens)
+    return out
+
+
+def fastgs_inputs(sc, view=0):
+    """(w2c [4,4], cam_position [3], fx, fy, cx, cy) of a scene view, as fast_rasterizer.cpp:20-45 derives them."""
+    vm = np.asarray(sc.viewmats[view], np.float64)
+    K = np.asarray(sc.Ks[view], np.float64)
+    cam_pos = -vm[:3, :3].T @ vm[:3, 3]
+    return vm, cam_pos, float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])
