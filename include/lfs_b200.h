@@ -182,6 +182,49 @@ int lfs_relocation(const float* opacities, const float* scales, const int32_t* r
 int lfs_add_noise(const float* raw_opacities, const float* raw_scales, const float* raw_quats, const float* noise,
                   float* means, float current_lr, uint32_t n, void* stream);
 
+/* ---- fastgs (EWA) rasterizer surface ----------------------------------------------------------------------
+ * Replaces fast_gs::rasterization::forward (fastgs/rasterization/include/forward.h:13-38, src/forward.cu:15-199;
+ * called by forward_wrapper, src/rasterization_api.cu:15-89, which fast_rasterize() binds,
+ * src/training/rasterization/fast_rasterizer.cpp:12-60).  RAW parameters, reference layouts:
+ * means [N,3], scales_raw [N,3] (log), rotations_raw [N,4] (w,x,y,z, not normalised), opacities_raw [N,1] (logit),
+ * sh_coefficients_0 [N,1,3], sh_coefficients_rest [N,total_bases_sh_rest,3], w2c [4,4] row-major on the DEVICE,
+ * cam_position [3] on the DEVICE; active_sh_bases in {1,4,9,16}.  Outputs image [3,H,W] (no background), alpha [1,H,W].
+ * The four state buffers of the reference (buffer_utils.h:38-151) are requested through `alloc` with the tags below,
+ * must stay valid and unmodified until the matching backward (fast_rasterizer_autograd.cpp:61-72), and their contents
+ * are private to this library.  Like the reference the call blocks twice to read n_instances and n_buckets.
+ * Equal-depth primitives are ordered by index (the reference's order there is non-deterministic).  Launches on
+ * `stream` (the reference uses the legacy default stream and a process-global memset stream; this is re-entrant). */
+#define LFS_TAG_FG_PER_PRIMITIVE 10
+#define LFS_TAG_FG_PER_TILE 11
+#define LFS_TAG_FG_PER_INSTANCE 12
+#define LFS_TAG_FG_PER_BUCKET 13
+int lfs_fastgs_forward(const float* means, const float* scales_raw, const float* rotations_raw,
+                       const float* opacities_raw, const float* sh_coefficients_0, const float* sh_coefficients_rest,
+                       const float* w2c, const float* cam_position, uint32_t n_primitives, int active_sh_bases,
+                       int total_bases_sh_rest, int width, int height, float focal_x, float focal_y, float center_x,
+                       float center_y, float near_plane, float far_plane, float* image, float* alpha,
+                       lfs_alloc_fn alloc, void* alloc_ctx, int* n_visible_primitives, int* n_instances,
+                       int* n_buckets, int* instance_selector, void* stream);
+
+/* Replaces fast_gs::rasterization::backward (include/backward.h:13-52, src/backward.cu:14-116; called by
+ * backward_wrapper, src/rasterization_api.cu:91-181).  grad_image [3,H,W], grad_alpha [1,H,W]; the four buffers and
+ * the three counters come from the matching lfs_fastgs_forward.  Writes ALL N rows of grad_means [N,3],
+ * grad_scales_raw [N,3], grad_rotations_raw [N,4], grad_opacities_raw [N,1], grad_sh_coefficients_0 [N,1,3],
+ * grad_sh_coefficients_rest [N,total,3] (zeros for primitives that touched no tile; the reference relies on
+ * torch::zeros for those).  grad_w2c [4,4] (nullable) is ACCUMULATED into rows 0-2 exactly as the reference does
+ * (kernels_backward.cuh:162-175); densification_info [2,N] (nullable) is accumulated (:233-236).
+ * Scratch is requested through `alloc` with LFS_TAG_SCRATCH. */
+int lfs_fastgs_backward(const float* grad_image, const float* grad_alpha, const float* means, const float* scales_raw,
+                        const float* rotations_raw, const float* sh_coefficients_rest, const float* w2c,
+                        const float* cam_position, const void* per_primitive_buffers, const void* per_tile_buffers,
+                        const void* per_instance_buffers, const void* per_bucket_buffers, float* grad_means,
+                        float* grad_scales_raw, float* grad_rotations_raw, float* grad_opacities_raw,
+                        float* grad_sh_coefficients_0, float* grad_sh_coefficients_rest, float* grad_w2c,
+                        float* densification_info, uint32_t n_primitives, int n_instances, int n_buckets,
+                        int instance_selector, int active_sh_bases, int total_bases_sh_rest, int width, int height,
+                        float focal_x, float focal_y, float center_x, float center_y, lfs_alloc_fn alloc,
+                        void* alloc_ctx, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * fused training step (the fast path; what bench.py times)
  *

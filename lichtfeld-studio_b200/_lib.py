@@ -17,6 +17,8 @@ CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 LFS_OK = 0
 LFS_ERR_UNSUPPORTED = -2
 LFS_ERR_CAPACITY = -5
+LFS_TAG_SCRATCH, LFS_TAG_ISECT_IDS, LFS_TAG_FLATTEN_IDS = 0, 1, 2
+LFS_TAG_FG_PER_PRIMITIVE, LFS_TAG_FG_PER_TILE, LFS_TAG_FG_PER_INSTANCE, LFS_TAG_FG_PER_BUCKET = 10, 11, 12, 13
 
 PINHOLE, ORTHO, FISHEYE = 0, 1, 2
 SHUTTER_GLOBAL = 4
@@ -85,6 +87,14 @@ SIGNATURES = {
         C.c_int,
         [_vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, C.c_int, _vp, ALLOC_FN, _vp, C.POINTER(_vp), C.POINTER(_vp),
          C.POINTER(_i64), _vp],
+    ),
+    "lfs_fastgs_forward": (
+        C.c_int,
+        [_vp] * 8 + [_u32] + [C.c_int] * 4 + [C.c_float] * 6 + [_vp, _vp, ALLOC_FN, _vp] + [C.POINTER(C.c_int)] * 4 + [_vp],
+    ),
+    "lfs_fastgs_backward": (
+        C.c_int,
+        [_vp] * 8 + [_vp] * 4 + [_vp] * 8 + [_u32] + [C.c_int] * 7 + [C.c_float] * 4 + [ALLOC_FN, _vp, _vp],
     ),
     "lfs_intersect_offset": (C.c_int, [_vp, _i64, _u32, _u32, _u32, _vp, _vp]),
     "lfs_rasterize_to_pixels_from_world_3dgs_fwd": (

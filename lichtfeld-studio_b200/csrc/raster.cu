@@ -63,6 +63,26 @@ __device__ __forceinline__ void expand_record(const float4 g0, const float4 g1, 
     Cc.w = dot_rn(vy, vy);
 }
 
+// EWA (fastgs surface) record: g0 = (mean2d.x, mean2d.y, conic.a, conic.b), g1 = (conic.c, opacity, r, g), g2.x = b
+// (colour before the clamp).  sigma/2 = 1/2 a ex^2 + 1/2 c ey^2 + b ex ey with e = mean2d - pixel is a plain quadratic
+// in the tile-local pixel offset (dx, dy):  N'(dx,dy) = -log2(e) * sigma/2, D == 1.
+//   A = (n0, n1x, n1y, n2xx)   B = (n2xy, n2yy, opacity, max(r,0))   C = (max(g,0), max(b,0), -, -)
+constexpr float kEScale = -1.4426950408889634f; // -log2(e)
+__device__ __forceinline__ void expand_record_ewa(const float4 g0, const float4 g1, const float4 g2, const float tcx,
+                                                  const float tcy, float4& A, float4& B, float4& Cc) {
+    const float ex = g0.x - tcx, ey = g0.y - tcy, a = g0.z, b = g0.w, c = g1.x;
+    const float ax = fmaf(a, ex, __fmul_rn(b, ey)), cy = fmaf(c, ey, __fmul_rn(b, ex)); // (conic e).x, (conic e).y
+    A.x = __fmul_rn(kEScale * 0.5f, fmaf(ex, ax, __fmul_rn(ey, cy)));
+    A.y = __fmul_rn(-kEScale, ax);
+    A.z = __fmul_rn(-kEScale, cy);
+    A.w = __fmul_rn(kEScale * 0.5f, a);
+    B.x = __fmul_rn(kEScale, b);
+    B.y = __fmul_rn(kEScale * 0.5f, c);
+    B.z = g1.y;
+    B.w = fmaxf(g1.z, 0.f);
+    Cc = make_float4(fmaxf(g1.w, 0.f), fmaxf(g2.x, 0.f), 0.f, 0.f);
+}
+
 __global__ void __launch_bounds__(kExThreads)
     k_expand_instances(const GaussRec* __restrict__ gauss, const int32_t* __restrict__ inst_gid,
                        const int32_t* __restrict__ tile_off, const uint32_t* __restrict__ sorted_tile_keys,
@@ -185,7 +205,8 @@ __device__ __forceinline__ float poly2(const float dx, const float dy, const flo
     return fmaf(dx, fmaf(dx, cxx, fmaf(dy, cxy, cx)), fmaf(dy, fmaf(dy, cyy, cy), c0));
 }
 
-template <int MODE> // 0: register-staged InstRec, 1: TMA-staged InstRec, 2: fused expansion (GaussRec gather)
+template <int MODE, bool EWA> // MODE 0: register-staged InstRec, 1: TMA-staged InstRec, 2: fused expansion (GaussRec gather);
+                               // EWA: fastgs-surface records (2-D conic, D == 1), MODE 2 only
 __global__ void __launch_bounds__(kFwdThreads)
     k_blend_fwd(const RasterBuffers rb, const ViewCam* __restrict__ cams, const uint32_t width, const uint32_t height, const uint32_t tile_w,
                 const uint32_t tile_h, const bool write_ckpt, const float* __restrict__ backgrounds,
@@ -264,7 +285,9 @@ __global__ void __launch_bounds__(kFwdThreads)
     const float4* gsrc = reinterpret_cast<const float4*>(rb.inst + start);
     float Xo = 0.f, Yo = 0.f;
     uint32_t gid_next = 0; // FUSED: flattened Gaussian id this thread expands for the NEXT batch
-    if (FUSED) {
+    if (FUSED && EWA) {
+        Xo = (float)(tx * kTile + kTile / 2), Yo = (float)(ty * kTile + kTile / 2); // tile centre in pixel units
+    } else if (FUSED) {
         Xo = (float)(tx * kTile + kTile / 2) - cams[cam].cx;
         Yo = (float)(ty * kTile + kTile / 2) - cams[cam].cy;
     }
@@ -289,9 +312,13 @@ __global__ void __launch_bounds__(kFwdThreads)
             if ((int)tid < min(kBatch, cnt)) {
                 const float4* gp = reinterpret_cast<const float4*>(rb.gauss + (uint32_t)__ldg(rb.inst_gid + start + tid));
                 float4 A, B, Cc;
-                expand_record(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), Xo, Yo, A, B, Cc);
+                if (EWA) {
+                    expand_record_ewa(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), Xo, Yo, A, B, Cc);
+                } else {
+                    expand_record(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), Xo, Yo, A, B, Cc);
+                    s_rec[0][4 * tid + 3] = __ldg(gp + 3);
+                }
                 s_rec[0][4 * tid] = A, s_rec[0][4 * tid + 1] = B, s_rec[0][4 * tid + 2] = Cc;
-                s_rec[0][4 * tid + 3] = __ldg(gp + 3);
             }
             if ((int)tid < cnt - kBatch)
                 gid_next = (uint32_t)__ldg(rb.inst_gid + start + kBatch + tid);
@@ -345,7 +372,9 @@ __global__ void __launch_bounds__(kFwdThreads)
             next_f4 = (kb + 1 < nbatch) ? min(kBatch, cnt - (kb + 1) * kBatch) : 0;
             if ((int)tid < next_f4) {
                 const float4* gp = reinterpret_cast<const float4*>(rb.gauss + gid_next);
-                pre[0] = __ldg(gp), pre[1] = __ldg(gp + 1), pre[2] = __ldg(gp + 2), pre[3] = __ldg(gp + 3);
+                pre[0] = __ldg(gp), pre[1] = __ldg(gp + 1), pre[2] = __ldg(gp + 2);
+                if (!EWA)
+                    pre[3] = __ldg(gp + 3);
             }
             if ((int)tid < cnt - (kb + 2) * kBatch)
                 gid_next = (uint32_t)__ldg(rb.inst_gid + start + (kb + 2) * kBatch + tid);
@@ -370,16 +399,29 @@ __global__ void __launch_bounds__(kFwdThreads)
                         if ((live >> k) & 1u)
                             c[pid[k]] = make_float4(r[k], g[k], b[k], T[k]);
                 }
-                const float4 A = s[4 * t], B = s[4 * t + 1], Cc = s[4 * t + 2], E = s[4 * t + 3];
+                const float4 A = s[4 * t], B = s[4 * t + 1], Cc = s[4 * t + 2];
+                float4 E;
+                if (EWA)
+                    E = make_float4(B.z, B.w, Cc.x, Cc.y);
+                else
+                    E = s[4 * t + 3];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const float Nv = poly2(dx[k], dy[k], A.x, A.y, A.z, A.w, B.x, B.y);
-                    const float Dv = poly2(dx[k], dy[k], B.z, B.w, Cc.x, Cc.y, Cc.z, Cc.w);
-                    const float vis = ex2_approx(Nv * rcp_approx(Dv));
+                    float vis;
+                    bool ok = true;
+                    if (EWA) {
+                        vis = ex2_approx(Nv);
+                        ok = Nv <= 0.f; // sigma/2 < 0 is skipped (kernels_forward.cuh:423-424)
+                    } else {
+                        const float Dv = poly2(dx[k], dy[k], B.z, B.w, Cc.x, Cc.y, Cc.z, Cc.w);
+                        vis = ex2_approx(Nv * rcp_approx(Dv));
+                    }
                     const float alpha = fminf(kAlphaMax, E.x * vis);
-                    if (((live >> k) & 1u) && alpha >= kAlphaMin) {
+                    if (((live >> k) & 1u) && alpha >= kAlphaMin && ok) {
                         const float next_T = T[k] * (1.0f - alpha);
-                        if (next_T <= kTMin) {
+                        // gsplat stops at T <= 1e-4 (RasterizeToPixelsFromWorld3DGSFwd.cu), fastgs at T < 1e-4
+                        if (EWA ? (next_T < kTMin) : (next_T <= kTMin)) {
                             live &= ~(1u << k);
                         } else {
                             const float w = alpha * T[k];
@@ -405,9 +447,14 @@ __global__ void __launch_bounds__(kFwdThreads)
         if (FUSED) {
             if ((int)tid < next_f4) {
                 float4 A, B, Cc;
-                expand_record(pre[0], pre[1], pre[2], Xo, Yo, A, B, Cc);
                 float4* d = &s_rec[buf ^ 1][4 * tid];
-                d[0] = A, d[1] = B, d[2] = Cc, d[3] = pre[3];
+                if (EWA) {
+                    expand_record_ewa(pre[0], pre[1], pre[2], Xo, Yo, A, B, Cc);
+                } else {
+                    expand_record(pre[0], pre[1], pre[2], Xo, Yo, A, B, Cc);
+                    d[3] = pre[3];
+                }
+                d[0] = A, d[1] = B, d[2] = Cc;
             }
         } else if (!USE_TMA) {
 #pragma unroll
@@ -485,15 +532,25 @@ int launch_blend_fwd(const RasterBuffers& rb, const ViewCam* cams_dev, uint32_t 
         return LFS_OK;
     dim3 grid(tile_w * tile_h, C);
     if (raster_options().fuse_expand)
-        k_blend_fwd<2><<<grid, kFwdThreads, 0, stream>>>(rb, cams_dev, width, height, tile_w, tile_h, write_ckpt,
+        k_blend_fwd<2, false><<<grid, kFwdThreads, 0, stream>>>(rb, cams_dev, width, height, tile_w, tile_h, write_ckpt,
                                                       backgrounds, masks, renders, alphas, last_ids);
     else if (raster_options().use_tma)
-        k_blend_fwd<1><<<grid, kFwdThreads, 0, stream>>>(rb, cams_dev, width, height, tile_w, tile_h, write_ckpt,
+        k_blend_fwd<1, false><<<grid, kFwdThreads, 0, stream>>>(rb, cams_dev, width, height, tile_w, tile_h, write_ckpt,
                                                       backgrounds, masks, renders, alphas, last_ids);
     else
-        k_blend_fwd<0><<<grid, kFwdThreads, 0, stream>>>(rb, cams_dev, width, height, tile_w, tile_h, write_ckpt,
+        k_blend_fwd<0, false><<<grid, kFwdThreads, 0, stream>>>(rb, cams_dev, width, height, tile_w, tile_h, write_ckpt,
                                                       backgrounds, masks, renders, alphas, last_ids);
     LFS_LAUNCH_OK("k_blend_fwd");
+    return LFS_OK;
+}
+
+int launch_blend_fwd_ewa(const RasterBuffers& rb, uint32_t width, uint32_t height, uint32_t tile_w, uint32_t tile_h,
+                         bool write_ckpt, cudaStream_t stream) {
+    if (tile_w == 0 || tile_h == 0)
+        return LFS_OK;
+    k_blend_fwd<2, true><<<dim3(tile_w * tile_h, 1), kFwdThreads, 0, stream>>>(
+        rb, nullptr, width, height, tile_w, tile_h, write_ckpt, nullptr, nullptr, nullptr, nullptr, nullptr);
+    LFS_LAUNCH_OK("k_blend_fwd<ewa>");
     return LFS_OK;
 }
 
@@ -513,7 +570,11 @@ __device__ __forceinline__ void quat_to_rotmat_dev(const float4 q_wxyz, float R[
     R[6] = 2.f * (xz - wy), R[7] = 2.f * (yz + wx), R[8] = 1.f - 2.f * (x2 + y2);
 }
 
-template <bool FUSED, int kBwdWarps, int kMinBlocks>
+// EWA = fastgs surface: records are 2-D conics (D == 1), outputs are the per-primitive helpers of the reference's
+// blend_backward_cu (kernels_backward.cuh:240-449) passed in the slots v_means -> grad_mean2d [N,2],
+// v_quats -> grad_conic [N,3] (a, b, c; b is the TRUE derivative, twice the reference's stored value),
+// v_colors -> grad_color [N,3], v_opacities -> grad_raw_opacity [N]; quats / scales / means / cams are unused.
+template <bool FUSED, int kBwdWarps, int kMinBlocks, bool EWA = false>
 __global__ void __launch_bounds__(kBwdWarps * 32, kMinBlocks)
     k_blend_bwd(const RasterBuffers rb, const ViewCam* __restrict__ cams, const float4* __restrict__ v_pix,
                 const float* __restrict__ quats, const float* __restrict__ scales, const float* __restrict__ means,
@@ -545,15 +606,18 @@ __global__ void __launch_bounds__(kBwdWarps * 32, kMinBlocks)
     const uint32_t li = local_b * kBucket + lane; // tile-local instance index of this lane
     const int32_t inst = tstart + (int32_t)li;
     const bool valid = inst < tend;
-    const ViewCam& cm = cams[cam];
-    const float Xo = (float)(tx * kTile + kTile / 2) - cm.cx;
-    const float Yo = (float)(ty * kTile + kTile / 2) - cm.cy;
+    const float Xo = (float)(tx * kTile + kTile / 2) - (EWA ? 0.f : cams[cam].cx);
+    const float Yo = (float)(ty * kTile + kTile / 2) - (EWA ? 0.f : cams[cam].cy);
 
     float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A, Cc = A, E = A;
     uint32_t g = 0;
     if (valid) {
         g = (uint32_t)__ldg(rb.inst_gid + inst);
-        if (FUSED) {
+        if (EWA) {
+            const float4* gp = reinterpret_cast<const float4*>(rb.gauss + g);
+            expand_record_ewa(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), Xo, Yo, A, B, Cc);
+            E = make_float4(B.z, B.w, Cc.x, Cc.y);
+        } else if (FUSED) {
             const float4* gp = reinterpret_cast<const float4*>(rb.gauss + g);
             expand_record(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), Xo, Yo, A, B, Cc);
             E = __ldg(gp + 3);
@@ -627,9 +691,15 @@ __global__ void __launch_bounds__(kBwdWarps * 32, kMinBlocks)
             continue;
         const float dx = ea.w, dy = eb.x;
         const float Nv = poly2(dx, dy, A.x, A.y, A.z, A.w, B.x, B.y);
-        const float Dv = poly2(dx, dy, B.z, B.w, Cc.x, Cc.y, Cc.z, Cc.w);
-        const float rD = rcp_approx(Dv);
-        const float p2 = Nv * rD;
+        float rD = 1.f, p2 = Nv;
+        if (EWA) {
+            if (Nv > 0.f) // sigma/2 < 0 is skipped (kernels_backward.cuh:391-392)
+                continue;
+        } else {
+            const float Dv = poly2(dx, dy, B.z, B.w, Cc.x, Cc.y, Cc.z, Cc.w);
+            rD = rcp_approx(Dv);
+            p2 = Nv * rD;
+        }
         const float vis = ex2_approx(p2);
         const float a_raw = E.x * vis;
         const float alpha = fminf(kAlphaMax, a_raw);
@@ -643,7 +713,18 @@ __global__ void __launch_bounds__(kBwdWarps * 32, kMinBlocks)
         u = fmaf(-w, Ev, u);                                           // now the sum over j > i
         const float om = 1.0f - alpha;                                 // >= 0.001: plain rcp is safe
         const float v_alpha = fmaf(T, Ev, -u * rcp_approx(om));
-        if (a_raw <= kAlphaMax) {
+        if (EWA) {
+            // the reference differentiates through the clamped alpha as if it were not clamped (:418-427)
+            aop = fmaf(alpha, v_alpha, aop);
+            const float vN = v_alpha * alpha * kLn2;
+            const float dxx = dx * dx, dxy = dx * dy, dyy = dy * dy;
+            an0 += vN;
+            an1 = fmaf(vN, dx, an1);
+            an2 = fmaf(vN, dy, an2);
+            an3 = fmaf(vN, dxx, an3);
+            an4 = fmaf(vN, dxy, an4);
+            an5 = fmaf(vN, dyy, an5);
+        } else if (a_raw <= kAlphaMax) {
             aop = fmaf(vis, v_alpha, aop);
             const float vN = v_alpha * a_raw * kLn2 * rD;
             const float vD = -vN * p2;
@@ -666,7 +747,30 @@ __global__ void __launch_bounds__(kBwdWarps * 32, kMinBlocks)
 
     if (!valid)
         return;
+    if (EWA) {
+        // ---- polynomial-coefficient gradients -> (conic, mean2d); e = mean2d - tile centre
+        const float4* gp = reinterpret_cast<const float4*>(rb.gauss + g);
+        const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1), g2 = __ldg(gp + 2);
+        const float ex = g0.x - Xo, ey = g0.y - Yo, a = g0.z, b = g0.w, c = g1.x;
+        const float v_a = kEScale * (0.5f * ex * ex * an0 - ex * an1 + 0.5f * an3);
+        const float v_b = kEScale * (ex * ey * an0 - ey * an1 - ex * an2 + an4);
+        const float v_c = kEScale * (0.5f * ey * ey * an0 - ey * an2 + 0.5f * an5);
+        const float v_ex = kEScale * ((a * ex + b * ey) * an0 - a * an1 - b * an2);
+        const float v_ey = kEScale * ((c * ey + b * ex) * an0 - b * an1 - c * an2);
+        atomicAdd(v_means + 2 * (size_t)g, v_ex);
+        atomicAdd(v_means + 2 * (size_t)g + 1, v_ey);
+        atomicAdd(v_quats + 3 * (size_t)g, v_a);
+        atomicAdd(v_quats + 3 * (size_t)g + 1, v_b);
+        atomicAdd(v_quats + 3 * (size_t)g + 2, v_c);
+        // colour: gradient passes where the unclamped colour is >= 0 (color_grad_factor, :304-309)
+        atomicAdd(v_colors + 3 * (size_t)g, g1.z >= 0.f ? acr : 0.f);
+        atomicAdd(v_colors + 3 * (size_t)g + 1, g1.w >= 0.f ? acg : 0.f);
+        atomicAdd(v_colors + 3 * (size_t)g + 2, g2.x >= 0.f ? acb : 0.f);
+        atomicAdd(v_opacities + g, aop * (1.0f - g1.y)); // d alpha / d raw opacity = alpha (1 - opacity), :441
+        return;
+    }
     // ---- per-instance chain rule: polynomial coefficients -> (vx, vy, w2, gro) -> (mean, quat, scale)
+    const ViewCam& cm = cams[cam];
     const uint32_t gid = g % N;
     const float4* gp = reinterpret_cast<const float4*>(rb.gauss + g);
     const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1), g2 = __ldg(gp + 2);
@@ -786,6 +890,18 @@ int launch_blend_bwd(const RasterBuffers& rb, const ViewCam* cams_dev, const flo
     }
 #undef LFS_BWD_LAUNCH
     LFS_LAUNCH_OK("k_blend_bwd");
+    return LFS_OK;
+}
+
+int launch_blend_bwd_ewa(const RasterBuffers& rb, const float4* v_pix, uint32_t N, uint32_t width, uint32_t height,
+                         uint32_t tile_w, uint32_t tile_h, uint32_t n_bucket_cap, const uint32_t* n_buckets_dev,
+                         float* v_mean2d, float* v_conic, float* v_color, float* v_raw_opacity, cudaStream_t stream) {
+    if (n_bucket_cap == 0)
+        return LFS_OK;
+    k_blend_bwd<true, 4, 1, true><<<div_up(n_bucket_cap, 4), 4 * 32, 0, stream>>>(
+        rb, nullptr, v_pix, nullptr, nullptr, nullptr, N, width, height, tile_w, tile_h, n_bucket_cap, n_buckets_dev,
+        v_mean2d, v_conic, nullptr, v_color, v_raw_opacity);
+    LFS_LAUNCH_OK("k_blend_bwd<ewa>");
     return LFS_OK;
 }
 

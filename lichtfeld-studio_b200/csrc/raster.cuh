@@ -92,4 +92,13 @@ int launch_blend_bwd(const RasterBuffers& rb, const ViewCam* cams_dev, const flo
                      float* v_means, float* v_quats, float* v_scales, float* v_colors, float* v_opacities,
                      cudaStream_t stream);
 
+// fastgs (EWA) surface: rb.gauss holds EWA records (see expand_record_ewa), one camera, outputs stay in rb.pix_state /
+// rb.n_contrib / rb.ckpt.  Backward accumulates grad_mean2d [N,2], grad_conic [N,3] (true d/db), grad_color [N,3]
+// (already masked by the clamp) and grad_raw_opacity [N].
+int launch_blend_fwd_ewa(const RasterBuffers& rb, uint32_t width, uint32_t height, uint32_t tile_w, uint32_t tile_h,
+                         bool write_ckpt, cudaStream_t stream);
+int launch_blend_bwd_ewa(const RasterBuffers& rb, const float4* v_pix, uint32_t N, uint32_t width, uint32_t height,
+                         uint32_t tile_w, uint32_t tile_h, uint32_t n_bucket_cap, const uint32_t* n_buckets_dev,
+                         float* v_mean2d, float* v_conic, float* v_color, float* v_raw_opacity, cudaStream_t stream);
+
 } // namespace lfs

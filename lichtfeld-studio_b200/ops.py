@@ -264,3 +264,74 @@ def add_noise(raw_opacities, raw_scales, raw_quats, noise, means, current_lr: fl
         _chk(t, nme)
     check(lib.lfs_add_noise(_p(raw_opacities), _p(raw_scales), _p(raw_quats), _p(noise), _p(means), current_lr,
                             raw_opacities.shape[0], _stream()))
+
+
+class FastGSContext:
+    """State the reference keeps between forward and backward: the four opaque byte buffers, the three counters and
+    the selector (fast_rasterizer_autograd.cpp:61-72)."""
+
+    def __init__(self, alloc, n_visible, n_instances, n_buckets, selector, dims):
+        self.alloc = alloc  # keeps the buffers alive
+        self.n_visible_primitives, self.n_instances, self.n_buckets = n_visible, n_instances, n_buckets
+        self.instance_selector = selector
+        self.dims = dims
+
+    def buffer(self, tag: int) -> int:
+        t, off, _ = self.alloc.bufs[tag]
+        return t.data_ptr() + off
+
+
+def fastgs_forward(means, scales_raw, rotations_raw, opacities_raw, sh_coefficients_0, sh_coefficients_rest, w2c,
+                   cam_position, active_sh_bases: int, width: int, height: int, focal_x: float, focal_y: float,
+                   center_x: float, center_y: float, near_plane: float, far_plane: float):
+    """fast_gs::rasterization::forward_wrapper (fastgs/rasterization/include/rasterization_api.h:26-44)
+    -> (image [3,H,W], alpha [1,H,W], FastGSContext)."""
+    lib = load()
+    for t, n in ((means, "means"), (scales_raw, "scales_raw"), (rotations_raw, "rotations_raw"),
+                 (opacities_raw, "opacities_raw"), (sh_coefficients_0, "sh_coefficients_0"),
+                 (sh_coefficients_rest, "sh_coefficients_rest")):
+        _chk(t, n)
+    w2c, cam_position = w2c.contiguous(), cam_position.contiguous()
+    _chk(w2c, "w2c"), _chk(cam_position, "cam_position")
+    dev = means.device
+    N, total_rest = means.shape[0], sh_coefficients_rest.shape[1]
+    image = torch.empty((3, height, width), dtype=torch.float32, device=dev)
+    alpha = torch.empty((1, height, width), dtype=torch.float32, device=dev)
+    al = _Alloc(dev)
+    cnt = [C.c_int(0) for _ in range(4)]
+    check(lib.lfs_fastgs_forward(_p(means), _p(scales_raw), _p(rotations_raw), _p(opacities_raw), _p(sh_coefficients_0),
+                                 _p(sh_coefficients_rest), _p(w2c), _p(cam_position), N, active_sh_bases, total_rest,
+                                 width, height, focal_x, focal_y, center_x, center_y, near_plane, far_plane, _p(image),
+                                 _p(alpha), al.cb, None, C.byref(cnt[0]), C.byref(cnt[1]), C.byref(cnt[2]),
+                                 C.byref(cnt[3]), _stream()))
+    ctx = FastGSContext(al, cnt[0].value, cnt[1].value, cnt[2].value, cnt[3].value,
+                        (N, total_rest, active_sh_bases, width, height, focal_x, focal_y, center_x, center_y))
+    return image, alpha, ctx
+
+
+def fastgs_backward(ctx: FastGSContext, grad_image, grad_alpha, means, scales_raw, rotations_raw, sh_coefficients_rest,
+                    w2c, cam_position, densification_info=None, want_w2c_grad: bool = False):
+    """fast_gs::rasterization::backward_wrapper (rasterization_api.h:46-75) -> (grad_means, grad_scales_raw,
+    grad_rotations_raw, grad_opacities_raw, grad_sh_coefficients_0, grad_sh_coefficients_rest, grad_w2c | None)."""
+    lib = load()
+    N, total_rest, active, width, height, fx, fy, cx, cy = ctx.dims
+    _chk(grad_image, "grad_image"), _chk(grad_alpha, "grad_alpha")
+    dev = means.device
+    g_means = torch.empty((N, 3), dtype=torch.float32, device=dev)
+    g_scales = torch.empty((N, 3), dtype=torch.float32, device=dev)
+    g_rot = torch.empty((N, 4), dtype=torch.float32, device=dev)
+    g_op = torch.empty((N, 1), dtype=torch.float32, device=dev)
+    g_sh0 = torch.empty((N, 1, 3), dtype=torch.float32, device=dev)
+    g_shN = torch.empty((N, total_rest, 3), dtype=torch.float32, device=dev)
+    g_w2c = torch.zeros((4, 4), dtype=torch.float32, device=dev) if want_w2c_grad else None
+    if densification_info is not None and densification_info.numel() == 0:
+        densification_info = None
+    al = _Alloc(dev)
+    check(lib.lfs_fastgs_backward(_p(grad_image), _p(grad_alpha), _p(means), _p(scales_raw), _p(rotations_raw),
+                                  _p(sh_coefficients_rest), _p(w2c.contiguous()), _p(cam_position.contiguous()),
+                                  ctx.buffer(_lib.LFS_TAG_FG_PER_PRIMITIVE), ctx.buffer(_lib.LFS_TAG_FG_PER_TILE),
+                                  ctx.buffer(_lib.LFS_TAG_FG_PER_INSTANCE), ctx.buffer(_lib.LFS_TAG_FG_PER_BUCKET),
+                                  _p(g_means), _p(g_scales), _p(g_rot), _p(g_op), _p(g_sh0), _p(g_shN), _p(g_w2c),
+                                  _p(densification_info), N, ctx.n_instances, ctx.n_buckets, ctx.instance_selector,
+                                  active, total_rest, width, height, fx, fy, cx, cy, al.cb, None, _stream()))
+    return g_means, g_scales, g_rot, g_op, g_sh0, g_shN, g_w2c

@@ -345,3 +345,68 @@ if __name__ == "__main__":
         path = sys.argv[sys.argv.index("--json") + 1]
         os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
         json.dump(rep, open(path, "w"), indent=1, default=str)
+
+
+def fastgs_case(n=3000, w=200, h=136, deg=3, seed=11, sigma_px=4.0):
+    """Seeded inputs of the fastgs surface (raw parameters) for one view: numpy dict."""
+    sc = scene.make_scene(n, 1, w, h, deg, seed=seed, sigma_px=sigma_px)
+    w2c, cam, fx, fy, cx, cy = O.fastgs_inputs(sc)
+    rng = np.random.RandomState(seed + 1)
+    return dict(means=sc.means, scales_raw=sc.scaling, rotations_raw=sc.rotation, opacities_raw=sc.opacity.reshape(-1, 1),
+                sh0=sc.sh0, shN=sc.shN, w2c=w2c.astype(np.float32), cam_pos=cam.astype(np.float32),
+                active_sh_bases=(deg + 1) ** 2, width=w, height=h, fx=fx, fy=fy, cx=cx, cy=cy,
+                grad_image=rng.normal(size=(3, h, w)).astype(np.float32),
+                grad_alpha=rng.normal(size=(1, h, w)).astype(np.float32))
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    if a.size == 0:
+        return 0.0
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))
+
+
+def diag_fastgs(n=3000, w=200, h=136, deg=3, seed=11, sigma_px=4.0, with_ref=True):
+    """lfs_fastgs_forward / backward vs the double-precision oracle (and vs the unmodified reference CUDA build)."""
+    from lichtfeld_studio_b200 import ops
+    c = fastgs_case(n, w, h, deg, seed, sigma_px)
+    out = {}
+    t = {k: T(c[k]) for k in ("means", "scales_raw", "rotations_raw", "opacities_raw", "sh0", "shN", "w2c", "cam_pos",
+                              "grad_image", "grad_alpha")}
+    img, alpha, ctx = ops.fastgs_forward(t["means"], t["scales_raw"], t["rotations_raw"], t["opacities_raw"], t["sh0"],
+                                         t["shN"], t["w2c"], t["cam_pos"], c["active_sh_bases"], w, h, c["fx"], c["fy"],
+                                         c["cx"], c["cy"], 0.01, 1e10)
+    dens = torch.zeros((2, n), device=DEV)
+    g = ops.fastgs_backward(ctx, t["grad_image"], t["grad_alpha"], t["means"], t["scales_raw"], t["rotations_raw"],
+                            t["shN"], t["w2c"], t["cam_pos"], densification_info=dens, want_w2c_grad=True)
+    torch.cuda.synchronize()
+    names = ("means", "scales_raw", "rotations_raw", "opacities_raw", "sh0", "shN")
+    orc = O.fastgs(c["means"], c["scales_raw"], c["rotations_raw"], c["opacities_raw"], c["sh0"], c["shN"], c["w2c"],
+                   c["cam_pos"], c["active_sh_bases"], w, h, c["fx"], c["fy"], c["cx"], c["cy"], 0.01, 1e10,
+                   grad_image=c["grad_image"], grad_alpha=c["grad_alpha"], want_w2c_grad=True,
+                   densification_info=np.zeros((2, n)), prec=64)
+    out["n_instances"], out["n_instances_oracle"] = ctx.n_instances, orc["n_instances"]
+    out["n_visible"], out["n_visible_oracle"] = ctx.n_visible_primitives, int((orc["n_touched"] > 0).sum())
+    out["n_buckets"] = ctx.n_buckets
+    out["image_rel"], out["alpha_rel"] = _rel(img.cpu().numpy(), orc["image"]), _rel(alpha.cpu().numpy(), orc["alpha"])
+    for k, gg in zip(names, g[:6]):
+        out[f"grad_{k}_rel"] = _rel(gg.cpu().numpy().reshape(orc["grads"][k].shape), orc["grads"][k])
+    out["grad_w2c_rel"] = _rel(g[6].cpu().numpy()[:3], orc["grad_w2c"][:3])
+    out["dens_count_equal"] = bool((dens[0].cpu().numpy() == orc["densification_info"][0]).all())
+    out["dens_norm_rel"] = _rel(dens[1].cpu().numpy(), orc["densification_info"][1])
+    if with_ref and R.have_fastgs():
+        fg = R.FastGS()
+        rimg, ralpha, counts = fg.forward(t["means"], t["scales_raw"], t["rotations_raw"], t["opacities_raw"], t["sh0"],
+                                          t["shN"], t["w2c"], t["cam_pos"], c["active_sh_bases"], w, h, c["fx"], c["fy"],
+                                          c["cx"], c["cy"])
+        rg = fg.backward(t["grad_image"], t["grad_alpha"], rimg, ralpha, t["means"], t["scales_raw"], t["rotations_raw"],
+                         t["shN"], t["w2c"], t["cam_pos"], c["active_sh_bases"], w, h, c["fx"], c["fy"], c["cx"], c["cy"])
+        torch.cuda.synchronize()
+        out["ref_counts"] = list(counts)
+        out["ref_image_rel"], out["ref_alpha_rel"] = _rel(img.cpu().numpy(), rimg.cpu().numpy()), _rel(
+            alpha.cpu().numpy(), ralpha.cpu().numpy())
+        out["ref_oracle_image_rel"] = _rel(rimg.cpu().numpy(), orc["image"])
+        for k, rk, gg in zip(names, ("means", "scales", "rot", "op", "sh0", "shN"), g[:6]):
+            out[f"ref_grad_{k}_rel"] = _rel(gg.cpu().numpy(), rg[rk].cpu().numpy().reshape(gg.shape))
+            out[f"ref_oracle_grad_{k}_rel"] = _rel(rg[rk].cpu().numpy().reshape(orc["grads"][k].shape), orc["grads"][k])
+    return out

@@ -99,6 +99,24 @@ def test_fused_trainer_step(tma, fused):
     assert r["loss_rel"] <= 1e-5 and r["adam_param_ulp_max"] <= 1.01 and r["grads_cleared"], r
 
 
+@pytest.mark.parametrize("case", [dict(), dict(n=1500, w=120, h=100, deg=1, seed=5, sigma_px=7.0),
+                                  dict(n=800, w=64, h=48, deg=0, seed=6, sigma_px=3.0)])
+def test_fastgs_forward_backward(case):
+    """fastgs (EWA) surface, SURVEY §8 a9/a10: image 1e-4, gradients 1e-3 (relative to the largest entry)."""
+    r = D.diag_fastgs(**case)
+    assert abs(r["n_instances"] - r["n_instances_oracle"]) <= 2 + r["n_instances_oracle"] // 2000, r
+    assert abs(r["n_visible"] - r["n_visible_oracle"]) <= 2, r
+    assert r["image_rel"] <= 1e-4 and r["alpha_rel"] <= 1e-4, r
+    for k in ("means", "scales_raw", "rotations_raw", "opacities_raw", "sh0", "shN"):
+        assert r[f"grad_{k}_rel"] <= 1e-3, (k, r)
+    assert r["grad_w2c_rel"] <= 1e-3 and r["dens_count_equal"] and r["dens_norm_rel"] <= 1e-3, r
+    if "ref_image_rel" in r:  # the unmodified reference CUDA build, same inputs
+        assert abs(r["n_instances"] - r["ref_counts"][1]) <= 2 + r["n_instances"] // 2000, r
+        assert r["ref_image_rel"] <= 1e-4 and r["ref_alpha_rel"] <= 1e-4, r
+        for k in ("means", "scales_raw", "rotations_raw", "opacities_raw", "sh0", "shN"):
+            assert r[f"ref_grad_{k}_rel"] <= 2e-3, (k, r)
+
+
 def test_unsupported_configurations_fail_loudly():
     import lichtfeld_studio_b200 as L
     from lichtfeld_studio_b200 import ops
