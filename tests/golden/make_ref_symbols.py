@@ -1,5 +1,5 @@
 """Lists the mangled names of the reference's public operator surface as DEFINED by the reference's own objects
-(oracle/_ref/obj/gs_*.o = /root/reference/gsplat/*.cpp compiled in place, fg_adam*.o) -> tests/golden/ref_symbols.txt.
+(oracle/_ref/obj/gs_*.o = /root/reference/gsplat/*.cpp compiled in place, fg_adam*.o, fg_rasterization_api.o from `make -C oracle fastgs_api_syms`) -> tests/golden/ref_symbols.txt.
 Run in the build container after `make -C oracle ref`."""
 import os
 import re
@@ -18,7 +18,9 @@ for f in sorted(os.listdir(OBJ)):
     for line in out.splitlines():
         parts = line.split()
         if len(parts) == 3 and parts[1] in "TW":
-            if want.match(parts[2]) or parts[2].startswith("_ZN7fast_gs9optimizer9adam_step"):
+            if want.match(parts[2]) or parts[2].startswith("_ZN7fast_gs9optimizer9adam_step") or \
+                    parts[2].startswith("_ZN7fast_gs13rasterization15forward_wrapper") or \
+                    parts[2].startswith("_ZN7fast_gs13rasterization16backward_wrapper"):
                 names.add(parts[2])
 path = os.path.join(ROOT, "tests", "golden", "ref_symbols.txt")
 open(path, "w").write("\n".join(sorted(names)) + "\n")

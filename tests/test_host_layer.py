@@ -1,4 +1,4 @@
-"""The C++/libtorch host layer (lichtfeld-studio_b200/host/gsplat_backend.cpp, fastgs_adam_backend.cpp) compiled
+"""The C++/libtorch host layer (lichtfeld-studio_b200/host/gsplat_backend.cpp, fastgs_adam_backend.cpp, fastgs_raster_backend.cpp) compiled
 against the REFERENCE's own headers must export exactly the mangled symbols that the reference's own objects define
 for its public operator surface (tests/golden/ref_symbols.txt, generated from the unmodified reference build by
 tests/golden/make_ref_symbols.py) -- that is what "src/training links against it unchanged" means at the ABI level."""
@@ -19,6 +19,8 @@ def test_reference_symbol_fixture_is_complete():
                "rasterize_to_pixels_from_world_3dgs_fwd", "rasterize_to_pixels_from_world_3dgs_bwd"):
         assert f"gsplat::{fn}(" in demangled
     assert "fast_gs::optimizer::adam_step(" in demangled
+    assert "fast_gs::rasterization::forward_wrapper(" in demangled
+    assert "fast_gs::rasterization::backward_wrapper(" in demangled
 
 
 def test_host_layer_exports_the_reference_symbols():
