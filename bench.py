@@ -5,7 +5,7 @@
   python bench.py --impl reference --gpus N --steps K --warmup W
 
 A "step" is one pass of the hot path over one batch of synthetic views: every view is rendered (projection +
-SH + tile sort + blend forward), its L1 photometric gradient is back-propagated (blend backward + per-Gaussian
+SH + tile sort + blend forward), its L1 + fused-SSIM photometric gradient (the reference's loss) is back-propagated (blend backward + per-Gaussian
 backward), gradients of the batch are summed (NCCL all-reduce across ranks) and ONE fused Adam step is taken.
 Workload = BASELINE.json configs[2] ("C3": 1M Gaussians, 8 views of 1920x1080 per GPU, SH degree 3); with N GPUs
 the global batch is 8 N views (weak scaling; the views of a step are sharded round-robin over the ranks).
@@ -32,6 +32,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "training views/sec (fwd+bwd+Adam) @1M Gaussians 1080p"
 UNIT = "views/s"
+LAMBDA_DSSIM = 0.2  # eval/default_optimization_params.json; loss = (1-l) L1 + l (1 - SSIM), src/training/trainer.cpp:122-125
 
 
 def parse():
@@ -373,7 +374,7 @@ def main():
         tr.loss_dev.zero_()
         for v in my_views:
             tr.forward(sc.viewmats[v], sc.Ks[v], deg, bg)
-            tr.loss_l1(targets_dev[v])
+            tr.loss_ssim_l1(targets_dev[v], LAMBDA_DSSIM)
             tr.backward()
         if world > 1:
             dist.all_reduce(tr.grads, op=dist.ReduceOp.SUM)
@@ -434,7 +435,7 @@ def main():
         "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{a.config}: {n} Gaussians, {vpg} views/GPU x {world} GPU of {W}x{H}, SH degree {deg}, "
-                               "3DGUT from-world rasterizer, L1 loss, eval/default_optimization_params.json lrs",
+                               "3DGUT from-world rasterizer, L1 + fused-SSIM loss (lambda_dssim 0.2), eval/default_optimization_params.json lrs",
                    "gaussians": n, "views_per_step": V, "width": W, "height": H, "sh_degree": deg,
                    "parallelism": f"view-sharded dp{world} + NCCL all-reduce of the flat gradient arena",
                    "instances_per_view": I, "l2": "per-step working set (params+grads+Adam state+records) >= 1 GB, "

@@ -270,9 +270,16 @@ int lfs_trainer_view_forward(void* trainer, const float* params_arena, const flo
                              const float* K_host, uint32_t active_sh_degree, const float* bg_host, float* image_out,
                              float* alpha_out, void* stream);
 /* L1 photometric loss of the last forward against `target` (device); loss_accum (device float, may be NULL)
- * += scale * sum|render - target|;  sets the upstream gradient for lfs_trainer_view_backward. */
+ * += scale * sum|clamp(render,0,1) - target|;  sets the upstream gradient for lfs_trainer_view_backward. */
 int lfs_trainer_view_loss_l1(void* trainer, const void* target, int target_format, float scale, float* loss_accum,
                              void* stream);
+/* L1 + fused-SSIM photometric loss of the last forward, the reference's training loss
+ * (Trainer::compute_photometric_loss, src/training/trainer.cpp:103-131: (1-lambda) * l1_loss + lambda * (1 - fused_ssim(
+ * rendered, gt, "valid")); include/kernels/fused_ssim.cuh:27-122; kernels src/training/kernels/ssim.cu:64-460).
+ * The render is clamped to [0,1] first (rasterizer.cpp:401).  loss_accum (device float, may be NULL) += weight * loss;
+ * sets the upstream gradient (scaled by weight) for lfs_trainer_view_backward. */
+int lfs_trainer_view_loss_ssim_l1(void* trainer, const void* target, int target_format, float lambda_dssim, float weight,
+                                  float* loss_accum, void* stream);
 /* alternative: caller-provided upstream gradients v_image [H,W,3], v_alpha [H,W] or NULL (device) */
 int lfs_trainer_view_set_grad(void* trainer, const float* v_image, const float* v_alpha, void* stream);
 /* backward of the last forward: grads_arena += d loss / d raw parameters */

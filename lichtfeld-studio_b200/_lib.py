@@ -125,6 +125,7 @@ SIGNATURES = {
     "lfs_trainer_unpack": (C.c_int, [_vp] * 9),
     "lfs_trainer_view_forward": (C.c_int, [_vp, _vp, C.POINTER(_f), C.POINTER(_f), _u32, C.POINTER(_f), _vp, _vp, _vp]),
     "lfs_trainer_view_loss_l1": (C.c_int, [_vp, _vp, C.c_int, _f, _vp, _vp]),
+    "lfs_trainer_view_loss_ssim_l1": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_float, _vp, _vp]),
     "lfs_trainer_view_set_grad": (C.c_int, [_vp, _vp, _vp, _vp]),
     "lfs_trainer_view_backward": (C.c_int, [_vp, _vp, _vp, _vp]),
     "lfs_trainer_set_profile": (C.c_int, [_vp, C.c_int]),

@@ -39,6 +39,10 @@ extern "C" int lfs_set_option(const char* name, int value) {
         lfs::raster_options().pre_bwd_split = value;
         return LFS_OK;
     }
+    if (name && std::string(name) == "exact_cull") {
+        lfs::raster_options().exact_cull = value;
+        return LFS_OK;
+    }
     if (name && std::string(name) == "blend_fused") {
         lfs::raster_options().fuse_expand = value ? 1 : 0;
         return LFS_OK;

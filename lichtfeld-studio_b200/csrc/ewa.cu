@@ -5,7 +5,7 @@
 // Same pipeline shape as the from-world path and the same blend kernels (raster.cu, EWA instantiation): the 2-D conic
 // response is a plain quadratic in the tile-local pixel offset, so a record is 6 coefficients + opacity + colour.
 //   preprocess (1 thread / primitive, exact tile count) -> depth radix sort of all primitives (invisible = 0xFFFFFFFF,
-//   ties by index: deterministic, unlike the reference's atomic compaction) -> scan -> warp-cooperative instance
+//   ties by index: deterministic, unlike the reference's atomic compaction) -> scan -> one-thread-per-primitive instance
 //   emission with the exact ellipse/tile test -> tile-bits radix sort -> offsets / buckets -> blend.
 #include "intersect.cuh"
 #include "raster.cuh"
@@ -17,7 +17,9 @@ constexpr float kFgDilation = 0.3f;          // rasterization_config.h:16
 constexpr float kFgMinAlphaRcp = 255.0f;     // :17
 
 // kernel_utils.cuh:108-143 (mean already shifted by -0.5, :152): does the primitive reach alpha >= 1/255 in the tile?
-__device__ __forceinline__ bool fg_will_contribute(const float mx, const float my, const float ca, const float cb,
+// __noinline__ on purpose: the count (k_fg_preprocess) and the emission (k_fg_emit) must take the same decision for the
+// same inputs, so both call ONE compiled body instead of two inlined copies the optimiser may contract differently.
+__device__ __noinline__ bool fg_will_contribute(const float mx, const float my, const float ca, const float cb,
                                                    const float cc, const uint32_t tile_x, const uint32_t tile_y,
                                                    const float power_threshold) {
     const float rminx = (float)(tile_x * kTile), rminy = (float)(tile_y * kTile);
@@ -191,60 +193,31 @@ __global__ void __launch_bounds__(128)
     atomicAdd(n_visible, 1u);
 }
 
-// Warp-cooperative emission with the exact tile test (kernels_forward.cuh:221-320): a warp owns 32 consecutive slots
-// of the depth order and walks every non-empty rectangle 32 tiles at a time, compacting the survivors with a ballot.
+// Instance emission with the exact tile test (kernels_forward.cuh:221-320): one thread per slot of the depth order
+// re-evaluates the test over its rectangle (same function, same inputs as the count in k_fg_preprocess) and writes its
+// run; see k_emit_instances for why this beats the warp-cooperative walk.
 __global__ void __launch_bounds__(256)
     k_fg_emit(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ off, const uint32_t n_gauss,
               const TileRect* __restrict__ rects, const int32_t* __restrict__ counts, const GaussRec* __restrict__ gauss,
               const uint32_t tile_w, const uint32_t n_cap, uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ vals) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t lt = (1u << lane) - 1u;
-    const uint32_t warps = (gridDim.x * 256) >> 5;
-    for (uint32_t base = ((blockIdx.x * 256 + threadIdx.x) >> 5) * 32u; base < n_gauss; base += warps * 32u) {
-        const uint32_t slot = base + lane;
-        uint32_t g = 0, o = 0, xy0 = 0, w = 0, area = 0;
-        float mx = 0.f, my = 0.f, ca = 0.f, cb = 0.f, cc = 0.f, pt = 0.f;
-        if (slot < n_gauss) {
-            g = __ldg(perm + slot);
-            if (counts[g] > 0) {
-                const TileRect r = rects[g];
-                w = (uint32_t)r.x1 - (uint32_t)r.x0;
-                area = w * ((uint32_t)r.y1 - (uint32_t)r.y0);
-                xy0 = (uint32_t)r.x0 | ((uint32_t)r.y0 << 16);
-                o = __ldg(off + slot);
-                const float4* gp = reinterpret_cast<const float4*>(gauss + g);
-                const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1), g2 = __ldg(gp + 2);
-                mx = g0.x - 0.5f, my = g0.y - 0.5f, ca = g0.z, cb = g0.w, cc = g1.x, pt = g2.y;
-            }
-        }
-        uint32_t todo = __ballot_sync(0xffffffffu, area > 0);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            uint32_t wo = __shfl_sync(0xffffffffu, o, src);
-            const uint32_t ba = __shfl_sync(0xffffffffu, area, src), bw = __shfl_sync(0xffffffffu, w, src);
-            const uint32_t bxy = __shfl_sync(0xffffffffu, xy0, src), bg = __shfl_sync(0xffffffffu, g, src);
-            const float bmx = __shfl_sync(0xffffffffu, mx, src), bmy = __shfl_sync(0xffffffffu, my, src);
-            const float bca = __shfl_sync(0xffffffffu, ca, src), bcb = __shfl_sync(0xffffffffu, cb, src);
-            const float bcc = __shfl_sync(0xffffffffu, cc, src), bpt = __shfl_sync(0xffffffffu, pt, src);
-            for (uint32_t k0 = 0; k0 < ba; k0 += 32u) {
-                const uint32_t k = k0 + lane;
-                bool wr = false;
-                uint32_t tx = 0, ty = 0;
-                if (k < ba) {
-                    const uint32_t q = k / bw;
-                    ty = (bxy >> 16) + q, tx = (bxy & 0xffffu) + (k - q * bw);
-                    wr = fg_will_contribute(bmx, bmy, bca, bcb, bcc, tx, ty, bpt);
-                }
-                const uint32_t m = __ballot_sync(0xffffffffu, wr);
-                const uint32_t pos = wo + __popc(m & lt);
-                if (wr && pos < n_cap) {
+    for (uint32_t slot = blockIdx.x * 256 + threadIdx.x; slot < n_gauss; slot += gridDim.x * 256) {
+        const uint32_t g = __ldg(perm + slot);
+        const int32_t cnt = counts[g];
+        if (cnt <= 0)
+            continue;
+        const TileRect r = rects[g];
+        const float4* gp = reinterpret_cast<const float4*>(gauss + g);
+        const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1), g2 = __ldg(gp + 2);
+        const float mx = g0.x - 0.5f, my = g0.y - 0.5f, ca = g0.z, cb = g0.w, cc = g1.x, pt = g2.y;
+        uint32_t pos = __ldg(off + slot);
+        const uint32_t end = pos + (uint32_t)cnt; // never write past this Gaussian's share
+        for (uint32_t ty = r.y0; ty < r.y1; ++ty)
+            for (uint32_t tx = r.x0; tx < r.x1; ++tx)
+                if (fg_will_contribute(mx, my, ca, cb, cc, tx, ty, pt) && pos < end && pos < n_cap) {
                     tile_keys[pos] = ty * tile_w + tx;
-                    vals[pos] = bg;
+                    vals[pos] = g;
+                    ++pos;
                 }
-                wo += __popc(m);
-            }
-        }
     }
 }
 

@@ -61,10 +61,10 @@ __device__ __forceinline__ uint32_t upper_slot(const uint32_t* __restrict__ off,
     return lo;
 }
 
-// Warp-cooperative emission: a warp owns 32 consecutive slots of the depth order; for every slot with a non-empty
-// tile rectangle the whole warp writes that Gaussian's run of instances (coalesced: the run is contiguous at
-// off[slot]).  Replaces the instance-parallel version whose 20-step binary search over `off` per instance was
-// latency bound (ncu r01c: 0.150 ms, 28 long-scoreboard stall cycles per issue).
+// Emission: one thread per slot of the depth order writes that Gaussian's run of instances (contiguous at off[slot],
+// ~9 entries = two 32-B sectors per output array: the scattered stores merge in L2).  History: the instance-parallel
+// version (20-step binary search over `off` per instance) took 0.150 ms per 1080p view, a warp-cooperative version that
+// serialised 32 Gaussians per warp 0.085 ms (ncu r01c / r01f).
 __global__ void __launch_bounds__(kIsThreads)
     k_emit_instances(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ off, const uint32_t n_gauss,
                      const TileRect* __restrict__ rects, const uint32_t tile_w, const uint32_t id_offset,
@@ -75,35 +75,18 @@ __global__ void __launch_bounds__(kIsThreads)
         const uint32_t nd = *n_dev;
         n = nd < n_cap ? nd : n_cap;
     }
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t warps = (gridDim.x * kIsThreads) >> 5;
-    for (uint32_t base = ((blockIdx.x * kIsThreads + threadIdx.x) >> 5) * 32u; base < n_gauss; base += warps * 32u) {
-        const uint32_t slot = base + lane;
-        uint32_t g = 0, o = 0, xy0 = 0, w = 0, c = 0;
-        if (slot < n_gauss) {
-            g = perm ? __ldg(perm + slot) : slot;
-            const TileRect r = rects[g];
-            w = (uint32_t)r.x1 - (uint32_t)r.x0;
-            c = w * ((uint32_t)r.y1 - (uint32_t)r.y0);
-            xy0 = (uint32_t)r.x0 | ((uint32_t)r.y0 << 16);
-            o = __ldg(off + slot);
-        }
-        uint32_t todo = __ballot_sync(0xffffffffu, c > 0);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const uint32_t bo = __shfl_sync(0xffffffffu, o, src), bc = __shfl_sync(0xffffffffu, c, src);
-            const uint32_t bw = __shfl_sync(0xffffffffu, w, src), bxy = __shfl_sync(0xffffffffu, xy0, src);
-            const uint32_t bg = __shfl_sync(0xffffffffu, g, src) + id_offset;
-            for (uint32_t k = lane; k < bc; k += 32u) {
-                const uint32_t j = bo + k;
-                if (j < n) {
-                    const uint32_t q = k / bw;
-                    tile_keys[j] = ((bxy >> 16) + q) * tile_w + (bxy & 0xffffu) + (k - q * bw);
-                    vals[j] = bg;
+    for (uint32_t slot = blockIdx.x * kIsThreads + threadIdx.x; slot < n_gauss; slot += gridDim.x * kIsThreads) {
+        const uint32_t g = perm ? __ldg(perm + slot) : slot;
+        const TileRect r = rects[g];
+        if (r.x1 <= r.x0 || r.y1 <= r.y0)
+            continue;
+        uint32_t pos = __ldg(off + slot);
+        for (uint32_t ty = r.y0; ty < r.y1; ++ty)
+            for (uint32_t tx = r.x0; tx < r.x1; ++tx, ++pos)
+                if (pos < n) {
+                    tile_keys[pos] = ty * tile_w + tx;
+                    vals[pos] = g + id_offset;
                 }
-            }
-        }
     }
 }
 
@@ -117,6 +100,55 @@ int launch_emit_instances(const uint32_t* perm, const uint32_t* off, uint32_t n_
     k_emit_instances<<<grid, kIsThreads, 0, stream>>>(perm, off, n_gauss, rects, tile_w, id_offset, n_cap, n_dev,
                                                       tile_keys, vals);
     LFS_LAUNCH_OK("k_emit_instances");
+    return LFS_OK;
+}
+
+// emission with the exact tile test (see CullRec): ONE THREAD per slot of the depth order walks the rows of its
+// rectangle, computes each row span once (the very predicate the count used) and writes its run.  A Gaussian's run is
+// ~7 instances, i.e. one 32-B sector per output array, so the scattered 4-B stores merge in L2; the warp-cooperative
+// variants tried first (32 Gaussians serialised per warp, span per tile) cost 0.2 ms per 1080p view, this one ~0.05.
+__global__ void __launch_bounds__(kIsThreads)
+    k_emit_instances_cull(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ off, const uint32_t n_gauss,
+                          const TileRect* __restrict__ rects, const int32_t* __restrict__ counts,
+                          const CullRec* __restrict__ cull, const uint32_t tile_w, const uint32_t n_cap,
+                          const uint32_t* __restrict__ n_dev, uint32_t* __restrict__ tile_keys,
+                          uint32_t* __restrict__ vals) {
+    uint32_t n = n_cap;
+    if (n_dev) {
+        const uint32_t nd = *n_dev;
+        n = nd < n_cap ? nd : n_cap;
+    }
+    for (uint32_t slot = blockIdx.x * kIsThreads + threadIdx.x; slot < n_gauss; slot += gridDim.x * kIsThreads) {
+        const uint32_t g = perm ? __ldg(perm + slot) : slot;
+        if (counts[g] <= 0)
+            continue;
+        const TileRect r = rects[g];
+        const float4* cp = reinterpret_cast<const float4*>(cull + g);
+        const float4 c0 = __ldg(cp), c1 = __ldg(cp + 1);
+        const CullRec cr{c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        uint32_t pos = __ldg(off + slot);
+        for (uint32_t ty = r.y0; ty < r.y1; ++ty) {
+            int first, last;
+            cull_row_span(cr, ty, r.x0, r.x1, first, last);
+            for (int tx = first; tx <= last; ++tx, ++pos)
+                if (pos < n) {
+                    tile_keys[pos] = ty * tile_w + (uint32_t)tx;
+                    vals[pos] = g;
+                }
+        }
+    }
+}
+
+int launch_emit_instances_cull(const uint32_t* perm, const uint32_t* off, uint32_t n_gauss, const TileRect* rects,
+                               const int32_t* counts, const CullRec* cull, uint32_t tile_w, uint32_t n_cap,
+                               const uint32_t* n_dev, uint32_t* tile_keys, uint32_t* vals, cudaStream_t stream) {
+    if (n_cap == 0 || n_gauss == 0)
+        return LFS_OK;
+    const unsigned want = div_up(n_gauss, kIsThreads);
+    const unsigned grid = want < (unsigned)(kNumSMs * 16) ? want : (unsigned)(kNumSMs * 16);
+    k_emit_instances_cull<<<grid, kIsThreads, 0, stream>>>(perm, off, n_gauss, rects, counts, cull, tile_w, n_cap, n_dev,
+                                                           tile_keys, vals);
+    LFS_LAUNCH_OK("k_emit_instances_cull");
     return LFS_OK;
 }
 

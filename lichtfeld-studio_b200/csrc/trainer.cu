@@ -42,6 +42,7 @@ struct Trainer {
     ViewCam* cam_dev;
     GaussRec* gauss;
     TileRect* rects;
+    CullRec* cull;
     int32_t* counts;
     uint32_t *dk_a, *dk_b, *pm_a, *pm_b, *off;
     uint32_t* n_inst; // [4] device counters: n_inst, n_buckets, overflow flag
@@ -56,6 +57,7 @@ struct Trainer {
     float *v_means, *v_quats, *v_scales, *v_colors, *v_opac;
     float *act_means, *act_quats, *act_scales; // activated AoS copies for the blend-backward epilogue
     float* loss_partials;
+    float* ssim_maps; // [3 channels][3 maps][H*W]: dL/dmap * (dm/dmu1, dm/dsigma1^2, dm/dsigma12)
     void *scan_scr, *sort_scr;
     const uint32_t* sorted_keys = nullptr;
     const uint32_t* sorted_vals = nullptr;
@@ -83,6 +85,7 @@ static size_t trainer_carve(Trainer& t, void* base) {
     t.cam_dev = c.take<ViewCam>(1);
     t.gauss = c.take<GaussRec>(N);
     t.rects = c.take<TileRect>(N);
+    t.cull = c.take<CullRec>(N);
     t.counts = c.take<int32_t>(N);
     t.dk_a = c.take<uint32_t>(N), t.dk_b = c.take<uint32_t>(N);
     t.pm_a = c.take<uint32_t>(N), t.pm_b = c.take<uint32_t>(N);
@@ -108,7 +111,8 @@ static size_t trainer_carve(Trainer& t, void* base) {
     t.act_means = c.take<float>(3 * (size_t)N);
     t.act_quats = c.take<float>(4 * (size_t)N);
     t.act_scales = c.take<float>(3 * (size_t)N);
-    t.loss_partials = c.take<float>(t.n_tiles + 1);
+    t.loss_partials = c.take<float>(2 * (size_t)t.n_tiles + 2);
+    t.ssim_maps = c.take<float>(9 * (size_t)npix);
     t.scan_scr = c.take<char>(scan_scratch_bytes(N > t.n_tiles + 1 ? N : t.n_tiles + 1));
     t.sort_scr = c.take<char>(radix_scratch_bytes(N > t.inst_cap ? N : t.inst_cap));
     return c.total();
@@ -164,7 +168,7 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __ex
 __global__ void __launch_bounds__(256)
     k_preprocess_fwd(const float* __restrict__ arena, const Planes pl, const uint32_t N, const ViewCam cam,
                      const PreCfg cfg, GaussRec* __restrict__ gauss, TileRect* __restrict__ rects,
-                     int32_t* __restrict__ counts, uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ ident,
+                     CullRec* __restrict__ cull /* null: keep every tile of the AABB */, int32_t* __restrict__ counts, uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ ident,
                      float* __restrict__ act_means, float* __restrict__ act_quats, float* __restrict__ act_scales) {
     const uint32_t g = blockIdx.x * 256 + threadIdx.x;
     if (g >= N)
@@ -201,19 +205,9 @@ __global__ void __launch_bounds__(256)
     }
     uint32_t x0, y0, x1, y1;
     tile_rect(o.mx, o.my, o.rx, o.ry, (float)kTile, (uint32_t)cam.tile_w, (uint32_t)cam.tile_h, x0, y0, x1, y1);
-    const int32_t cnt = (int32_t)((y1 - y0) * (x1 - x0));
-    counts[g] = cnt;
-    rects[g] = TileRect{(unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1};
-    depth_keys[g] = cnt > 0 ? __float_as_uint(o.depth) : 0xFFFFFFFFu;
-    if (cnt <= 0)
-        return;
+    int32_t cnt = (int32_t)((y1 - y0) * (x1 - x0));
 
-    // view-dependent colour: clamp_min(SH(dir) + 0.5, 0)   (rasterizer.cpp:250-266)
-    const f3 dir = mk3(mean.x - cam.org[0], mean.y - cam.org[1], mean.z - cam.org[2]);
-    f3 col = sh_to_color(cfg.degree, dir, [&](int k) { return mk3(P(pl.sh(k, 0)), P(pl.sh(k, 1)), P(pl.sh(k, 2))); });
-    col = mk3(fmaxf(col.x + 0.5f, 0.f), fmaxf(col.y + 0.5f, 0.f), fmaxf(col.z + 0.5f, 0.f));
-
-    // GaussRec (same algebra as k_prep_gaussians)
+    // GaussRec geometry (same algebra as k_prep_gaussians)
     float w = qw, x = qx, y = qy, z = qz;
     const float inv_norm = rsqrtf(x * x + y * y + z * z + w * w);
     x *= inv_norm, y *= inv_norm, z *= inv_norm, w *= inv_norm;
@@ -230,6 +224,42 @@ __global__ void __launch_bounds__(256)
     const f3 vy = mk3(dot(m0, r1), dot(m1, r1), dot(m2, r1)) * ify;
     const f3 w2 = mk3(dot(m0, r2), dot(m1, r2), dot(m2, r2));
     const f3 gro = mk3(dot(m0, omu), dot(m1, omu), dot(m2, omu));
+
+    if (cull && cnt > 0) {
+        // Q = N - tau D in (X, Y) = pixel - principal point:  Q_ij = g2 <V_i,V_j> - <gro,V_i><gro,V_j>,  V = (vx, vy, w2)
+        const float tau = 2.0f * __logf(255.0f * op) * 1.001f + 0.01f; // margin: never culls a contributing pixel
+        const float g2 = dot(gro, gro) - tau;
+        const float gx_ = dot(gro, vx), gy_ = dot(gro, vy), gw_ = dot(gro, w2);
+        const float qa = g2 * dot(vx, vx) - gx_ * gx_, qb = g2 * dot(vx, vy) - gx_ * gy_, qc = g2 * dot(vy, vy) - gy_ * gy_;
+        const float qd = g2 * dot(vx, w2) - gx_ * gw_, qe = g2 * dot(vy, w2) - gy_ * gw_, qf = g2 * dot(w2, w2) - gw_ * gw_;
+        const float det = qa * qc - qb * qb;
+        CullRec cr{1.f, 0.f, 1.f, 0.f, 0.f, __int_as_float(0x7f800000), 1.f, 1.f}; // lim = +inf: keep everything
+        if (qa > 0.f && qc > 0.f && det > 1e-12f * qa * qc) {
+            const float Xc = (qb * qe - qc * qd) / det, Yc = (qb * qd - qa * qe) / det; // minimiser of Q
+            const float qmin = qf + qd * Xc + qe * Yc;
+            if (qmin < 0.f && -qmin < 3.0e38f)
+                cr = CullRec{qa, qb, qc, Xc + cam.cx, Yc + cam.cy, -qmin, 1.0f / det, 1.0f / qa};
+        }
+        cull[g] = cr;
+        int32_t hit = 0;
+        for (uint32_t ty = y0; ty < y1; ++ty) {
+            int first, last;
+            cull_row_span(cr, ty, x0, x1, first, last);
+            hit += last >= first ? last - first + 1 : 0;
+        }
+        cnt = hit;
+    }
+    counts[g] = cnt;
+    rects[g] = TileRect{(unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1};
+    depth_keys[g] = cnt > 0 ? __float_as_uint(o.depth) : 0xFFFFFFFFu;
+    if (cnt <= 0)
+        return;
+
+    // view-dependent colour: clamp_min(SH(dir) + 0.5, 0)   (rasterizer.cpp:250-266)
+    const f3 dir = mk3(mean.x - cam.org[0], mean.y - cam.org[1], mean.z - cam.org[2]);
+    f3 col = sh_to_color(cfg.degree, dir, [&](int k) { return mk3(P(pl.sh(k, 0)), P(pl.sh(k, 1)), P(pl.sh(k, 2))); });
+    col = mk3(fmaxf(col.x + 0.5f, 0.f), fmaxf(col.y + 0.5f, 0.f), fmaxf(col.z + 0.5f, 0.f));
+
     float4* og = reinterpret_cast<float4*>(gauss + g);
     og[0] = make_float4(vx.x, vx.y, vx.z, vy.x);
     og[1] = make_float4(vy.y, vy.z, w2.x, w2.y);
@@ -494,11 +524,14 @@ __global__ void __launch_bounds__(256)
             const float* t = static_cast<const float*>(target);
             tr = t[i], tg = t[npix + i], tb = t[2 * (size_t)npix + i];
         }
-        const float dr = fmaf(s.w, bg_r, s.x) - tr, dg = fmaf(s.w, bg_g, s.y) - tg, db = fmaf(s.w, bg_b, s.z) - tb;
+        // the reference clamps the render to [0,1] before the loss (rasterizer.cpp:401); clamp backward passes inside
+        const float rr = fmaf(s.w, bg_r, s.x), rg = fmaf(s.w, bg_g, s.y), rb = fmaf(s.w, bg_b, s.z);
+        const float dr = fminf(fmaxf(rr, 0.f), 1.f) - tr, dg = fminf(fmaxf(rg, 0.f), 1.f) - tg,
+                    db = fminf(fmaxf(rb, 0.f), 1.f) - tb;
         acc += fabsf(dr) + fabsf(dg) + fabsf(db);
-        const float vr = (dr > 0.f ? scale : (dr < 0.f ? -scale : 0.f));
-        const float vg = (dg > 0.f ? scale : (dg < 0.f ? -scale : 0.f));
-        const float vb = (db > 0.f ? scale : (db < 0.f ? -scale : 0.f));
+        const float vr = (rr >= 0.f && rr <= 1.f) ? (dr > 0.f ? scale : (dr < 0.f ? -scale : 0.f)) : 0.f;
+        const float vg = (rg >= 0.f && rg <= 1.f) ? (dg > 0.f ? scale : (dg < 0.f ? -scale : 0.f)) : 0.f;
+        const float vb = (rb >= 0.f && rb <= 1.f) ? (db > 0.f ? scale : (db < 0.f ? -scale : 0.f)) : 0.f;
         v_pix[i] = make_float4(vr, vg, vb, -s.w * (bg_r * vr + bg_g * vg + bg_b * vb));
     }
 #pragma unroll
@@ -531,6 +564,213 @@ __global__ void __launch_bounds__(256)
         for (int w = 0; w < 8; ++w)
             a += s_sum[w];
         *loss_accum += a;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// L1 + fused SSIM ("valid" crop) photometric loss, the reference's training loss
+// (Trainer::compute_photometric_loss, src/training/trainer.cpp:103-131; fused_ssim, include/kernels/fused_ssim.cuh:27-122;
+// kernels src/training/kernels/ssim.cu:64-460).  Same 11-tap separable Gaussian, zero padding and per-pixel formulas;
+// re-organised for the fused step: the rendered image is read from the blend state (rgb + T*bg, clamped to [0,1] like
+// rasterizer.cpp:401) and the result is written straight into the packed upstream-gradient record of the blend
+// backward, so the [3,H,W] image, the SSIM map and dL/dimage never exist as tensors.
+// ------------------------------------------------------------------------------------------------------
+__constant__ float c_ssim_g[11] = {0.001028380123898387f, 0.0075987582094967365f, 0.036000773310661316f,
+                                   0.10936068743467331f,  0.21300552785396576f,   0.26601171493530273f,
+                                   0.21300552785396576f,  0.10936068743467331f,   0.036000773310661316f,
+                                   0.0075987582094967365f, 0.001028380123898387f};
+constexpr int kSsimHalo = 5, kSsimS = kTile + 2 * kSsimHalo; // 26
+
+__device__ __forceinline__ float target_at(const void* __restrict__ target, const int fmt, const uint32_t npix,
+                                           const uint32_t i, const int c) {
+    if (fmt == LFS_IMG_U8_HWC)
+        return static_cast<const uint8_t*>(target)[3 * (size_t)i + c] * (1.0f / 255.0f);
+    if (fmt == LFS_IMG_F32_HWC)
+        return static_cast<const float*>(target)[3 * (size_t)i + c];
+    return static_cast<const float*>(target)[(size_t)c * npix + i];
+}
+__device__ __forceinline__ float chan(const float4 s, const int c) { return c == 0 ? s.x : (c == 1 ? s.y : s.z); }
+
+__global__ void __launch_bounds__(256)
+    k_ssim_fwd(const float4* __restrict__ pix_state, const void* __restrict__ target, const int fmt, const int W,
+               const int H, const float bg_r, const float bg_g, const float bg_b, const float dmap /* -w*lambda/count */,
+               float* __restrict__ maps, float* __restrict__ partials) {
+    // one global-load phase for all three channels (the per-channel load -> sync -> conv chain of the first version was
+    // latency bound: 0.28 ms per 1080p view), then the separable convolutions run out of shared memory
+    __shared__ float sX[3][kSsimS][kSsimS], sY[3][kSsimS][kSsimS];
+    __shared__ float xc[kSsimS][kTile][5];
+    __shared__ float s_red[2][8];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
+    const int px = x0 + tx, py = y0 + ty;
+    const uint32_t npix = (uint32_t)W * (uint32_t)H;
+    const bool crop_all = !(H > 10 && W > 10); // fused_ssim.cuh:63-70
+    for (int t = threadIdx.x; t < kSsimS * kSsimS; t += 256) {
+        const int ly = t / kSsimS, lx = t - ly * kSsimS;
+        const int gy = y0 + ly - kSsimHalo, gx = x0 + lx - kSsimHalo;
+        float X0 = 0.f, X1 = 0.f, X2 = 0.f, Y0 = 0.f, Y1 = 0.f, Y2 = 0.f;
+        if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
+            const uint32_t i = (uint32_t)gy * W + gx;
+            const float4 s = pix_state[i];
+            X0 = fminf(fmaxf(fmaf(s.w, bg_r, s.x), 0.f), 1.f);
+            X1 = fminf(fmaxf(fmaf(s.w, bg_g, s.y), 0.f), 1.f);
+            X2 = fminf(fmaxf(fmaf(s.w, bg_b, s.z), 0.f), 1.f);
+            Y0 = target_at(target, fmt, npix, i, 0), Y1 = target_at(target, fmt, npix, i, 1);
+            Y2 = target_at(target, fmt, npix, i, 2);
+        }
+        sX[0][ly][lx] = X0, sX[1][ly][lx] = X1, sX[2][ly][lx] = X2;
+        sY[0][ly][lx] = Y0, sY[1][ly][lx] = Y1, sY[2][ly][lx] = Y2;
+    }
+    __syncthreads();
+    float l1 = 0.f, ss = 0.f;
+    for (int c = 0; c < 3; ++c) {
+        for (int t = threadIdx.x; t < kSsimS * kTile; t += 256) { // horizontal 11x1, ssim.cu:118-210
+            const int ly = t >> 4, lx = (t & 15) + kSsimHalo;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+#pragma unroll
+            for (int d = -kSsimHalo; d <= kSsimHalo; ++d) {
+                const float w = c_ssim_g[d + kSsimHalo], X = sX[c][ly][lx + d], Y = sY[c][ly][lx + d];
+                a0 = fmaf(w, X, a0), a1 = fmaf(w, X * X, a1), a2 = fmaf(w, Y, a2), a3 = fmaf(w, Y * Y, a3);
+                a4 = fmaf(w, X * Y, a4);
+            }
+            float* o = xc[ly][t & 15];
+            o[0] = a0, o[1] = a1, o[2] = a2, o[3] = a3, o[4] = a4;
+        }
+        __syncthreads();
+        {
+            float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f, o4 = 0.f; // vertical 1x11, :216-247
+#pragma unroll
+            for (int d = 0; d < 2 * kSsimHalo + 1; ++d) {
+                const float w = c_ssim_g[d];
+                const float* r = xc[ty + d][tx];
+                o0 = fmaf(w, r[0], o0), o1 = fmaf(w, r[1], o1), o2 = fmaf(w, r[2], o2), o3 = fmaf(w, r[3], o3);
+                o4 = fmaf(w, r[4], o4);
+            }
+            if (px < W && py < H) {
+                const float mu1 = o0, mu2 = o2, s1 = o1 - mu1 * mu1, s2 = o3 - mu2 * mu2, s12 = o4 - mu1 * mu2;
+                const float C1 = 0.0001f, C2 = 0.0009f;
+                const float A = mu1 * mu1 + mu2 * mu2 + C1, B = s1 + s2 + C2, Cc = 2.f * mu1 * mu2 + C1, D = 2.f * s12 + C2;
+                const float iAB = 1.0f / (A * B);
+                const float val = Cc * D * iAB; // :262
+                const bool in_crop = crop_all || (px >= 5 && px < W - 5 && py >= 5 && py < H - 5);
+                const float dm = in_crop ? dmap : 0.f;
+                const float d_mu1 = (mu2 * 2.f * D) * iAB - (mu2 * 2.f * Cc) * iAB - (mu1 * 2.f * Cc * D) * iAB / A +
+                                    (mu1 * 2.f * Cc * D) * iAB / B; // :269
+                const uint32_t i = (uint32_t)py * W + px;
+                float* m = maps + (size_t)c * 3 * npix;
+                m[i] = dm * d_mu1;
+                m[npix + i] = dm * (-Cc * D) * iAB / B;          // dm/dsigma1^2, :270
+                m[2 * (size_t)npix + i] = dm * (2.f * Cc) * iAB; // dm/dsigma12,  :271
+                if (in_crop)
+                    ss += val;
+                l1 += fabsf(sX[c][ty + kSsimHalo][tx + kSsimHalo] - sY[c][ty + kSsimHalo][tx + kSsimHalo]);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if ((threadIdx.x & 31) == 0)
+        s_red[0][threadIdx.x >> 5] = l1, s_red[1][threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f;
+        for (int w = 0; w < 8; ++w)
+            a += s_red[0][w], b += s_red[1][w];
+        const uint32_t blk = blockIdx.y * gridDim.x + blockIdx.x;
+        partials[2 * blk] = a, partials[2 * blk + 1] = b;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    k_ssim_bwd(const float4* __restrict__ pix_state, const void* __restrict__ target, const int fmt, const int W,
+               const int H, const float bg_r, const float bg_g, const float bg_b, const float l1w /* w*(1-lambda)/(3HW) */,
+               const float* __restrict__ maps, float4* __restrict__ v_pix) {
+    __shared__ float sD[9][kSsimS][kSsimS]; // [channel * 3 + map], all loaded in one phase
+    __shared__ float xc[kSsimS][kTile][3];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
+    const int px = x0 + tx, py = y0 + ty;
+    const uint32_t npix = (uint32_t)W * (uint32_t)H;
+    const bool inside = px < W && py < H;
+    const uint32_t pi = inside ? (uint32_t)py * W + px : 0u;
+    const float4 st = inside ? pix_state[pi] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float Yt[3] = {0.f, 0.f, 0.f};
+    if (inside) {
+        Yt[0] = target_at(target, fmt, npix, pi, 0), Yt[1] = target_at(target, fmt, npix, pi, 1);
+        Yt[2] = target_at(target, fmt, npix, pi, 2);
+    }
+    for (int t = threadIdx.x; t < kSsimS * kSsimS; t += 256) {
+        const int ly = t / kSsimS, lx = t - ly * kSsimS;
+        const int gy = y0 + ly - kSsimHalo, gx = x0 + lx - kSsimHalo;
+        const bool in = gx >= 0 && gx < W && gy >= 0 && gy < H;
+        const uint32_t i = in ? (uint32_t)gy * W + gx : 0u;
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+            sD[k][ly][lx] = in ? maps[(size_t)k * npix + i] : 0.f;
+    }
+    __syncthreads();
+    float g[3] = {0.f, 0.f, 0.f};
+    for (int c = 0; c < 3; ++c) {
+        for (int t = threadIdx.x; t < kSsimS * kTile; t += 256) {
+            const int ly = t >> 4, lx = (t & 15) + kSsimHalo;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+            for (int d = -kSsimHalo; d <= kSsimHalo; ++d) {
+                const float w = c_ssim_g[d + kSsimHalo];
+                a0 = fmaf(w, sD[3 * c][ly][lx + d], a0), a1 = fmaf(w, sD[3 * c + 1][ly][lx + d], a1);
+                a2 = fmaf(w, sD[3 * c + 2][ly][lx + d], a2);
+            }
+            float* o = xc[ly][t & 15];
+            o[0] = a0, o[1] = a1, o[2] = a2;
+        }
+        __syncthreads();
+        if (inside) {
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int d = 0; d < 2 * kSsimHalo + 1; ++d) {
+                const float w = c_ssim_g[d];
+                const float* r = xc[ty + d][tx];
+                s0 = fmaf(w, r[0], s0), s1 = fmaf(w, r[1], s1), s2 = fmaf(w, r[2], s2);
+            }
+            const float bgc = c == 0 ? bg_r : (c == 1 ? bg_g : bg_b);
+            const float raw = fmaf(st.w, bgc, chan(st, c));
+            const float X = fminf(fmaxf(raw, 0.f), 1.f), Y = Yt[c];
+            const float diff = X - Y;
+            float gc = s0 + 2.f * X * s1 + Y * s2 + (diff > 0.f ? l1w : (diff < 0.f ? -l1w : 0.f)); // ssim.cu:417 + L1
+            if (!(raw >= 0.f && raw <= 1.f)) // torch::clamp backward (rasterizer.cpp:401)
+                gc = 0.f;
+            g[c] = gc;
+        }
+        __syncthreads();
+    }
+    if (inside)
+        v_pix[pi] = make_float4(g[0], g[1], g[2], -st.w * (bg_r * g[0] + bg_g * g[1] + bg_b * g[2]));
+}
+
+__global__ void __launch_bounds__(256)
+    k_ssim_finish(const float* __restrict__ partials, const int n, const float w_l1, const float w_ssim,
+                  const float ssim_const, float* __restrict__ loss_accum) {
+    __shared__ float s_red[2][8];
+    float a = 0.f, b = 0.f;
+    for (int i = threadIdx.x; i < n; i += 256) // fixed order -> deterministic loss value
+        a += partials[2 * i], b += partials[2 * i + 1];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if ((threadIdx.x & 31) == 0)
+        s_red[0][threadIdx.x >> 5] = a, s_red[1][threadIdx.x >> 5] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float x = 0.f, y = 0.f;
+        for (int w = 0; w < 8; ++w)
+            x += s_red[0][w], y += s_red[1][w];
+        *loss_accum += w_l1 * x + ssim_const - w_ssim * y;
     }
 }
 
@@ -670,8 +910,9 @@ extern "C" int lfs_trainer_view_forward(void* h, const float* params_arena, cons
 
     PreCfg cfg{t->d.eps2d, t->d.near_plane, t->d.far_plane, t->d.radius_clip, t->d.ut, (int)active_sh_degree};
     t->mark(0, stream);
+    const bool exact_cull = raster_options().exact_cull != 0;
     k_preprocess_fwd<<<div_up(N, 256), 256, 0, stream>>>(params_arena, t->pl, N, t->cam_host, cfg, t->gauss, t->rects,
-                                                         t->counts, t->dk_a, t->pm_a, t->act_means, t->act_quats,
+                                                         exact_cull ? t->cull : nullptr, t->counts, t->dk_a, t->pm_a, t->act_means, t->act_quats,
                                                          t->act_scales);
     LFS_LAUNCH_OK("k_preprocess_fwd");
     t->mark(1, stream);
@@ -684,8 +925,12 @@ extern "C" int lfs_trainer_view_forward(void* h, const float* params_arena, cons
                             t->scan_scr, stream);
     if (rc)
         return rc;
-    rc = launch_emit_instances(perm, t->off, N, t->rects, t->tile_w, 0, t->inst_cap, t->n_inst, t->tk_a, t->tv_a,
-                               stream);
+    if (exact_cull)
+        rc = launch_emit_instances_cull(perm, t->off, N, t->rects, t->counts, t->cull, t->tile_w, t->inst_cap, t->n_inst,
+                                        t->tk_a, t->tv_a, stream);
+    else
+        rc = launch_emit_instances(perm, t->off, N, t->rects, t->tile_w, 0, t->inst_cap, t->n_inst, t->tk_a, t->tv_a,
+                                   stream);
     if (rc)
         return rc;
     rc = radix_sort_pairs(t->tk_a, t->tv_a, t->tk_b, t->tv_b, t->inst_cap, t->n_inst, 0, tile_key_bits(t->n_tiles),
@@ -753,6 +998,34 @@ extern "C" int lfs_trainer_view_loss_l1(void* h, const void* target, int target_
     return LFS_OK;
 }
 
+extern "C" int lfs_trainer_view_loss_ssim_l1(void* h, const void* target, int target_format, float lambda_dssim,
+                                             float weight, float* loss_accum, void* stream_) {
+    Trainer* t = static_cast<Trainer*>(h);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LFS_CHECK_ARG(t && target, "trainer_view_loss_ssim_l1: null pointer");
+    LFS_CHECK_ARG(target_format >= 0 && target_format <= 2, "trainer_view_loss_ssim_l1: bad target format");
+    LFS_CHECK_ARG(lambda_dssim >= 0.f && lambda_dssim <= 1.f, "trainer_view_loss_ssim_l1: lambda_dssim %f not in [0,1]",
+                  (double)lambda_dssim);
+    const int W = (int)t->d.width, H = (int)t->d.height;
+    const double count = 3.0 * ((H > 10 && W > 10) ? (double)(H - 10) * (double)(W - 10) : (double)H * (double)W);
+    const double n_l1 = 3.0 * (double)H * (double)W;
+    const dim3 grid(t->tile_w, t->tile_h);
+    k_ssim_fwd<<<grid, 256, 0, stream>>>(t->pix_state, target, target_format, W, H, t->bg[0], t->bg[1], t->bg[2],
+                                         (float)(-(double)weight * lambda_dssim / count), t->ssim_maps, t->loss_partials);
+    LFS_LAUNCH_OK("k_ssim_fwd");
+    k_ssim_bwd<<<grid, 256, 0, stream>>>(t->pix_state, target, target_format, W, H, t->bg[0], t->bg[1], t->bg[2],
+                                         (float)((double)weight * (1.0 - lambda_dssim) / n_l1), t->ssim_maps, t->v_pix);
+    LFS_LAUNCH_OK("k_ssim_bwd");
+    if (loss_accum) {
+        k_ssim_finish<<<1, 256, 0, stream>>>(t->loss_partials, (int)t->n_tiles,
+                                             (float)((double)weight * (1.0 - lambda_dssim) / n_l1),
+                                             (float)((double)weight * lambda_dssim / count),
+                                             (float)((double)weight * lambda_dssim), loss_accum);
+        LFS_LAUNCH_OK("k_ssim_finish");
+    }
+    return LFS_OK;
+}
+
 extern "C" int lfs_trainer_view_set_grad(void* h, const float* v_image, const float* v_alpha, void* stream_) {
     Trainer* t = static_cast<Trainer*>(h);
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -816,8 +1089,8 @@ extern "C" int lfs_trainer_view_backward(void* h, const float* params_arena, flo
         cudaEventSynchronize(t->ev[7]);
         for (int i = 0; i < LFS_PROF_STAGES; ++i) {
             float ms = 0.f;
-            if (i == 4) // loss stage is not bracketed by library events
-                continue;
+            // stage 4 = everything enqueued between the end of the forward and the backward: the loss kernels (and, when
+            // targets arrive on a copy stream, the wait for them)
             if (cudaEventElapsedTime(&ms, t->ev[i], t->ev[i + 1]) == cudaSuccess) {
                 t->acc_ms[i] += ms;
                 t->acc_n[i] += 1;

@@ -126,6 +126,13 @@ class SplatTrainer:
         check(self.lib.lfs_trainer_view_loss_l1(self.h, target.data_ptr(), fmt, s, self.loss_dev.data_ptr(),
                                                 self._stream()))
 
+    def loss_ssim_l1(self, target: torch.Tensor, lambda_dssim: float = 0.2, weight: float = 1.0,
+                     fmt: int = IMG_U8_HWC) -> None:
+        """The reference's photometric loss (src/training/trainer.cpp:103-131): (1 - l) * L1 + l * (1 - SSIM_valid);
+        lambda_dssim = 0.2 is eval/default_optimization_params.json."""
+        check(self.lib.lfs_trainer_view_loss_ssim_l1(self.h, target.data_ptr(), fmt, lambda_dssim, weight,
+                                                     self.loss_dev.data_ptr(), self._stream()))
+
     def set_grad(self, v_image: torch.Tensor, v_alpha: Optional[torch.Tensor] = None) -> None:
         check(self.lib.lfs_trainer_view_set_grad(self.h, v_image.data_ptr(),
                                                  None if v_alpha is None else v_alpha.data_ptr(), self._stream()))
@@ -186,7 +193,7 @@ class SplatTrainer:
     # ---- full step: B views -> one Adam update --------------------------------------------------------------
     def train_step(self, viewmats: np.ndarray, Ks: np.ndarray, targets_pinned: Sequence[torch.Tensor],
                    bg=(0.0, 0.0, 0.0), active_sh_degree: Optional[int] = None, world_size: int = 1, rank: int = 0,
-                   read_loss: bool = True):
+                   read_loss: bool = True, lambda_dssim: Optional[float] = 0.2):
         """targets_pinned: pinned host uint8 [H,W,3] tensors, one per view of the GLOBAL batch; this rank renders
         views rank, rank + world_size, ...  Host->device copies run on a side stream, double buffered."""
         main = torch.cuda.current_stream(self.device)
@@ -201,7 +208,10 @@ class SplatTrainer:
                 self._tgt_ready[slot].record(self.copy_stream)
             self.forward(viewmats[v], Ks[v], active_sh_degree, bg)
             main.wait_event(self._tgt_ready[slot])
-            self.loss_l1(self._tgt[slot])
+            if lambda_dssim is None:
+                self.loss_l1(self._tgt[slot])
+            else:
+                self.loss_ssim_l1(self._tgt[slot], lambda_dssim)
             self._tgt_free[slot].record(main)
             self.backward()
         if world_size > 1:

@@ -210,7 +210,8 @@ def diag_adam(n=100003):
     return out
 
 
-def diag_trainer(n=3000, w=240, h=160, deg=3, views=2, seed=21, tma=1, fused=1):
+def diag_trainer(n=3000, w=240, h=160, deg=3, views=2, seed=21, tma=1, fused=1, lambda_dssim=None, cull=1):
+    L.load().lfs_set_option(b"exact_cull", cull)
     L.load().lfs_set_option(b"blend_tma", tma)
     L.load().lfs_set_option(b"blend_fused", fused)
     out = {}
@@ -226,10 +227,13 @@ def diag_trainer(n=3000, w=240, h=160, deg=3, views=2, seed=21, tma=1, fused=1):
     for v in range(views):
         tgt = scene.make_target(v, w, h)
         img, alpha = tr.forward(sc.viewmats[v], sc.Ks[v], deg, bg, want_image=True)
-        tr.loss_l1(T(tgt, torch.uint8))
+        if lambda_dssim is None:
+            tr.loss_l1(T(tgt, torch.uint8))
+        else:
+            tr.loss_ssim_l1(T(tgt, torch.uint8), lambda_dssim)
         tr.backward()
         n_inst, n_b = tr.stats()
-        r, g = O.view_loss_grads(raw, sc.viewmats[v], sc.Ks[v], w, h, deg, bg, target=tgt)
+        r, g = O.view_loss_grads(raw, sc.viewmats[v], sc.Ks[v], w, h, deg, bg, target=tgt, lambda_dssim=lambda_dssim)
         loss_o += r["loss"]
         out[f"v{v}_n_inst"] = n_inst
         out[f"v{v}_n_inst_oracle"] = int(len(r["flatten_ids"]))
@@ -409,4 +413,23 @@ def diag_fastgs(n=3000, w=200, h=136, deg=3, seed=11, sigma_px=4.0, with_ref=Tru
         for k, rk, gg in zip(names, ("means", "scales", "rot", "op", "sh0", "shN"), g[:6]):
             out[f"ref_grad_{k}_rel"] = _rel(gg.cpu().numpy(), rg[rk].cpu().numpy().reshape(gg.shape))
             out[f"ref_oracle_grad_{k}_rel"] = _rel(rg[rk].cpu().numpy().reshape(orc["grads"][k].shape), orc["grads"][k])
+    return out
+
+
+def diag_cull_lossless(n=20000, w=640, h=360, deg=1, seed=31, sigma_px=5.0):
+    """Exact tile culling must not change a single bit of the forward: a culled (tile, Gaussian) instance holds no
+    pixel with alpha >= 1/255, and contributing pairs keep their order."""
+    sc = scene.make_scene(n, 1, w, h, deg, seed=seed, sigma_px=sigma_px)
+    out = {}
+    imgs = []
+    for cull in (0, 1):
+        L.load().lfs_set_option(b"exact_cull", cull)
+        tr = SplatTrainer(n, w, h, deg, DEV, instance_capacity=40 * n)
+        tr.load_scene(sc)
+        img, alpha = tr.forward(sc.viewmats[0], sc.Ks[0], deg, (0.2, 0.1, 0.0), want_image=True)
+        out[f"n_inst_cull{cull}"] = tr.stats()[0]
+        imgs.append((img.clone(), alpha.clone()))
+    L.load().lfs_set_option(b"exact_cull", 1)
+    out["image_bit_identical"] = bool(torch.equal(imgs[0][0], imgs[1][0]) and torch.equal(imgs[0][1], imgs[1][1]))
+    out["image_max_abs_diff"] = float((imgs[0][0] - imgs[1][0]).abs().max())
     return out

@@ -187,7 +187,7 @@ def render_view(means, quats, scales, opacities, shs, sh_degree, viewmat, K, wid
 
 
 def view_loss_grads(scene_raw, viewmat, K, width, height, sh_degree, bg, v_image=None, v_alpha=None, target=None,
-                    l1_scale=None, prec=64):
+                    l1_scale=None, prec=64, lambda_dssim=None):
     """Full per-view chain on raw parameters, as the reference composes it with torch autograd
     (rasterizer.cpp:72-81 activations, :250-266 SH + clamp, rasterizer_autograd.cpp:329-392 blend bwd,
     :84-130 SH bwd): returns (outputs dict, grads dict in the reference's AoS layout).
@@ -206,10 +206,13 @@ def view_loss_grads(scene_raw, viewmat, K, width, height, sh_degree, bg, v_image
     loss = None
     if target is not None:
         tgt = np.asarray(target, np.float64) / (255.0 if np.asarray(target).dtype == np.uint8 else 1.0)
-        s = 1.0 / (3.0 * width * height) if l1_scale is None else l1_scale
-        diff = image - tgt
-        loss = s * np.abs(diff).sum()
-        v_image = s * np.sign(diff)
+        if lambda_dssim is not None:  # the reference's L1 + SSIM loss (src/training/trainer.cpp:103-131)
+            loss, v_image, _ = photometric_loss(image, tgt, lambda_dssim)
+        else:
+            s = 1.0 / (3.0 * width * height) if l1_scale is None else l1_scale
+            diff = np.clip(image, 0.0, 1.0) - tgt  # render clamped to [0,1] (rasterizer.cpp:401)
+            loss = s * np.abs(diff).sum()
+            v_image = s * np.sign(diff) * ((image >= 0.0) & (image <= 1.0))
         v_alpha = np.zeros((height, width))
     v_alpha = np.zeros((height, width)) if v_alpha is None else v_alpha
     vm, Kk = np.asarray(viewmat)[None], np.asarray(K)[None]
@@ -274,3 +277,54 @@ def fastgs_inputs(sc, view=0):
     K = np.asarray(sc.Ks[view], np.float64)
     cam_pos = -vm[:3, :3].T @ vm[:3, 3]
     return vm, cam_pos, float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])
+
+
+# ---- photometric loss: L1 + fused SSIM ("valid" crop), the reference's training loss ------------------------
+# Trainer::compute_photometric_loss (src/training/trainer.cpp:103-131), fused_ssim (include/kernels/fused_ssim.cuh:27-122),
+# kernels src/training/kernels/ssim.cu:64-460.  11-tap separable Gaussian (ssim.cu:17-28), zero padding (:45-53).
+_SSIM_G = np.array([0.001028380123898387, 0.0075987582094967365, 0.036000773310661316, 0.10936068743467331,
+                    0.21300552785396576, 0.26601171493530273, 0.21300552785396576, 0.10936068743467331,
+                    0.036000773310661316, 0.0075987582094967365, 0.001028380123898387], np.float32).astype(np.float64)
+
+
+def _gconv(a):
+    """zero-padded separable 11x11 Gaussian of a [H,W] map (horizontal pass then vertical, ssim.cu:118-236)."""
+    H, W = a.shape
+    p = np.pad(a, ((0, 0), (5, 5)))
+    h = sum(_SSIM_G[k] * p[:, k:k + W] for k in range(11))
+    p = np.pad(h, ((5, 5), (0, 0)))
+    return sum(_SSIM_G[k] * p[k:k + H, :] for k in range(11))
+
+
+def photometric_loss(image, target, lambda_dssim, clamp=True):
+    """image [H,W,3] (render incl. background, before the [0,1] clamp of rasterizer.cpp:401), target [H,W,3] in [0,1].
+    Returns (loss, dL/dimage [H,W,3], parts dict)."""
+    image, Y = np.asarray(image, np.float64), np.asarray(target, np.float64)
+    H, W, _ = image.shape
+    X = np.clip(image, 0.0, 1.0) if clamp else image
+    passes = ((image >= 0.0) & (image <= 1.0)) if clamp else np.ones_like(image, bool)
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    crop = np.zeros((H, W))
+    if H > 10 and W > 10:  # fused_ssim.cuh:63-70 "valid"
+        crop[5:H - 5, 5:W - 5] = 1.0
+    else:
+        crop[:] = 1.0
+    count = 3.0 * crop.sum()
+    ssim_sum, g = 0.0, np.zeros_like(X)
+    for c in range(3):
+        x, y = X[..., c], Y[..., c]
+        mu1, mu2 = _gconv(x), _gconv(y)
+        s1, s2, s12 = _gconv(x * x) - mu1 * mu1, _gconv(y * y) - mu2 * mu2, _gconv(x * y) - mu1 * mu2
+        A, B = mu1 * mu1 + mu2 * mu2 + C1, s1 + s2 + C2
+        Cc, D = 2.0 * mu1 * mu2 + C1, 2.0 * s12 + C2
+        m = (Cc * D) / (A * B)  # ssim.cu:262
+        d_mu1 = (mu2 * 2.0 * D) / (A * B) - (mu2 * 2.0 * Cc) / (A * B) - (mu1 * 2.0 * Cc * D) / (A * A * B) + (
+            mu1 * 2.0 * Cc * D) / (A * B * B)  # :269
+        d_s1, d_s12 = (-Cc * D) / (A * B * B), (2.0 * Cc) / (A * B)  # :270-271
+        ssim_sum += (m * crop).sum()
+        dmap = -lambda_dssim / count * crop  # d(lambda (1 - mean))/dmap
+        g[..., c] = _gconv(dmap * d_mu1) + 2.0 * x * _gconv(dmap * d_s1) + y * _gconv(dmap * d_s12)  # :417
+    l1 = np.abs(X - Y).mean()
+    g += (1.0 - lambda_dssim) * np.sign(X - Y) / X.size
+    loss = (1.0 - lambda_dssim) * l1 + lambda_dssim * (1.0 - ssim_sum / count)
+    return loss, g * passes, dict(l1=l1, ssim=ssim_sum / count)

@@ -1,14 +1,4 @@
-set -x
-timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k fastgs 2>&1 | tail -30
-timeout 300 python tests/golden/make_fastgs_golden.py gpurun_out/fastgs_ref_golden.npz 2>&1 | tail -3
-timeout 300 python - <<'PY' 2>&1 | tail -30
-import sys, json
-sys.path.insert(0, 'tests')
-import gpu_diag as D
-for kw in (dict(), dict(n=1500, w=120, h=100, deg=1, seed=5, sigma_px=7.0)):
-    try:
-        r = D.diag_fastgs(**kw)
-        print(json.dumps({k: (round(v, 8) if isinstance(v, float) else v) for k, v in r.items()}))
-    except Exception as e:
-        import traceback; traceback.print_exc()
-PY
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -6
+timeout 300 python tools/bench_fastgs.py C3 4 3 2>&1 | tail -1 | cut -c1-400
+timeout 300 python bench.py --steps 8 --warmup 3 > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err
+tail -1 gpurun_out/bench_full.json | cut -c1-300
