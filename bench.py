@@ -119,7 +119,8 @@ def cpu_reference_leg(scene_obj, seconds: float):
     t0 = time.time()
     reps = 0
     while True:
-        O.view_loss_grads(raw, sc.viewmats[0], K, cw, ch, sc.sh_degree, (0.0, 0.0, 0.0), target=tgt, prec=32)
+        O.view_loss_grads(raw, sc.viewmats[0], K, cw, ch, sc.sh_degree, (0.0, 0.0, 0.0), target=tgt, prec=32,
+                          lambda_dssim=LAMBDA_DSSIM)
         reps += 1
         if time.time() - t0 > seconds or reps >= 3:
             break
@@ -129,7 +130,7 @@ def cpu_reference_leg(scene_obj, seconds: float):
     # views/s is reported for the crop as if it were the image (an upper bound for the CPU path)
     return {"value": frac / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"1 view, all {sc.n} Gaussians, centred {cw}x{ch} crop of {W}x{H} ({frac:.4f} of the pixels), "
-                      f"fwd+bwd, {reps} reps, {dt:.2f} s each; value = crop fraction / time"}
+                      f"fwd + L1/SSIM loss + bwd, {reps} reps, {dt:.2f} s each; value = crop fraction / time"}
 
 
 def reference_gpu_leg(sc, steps: int, warmup: int, device):
@@ -430,6 +431,18 @@ def main():
     bwd_ms = prof.get("blend_bwd", 0.0)
     achieved = bwd_bytes / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 else 0.0
     h2d = sum(int(targets_host[v].numel()) for v in my_views) + len(my_views) * (16 + 9) * 4
+    # DRAM traffic of the same kernel from the committed `ncu --set full` capture of tools/profile_view.py on this
+    # workload (profiles/r01_ncu_full_final.json; ncu cannot run inside a timed bench)
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_full_final.json")) as f:
+            for k in json.load(f):
+                if k["kernel"].startswith("k_blend_bwd"):
+                    traffic = (k["dram__bytes_read.sum"] + k["dram__bytes_write.sum"]) * 1e6  # ncu reports Mbyte
+                    traffic_src = "profiles/r01_ncu_full_final.json (dram__bytes_read.sum + dram__bytes_write.sum)"
+                    break
+    except (OSError, KeyError, ValueError):
+        pass
     line = {
         "metric": METRIC, "value": V / ms_step * 1e3, "unit": UNIT, "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -447,7 +460,8 @@ def main():
                         "loss scalar read back per step"},
         "gpu_launches": launches,
         "roofline": {"kernel": "k_blend_bwd", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src,
                      "algorithmic_bytes": bwd_bytes, "launch_ms": bwd_ms,
                      "note": "algorithmic bytes = 172*I + 24*P per view (BASELINE.md s5); the kernel is FP32/SFU "
                              "bound, not HBM bound (SURVEY s7 'roofline honesty')"},

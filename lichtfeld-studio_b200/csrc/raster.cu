@@ -195,7 +195,7 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
 // tile's still-active pixels that is rebuilt in shared memory after every staged batch of 64 records.  Pixels
 // that saturate (T <= 1e-4) or lie outside the image drop out of the list, so the few pixels of a tile that never
 // saturate (silhouettes, sky) no longer drag 32-wide warps through the whole instance list with 1-2 live lanes
-// (measured before: 2.0 active threads per warp instruction on the C3 scene, profiles/r01_*).  One staged record
+// (measured before: 2.0 active threads per warp instruction on the C3 scene, profiles/r01_diag_first_gpu_run.json).  One staged record
 // (4 x LDS.128) serves 4 pixel evaluations.  The polynomial nesting is mirrored exactly by the backward so a pair
 // gets the same alpha bits in both passes.
 constexpr int kFwdThreads = kTilePix / 4;

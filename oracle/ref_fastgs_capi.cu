@@ -93,7 +93,7 @@ int ref_fastgs_forward(void* h, const float* means, const float* scales_raw, con
     };
     // The reference zeroes PerTileBuffers::instance_ranges with cudaMemsetAsync on a private static stream
     // (fastgs/rasterization/src/forward.cu:48-55).  On this image (CUDA 12.9 runtime inside a torch process)
-    // that call returns cudaErrorInvalidValue (compute-sanitizer, profiles/r01_ref_fastgs_memset.txt), the ranges of
+    // that call returns cudaErrorInvalidValue (compute-sanitizer, profiles/r01_ref_fastgs_diagnosis.txt), the ranges of
     // empty tiles stay uninitialised and n_buckets becomes garbage.  Zeroing the whole per-tile blob here, right
     // before the reference carves it, gives the state the reference intends without touching its sources.
     auto f_tile = [c](size_t n) {
