@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--config", default="C3")
     ap.add_argument("--n-gaussians", type=int, default=0, help="override N (testing only; invalidates the metric)")
     ap.add_argument("--views-per-gpu", type=int, default=0)
+    ap.add_argument("--dp", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="N > 1: fused reduce-scatter+Adam+all-gather over NVLink peer memory (p2p) or ncclAllReduce + "
+                         "local Adam (nccl); auto = p2p when symmetric memory can be set up")
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / reference_gpu legs")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--ref-gpu-leg", default="", choices=["", "fastgs", "gsplat"], help=argparse.SUPPRESS)
@@ -362,6 +365,21 @@ def main():
         tr.forward(sc.viewmats[v], sc.Ks[v], deg)
         n_inst_per_view.append(tr.stats()[0])
 
+    dp_mode = "single"
+    if world > 1:
+        dp_mode = "nccl all-reduce of the flat gradient arena + local Adam"
+        if a.dp in ("auto", "p2p"):
+            try:
+                tr.enable_p2p()
+                dp_mode = "fused reduce-scatter + Adam + all-gather over NVLink peer memory (lfs_adam_step_multi_p2p)"
+            except Exception as e:  # symmetric memory unavailable on this box: the NCCL path is the validated default
+                if a.dp == "p2p":
+                    raise
+                dp_mode += f" (p2p unavailable: {type(e).__name__})"
+        flag = torch.tensor([1 if tr.p2p else 0], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # all ranks or none
+        if int(flag.item()) == 0:
+            tr.p2p = False
     targets_host = [torch.as_tensor(S.make_target(v, W, H)).pin_memory() for v in range(V)]
     targets_dev = {v: targets_host[v].to(device) for v in my_views}
     bg = (0.0, 0.0, 0.0)
@@ -378,7 +396,10 @@ def main():
             tr.loss_ssim_l1(targets_dev[v], LAMBDA_DSSIM)
             tr.backward()
         if world > 1:
-            dist.all_reduce(tr.grads, op=dist.ReduceOp.SUM)
+            if tr.p2p:
+                tr._h_grads.barrier(channel=0)
+            else:
+                dist.all_reduce(tr.grads, op=dist.ReduceOp.SUM)
         tr.adam_step()
 
     def step_e2e():
@@ -450,7 +471,7 @@ def main():
         "config": {"workload": f"{a.config}: {n} Gaussians, {vpg} views/GPU x {world} GPU of {W}x{H}, SH degree {deg}, "
                                "3DGUT from-world rasterizer, L1 + fused-SSIM loss (lambda_dssim 0.2), eval/default_optimization_params.json lrs",
                    "gaussians": n, "views_per_step": V, "width": W, "height": H, "sh_degree": deg,
-                   "parallelism": f"view-sharded dp{world} + NCCL all-reduce of the flat gradient arena",
+                   "parallelism": f"view-sharded dp{world}: {dp_mode}",
                    "instances_per_view": I, "l2": "per-step working set (params+grads+Adam state+records) >= 1 GB, "
                                                   "larger than the 126 MB L2: no flush needed"},
         "clocks": clk,

@@ -79,6 +79,47 @@ __global__ void __launch_bounds__(kAdamThreads)
     }
 }
 
+// Multi-GPU step: reduce-scatter + Adam + all-gather in ONE kernel over NVLink peer memory.  Rank r owns the slice
+// [lo4, hi4) of the flat arena: it sums that slice of every rank's gradient arena with peer loads (fixed rank order ->
+// every element is reduced by exactly one rank, deterministically), applies Adam to its local p / m / v, then writes the
+// new parameters into every rank's parameter arena and clears the slice of every rank's gradient arena with peer stores.
+// Compared with ncclAllReduce(236 MB) + a full Adam on every rank this moves the same bytes over NVLink once, does 1/W of
+// the Adam traffic per GPU and needs no separate collective launch.  The caller brackets it with two stream-ordered
+// barriers (all backward passes done before; all parameter writes landed after).
+struct PeerPtrs {
+    float* const* grads;  // device array [world]: peer-mapped gradient arenas
+    float* const* params; // device array [world]: peer-mapped parameter arenas
+    int world, rank;
+};
+__global__ void __launch_bounds__(kAdamThreads)
+    k_adam_multi_p2p(const PeerPtrs pp, float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, const size_t base,
+                     const AdamSegs segs, const int64_t lo4, const int64_t hi4, const float beta1, const float beta2,
+                     const float eps) {
+    float4* m4 = reinterpret_cast<float4*>(exp_avg + base);
+    float4* v4 = reinterpret_cast<float4*>(exp_avg_sq + base);
+    float4* p4 = reinterpret_cast<float4*>(pp.params[pp.rank] + base);
+    const int64_t stride = (int64_t)gridDim.x * kAdamThreads;
+    for (int64_t i = lo4 + (int64_t)blockIdx.x * kAdamThreads + threadIdx.x; i < hi4; i += stride) {
+        float4 p = p4[i], m = m4[i], v = v4[i];
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < pp.world; ++r) {
+            const float4 x = __ldcv(reinterpret_cast<const float4*>(pp.grads[r] + base) + i); // never a stale L1 line
+            g.x += x.x, g.y += x.y, g.z += x.z, g.w += x.w;
+        }
+        int s = 0;
+#pragma unroll
+        for (int k = 1; k < kAdamMaxSeg; ++k)
+            if (k < segs.n)
+                s += (i >= segs.begin4[k]);
+        adam_update4(p, m, v, g, beta1, beta2, eps, segs.step_size[s], segs.bc2[s]);
+        m4[i] = m, v4[i] = v;
+        for (int r = 0; r < pp.world; ++r) {
+            reinterpret_cast<float4*>(pp.params[r] + base)[i] = p;
+            reinterpret_cast<float4*>(pp.grads[r] + base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+
 // single-tensor, arbitrary n / alignment: vector body + scalar head/tail
 __global__ void __launch_bounds__(kAdamThreads)
     k_adam_single(float* __restrict__ param, float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
@@ -163,5 +204,42 @@ extern "C" int lfs_adam_step_multi(float* params, float* exp_avg, float* exp_avg
     k_adam_multi<<<adam_grid((n4 + 1) / 2), kAdamThreads, 0, (cudaStream_t)stream>>>(
         params + base, exp_avg + base, exp_avg_sq + base, grads + base, segs, beta1, beta2, eps, zero_grad);
     LFS_LAUNCH_OK("k_adam_multi");
+    return LFS_OK;
+}
+
+extern "C" int lfs_adam_step_multi_p2p(float* exp_avg, float* exp_avg_sq, const void* grads_peers_dev,
+                                       const void* params_peers_dev, int world, int rank, int n_segments,
+                                       const int64_t* seg_begin_host, const float* lr_host, const float* bc1_rcp_host,
+                                       const float* bc2_sqrt_rcp_host, float beta1, float beta2, float eps, void* stream) {
+    using namespace lfs;
+    LFS_CHECK_ARG(n_segments >= 1 && n_segments <= kAdamMaxSeg, "adam_step_multi_p2p: n_segments=%d out of range",
+                  n_segments);
+    LFS_CHECK_ARG(exp_avg && exp_avg_sq && grads_peers_dev && params_peers_dev && seg_begin_host && lr_host &&
+                      bc1_rcp_host && bc2_sqrt_rcp_host,
+                  "adam_step_multi_p2p: null pointer");
+    LFS_CHECK_ARG(world >= 1 && rank >= 0 && rank < world, "adam_step_multi_p2p: bad rank %d of %d", rank, world);
+    AdamSegs segs;
+    segs.n = n_segments;
+    for (int s = 0; s <= n_segments; ++s) {
+        LFS_CHECK_ARG((seg_begin_host[s] & 3) == 0, "adam_step_multi_p2p: segment boundary %d not a multiple of 4", s);
+        LFS_CHECK_ARG(s == 0 || seg_begin_host[s] >= seg_begin_host[s - 1], "adam_step_multi_p2p: unsorted segments");
+        segs.begin4[s] = (seg_begin_host[s] - seg_begin_host[0]) / 4;
+    }
+    for (int s = 0; s < n_segments; ++s) {
+        segs.step_size[s] = lr_host[s] * bc1_rcp_host[s];
+        segs.bc2[s] = bc2_sqrt_rcp_host[s];
+    }
+    const int64_t n4 = segs.begin4[n_segments];
+    if (n4 == 0)
+        return LFS_OK;
+    const int64_t per = (n4 + world - 1) / world;
+    const int64_t lo4 = per * rank, hi4 = lo4 + per < n4 ? lo4 + per : n4;
+    if (hi4 <= lo4)
+        return LFS_OK;
+    const PeerPtrs pp{static_cast<float* const*>(grads_peers_dev), static_cast<float* const*>(params_peers_dev), world,
+                      rank};
+    k_adam_multi_p2p<<<adam_grid(hi4 - lo4), kAdamThreads, 0, (cudaStream_t)stream>>>(
+        pp, exp_avg, exp_avg_sq, (size_t)seg_begin_host[0], segs, lo4, hi4, beta1, beta2, eps);
+    LFS_LAUNCH_OK("k_adam_multi_p2p");
     return LFS_OK;
 }

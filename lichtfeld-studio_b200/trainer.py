@@ -64,6 +64,26 @@ class SplatTrainer:
         self._tgt_ready = [torch.cuda.Event() for _ in range(2)]
         self._tgt_free = [torch.cuda.Event() for _ in range(2)]
         self._loss_pinned = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self.p2p = False
+
+    # ---- multi-GPU: peer-mapped arenas for the fused reduce-scatter + Adam + all-gather step -----------------------
+    def enable_p2p(self, group=None) -> None:
+        """Re-homes the parameter and gradient arenas in torch symmetric memory (CUDA backend: cuMem + fabric/IPC
+        handles, every rank maps every peer's buffer over NVLink) so that adam_step() can run
+        lfs_adam_step_multi_p2p instead of ncclAllReduce + a full local Adam.  Collective: call on every rank."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group or dist.group.WORLD
+        self._p2p_world, self._p2p_rank = dist.get_world_size(group), dist.get_rank(group)
+        n = self.params.numel()
+        new_p = symm_mem.empty(n, dtype=torch.float32, device=self.device)
+        new_g = symm_mem.empty(n, dtype=torch.float32, device=self.device)
+        new_p.copy_(self.params)
+        new_g.copy_(self.grads)
+        self._h_params = symm_mem.rendezvous(new_p, group)
+        self._h_grads = symm_mem.rendezvous(new_g, group)
+        self.params, self.grads = new_p, new_g
+        self.p2p = True
 
     def __del__(self):
         h, self.h = getattr(self, "h", None), None
@@ -183,9 +203,17 @@ class SplatTrainer:
             lr = (C.c_float * n)(*[g[1] for g in run])
             bc1 = (C.c_float * n)(*[g[2] for g in run])
             bc2 = (C.c_float * n)(*[g[3] for g in run])
-            check(self.lib.lfs_adam_step_multi(self.params.data_ptr(), self.exp_avg.data_ptr(),
-                                               self.exp_avg_sq.data_ptr(), self.grads.data_ptr(), n, seg, lr, bc1, bc2,
-                                               b1, b2, self.eps, 1, self._stream()))
+            if self.p2p:
+                check(self.lib.lfs_adam_step_multi_p2p(self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                                                       self._h_grads.buffer_ptrs_dev, self._h_params.buffer_ptrs_dev,
+                                                       self._p2p_world, self._p2p_rank, n, seg, lr, bc1, bc2, b1, b2,
+                                                       self.eps, self._stream()))
+            else:
+                check(self.lib.lfs_adam_step_multi(self.params.data_ptr(), self.exp_avg.data_ptr(),
+                                                   self.exp_avg_sq.data_ptr(), self.grads.data_ptr(), n, seg, lr, bc1,
+                                                   bc2, b1, b2, self.eps, 1, self._stream()))
+        if self.p2p:
+            self._h_params.barrier(channel=1)  # every rank's parameter writes (and gradient clears) have landed
         if len(runs) != 1 or len(runs[0]) != 6:
             self.grads.zero_()  # skipped segments still need their gradients cleared
         self.lrs["means"] *= self.means_gamma  # ExponentialLR on group 0 only
@@ -215,7 +243,10 @@ class SplatTrainer:
             self._tgt_free[slot].record(main)
             self.backward()
         if world_size > 1:
-            dp.allreduce_sum_(self.grads)  # ONE collective over the flat planar gradient arena
+            if self.p2p:
+                self._h_grads.barrier(channel=0)  # all ranks finished their backward passes; then the fused step
+            else:
+                dp.allreduce_sum_(self.grads)  # ONE collective over the flat planar gradient arena
             dp.allreduce_sum_(self.loss_dev)
         self.adam_step()
         if read_loss:
