@@ -371,7 +371,9 @@ def main():
         if a.dp in ("auto", "p2p"):
             try:
                 tr.enable_p2p()
-                dp_mode = "fused reduce-scatter + Adam + all-gather over NVLink peer memory (lfs_adam_step_multi_p2p)"
+                dp_mode = ("fused reduce-scatter + Adam + all-gather in one kernel (lfs_adam_step_multi_p2p), " +
+                           ("NVSwitch multicast: multimem.ld_reduce / multimem.st" if tr._mc_grads
+                            else "NVLink peer loads / stores"))
             except Exception as e:  # symmetric memory unavailable on this box: the NCCL path is the validated default
                 if a.dp == "p2p":
                     raise

@@ -175,10 +175,14 @@ int lfs_adam_step_multi(float* params, float* exp_avg, float* exp_avg_sq, float*
  * params_peers_dev are DEVICE arrays of `world` pointers to every rank's (peer-mapped) gradient / parameter arena, e.g.
  * torch.distributed._symmetric_memory buffer_ptrs_dev; exp_avg / exp_avg_sq are this rank's.  This rank reduces and
  * updates slice `rank` of [seg_begin[0], seg_begin[n]) (split evenly in 16-byte units), writes the new parameters to all
- * ranks and clears that slice of all gradient arenas.  The caller issues a stream-ordered barrier over all ranks before
- * (all backward passes finished) and after (all parameter writes landed) this call. */
+ * ranks.  When grads_multicast / params_multicast (NVSwitch multicast addresses of the same buffers, e.g. symmetric
+ * memory multicast_ptr; NULL if unsupported) are given, the reduction happens inside the switch (multimem.ld_reduce) and
+ * the parameters are broadcast with one multimem.st; params_local is then this rank's own arena.  The caller issues a
+ * stream-ordered barrier over all ranks before (all backward passes finished) and after (all parameter writes landed)
+ * this call and clears its own gradient arena after the second barrier. */
 int lfs_adam_step_multi_p2p(float* exp_avg, float* exp_avg_sq, const void* grads_peers_dev, const void* params_peers_dev,
-                            int world, int rank, int n_segments, const int64_t* seg_begin_host, const float* lr_host,
+                            const float* grads_multicast, float* params_multicast, float* params_local, int world,
+                            int rank, int n_segments, const int64_t* seg_begin_host, const float* lr_host,
                             const float* bc1_rcp_host, const float* bc2_sqrt_rcp_host, float beta1, float beta2,
                             float eps, void* stream);
 

@@ -113,7 +113,7 @@ SIGNATURES = {
         [_vp, _vp, _vp, _vp, C.c_int, C.POINTER(_i64), C.POINTER(_f), C.POINTER(_f), C.POINTER(_f), _f, _f, _f,
          C.c_int, _vp],
     ),
-    "lfs_adam_step_multi_p2p": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _f, _f, _f, _vp]),
+    "lfs_adam_step_multi_p2p": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _f, _f, _f, _vp]),
     "lfs_quats_to_rotmats": (C.c_int, [_vp, _u32, _vp, _vp]),
     "lfs_relocation": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _u32, _vp, _vp, _vp]),
     "lfs_add_noise": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _f, _u32, _vp]),

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kAdamThreads)
 // Multi-GPU step: reduce-scatter + Adam + all-gather in ONE kernel over NVLink peer memory.  Rank r owns the slice
 // [lo4, hi4) of the flat arena: it sums that slice of every rank's gradient arena with peer loads (fixed rank order ->
 // every element is reduced by exactly one rank, deterministically), applies Adam to its local p / m / v, then writes the
-// new parameters into every rank's parameter arena and clears the slice of every rank's gradient arena with peer stores.
+// new parameters into every rank's parameter arena with peer stores (every rank clears its own gradients afterwards).
 // Compared with ncclAllReduce(236 MB) + a full Adam on every rank this moves the same bytes over NVLink once, does 1/W of
 // the Adam traffic per GPU and needs no separate collective launch.  The caller brackets it with two stream-ordered
 // barriers (all backward passes done before; all parameter writes landed after).
@@ -113,10 +113,39 @@ __global__ void __launch_bounds__(kAdamThreads)
                 s += (i >= segs.begin4[k]);
         adam_update4(p, m, v, g, beta1, beta2, eps, segs.step_size[s], segs.bc2[s]);
         m4[i] = m, v4[i] = v;
-        for (int r = 0; r < pp.world; ++r) {
+        for (int r = 0; r < pp.world; ++r)
             reinterpret_cast<float4*>(pp.params[r] + base)[i] = p;
-            reinterpret_cast<float4*>(pp.grads[r] + base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+    }
+}
+
+// Same step through the NVSwitch multicast object (NVLS): ONE multimem.ld_reduce returns the sum of the slice over all
+// ranks, reduced inside the switch (inbound traffic 1x instead of (W-1)x), ONE multimem.st broadcasts the new parameters.
+__global__ void __launch_bounds__(kAdamThreads)
+    k_adam_multi_mc(float* __restrict__ params_local, float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
+                    const float* __restrict__ grads_mc, float* __restrict__ params_mc, const size_t base,
+                    const AdamSegs segs, const int64_t lo4, const int64_t hi4, const float beta1, const float beta2,
+                    const float eps) {
+    float4* m4 = reinterpret_cast<float4*>(exp_avg + base);
+    float4* v4 = reinterpret_cast<float4*>(exp_avg_sq + base);
+    const float4* p4 = reinterpret_cast<const float4*>(params_local + base);
+    const int64_t stride = (int64_t)gridDim.x * kAdamThreads;
+    for (int64_t i = lo4 + (int64_t)blockIdx.x * kAdamThreads + threadIdx.x; i < hi4; i += stride) {
+        float4 p = p4[i], m = m4[i], v = v4[i], g;
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(g.x), "=f"(g.y), "=f"(g.z), "=f"(g.w)
+                     : "l"(reinterpret_cast<const float4*>(grads_mc + base) + i)
+                     : "memory");
+        int s = 0;
+#pragma unroll
+        for (int k = 1; k < kAdamMaxSeg; ++k)
+            if (k < segs.n)
+                s += (i >= segs.begin4[k]);
+        adam_update4(p, m, v, g, beta1, beta2, eps, segs.step_size[s], segs.bc2[s]);
+        m4[i] = m, v4[i] = v;
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(
+                         reinterpret_cast<float4*>(params_mc + base) + i),
+                     "f"(p.x), "f"(p.y), "f"(p.z), "f"(p.w)
+                     : "memory");
     }
 }
 
@@ -208,7 +237,8 @@ extern "C" int lfs_adam_step_multi(float* params, float* exp_avg, float* exp_avg
 }
 
 extern "C" int lfs_adam_step_multi_p2p(float* exp_avg, float* exp_avg_sq, const void* grads_peers_dev,
-                                       const void* params_peers_dev, int world, int rank, int n_segments,
+                                       const void* params_peers_dev, const float* grads_multicast,
+                                       float* params_multicast, float* params_local, int world, int rank, int n_segments,
                                        const int64_t* seg_begin_host, const float* lr_host, const float* bc1_rcp_host,
                                        const float* bc2_sqrt_rcp_host, float beta1, float beta2, float eps, void* stream) {
     using namespace lfs;
@@ -236,6 +266,14 @@ extern "C" int lfs_adam_step_multi_p2p(float* exp_avg, float* exp_avg_sq, const 
     const int64_t lo4 = per * rank, hi4 = lo4 + per < n4 ? lo4 + per : n4;
     if (hi4 <= lo4)
         return LFS_OK;
+    if (grads_multicast && params_multicast) {
+        LFS_CHECK_ARG(params_local != nullptr, "adam_step_multi_p2p: params_local is required with multicast pointers");
+        k_adam_multi_mc<<<adam_grid(hi4 - lo4), kAdamThreads, 0, (cudaStream_t)stream>>>(
+            params_local, exp_avg, exp_avg_sq, grads_multicast, params_multicast, (size_t)seg_begin_host[0], segs, lo4,
+            hi4, beta1, beta2, eps);
+        LFS_LAUNCH_OK("k_adam_multi_mc");
+        return LFS_OK;
+    }
     const PeerPtrs pp{static_cast<float* const*>(grads_peers_dev), static_cast<float* const*>(params_peers_dev), world,
                       rank};
     k_adam_multi_p2p<<<adam_grid(hi4 - lo4), kAdamThreads, 0, (cudaStream_t)stream>>>(

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Optional, Sequence
 
 import numpy as np
@@ -83,6 +84,12 @@ class SplatTrainer:
         self._h_params = symm_mem.rendezvous(new_p, group)
         self._h_grads = symm_mem.rendezvous(new_g, group)
         self.params, self.grads = new_p, new_g
+        # NVSwitch multicast (NVLS) addresses of the same buffers, 0 when the fabric has none; LFS_P2P_MULTICAST=0 forces
+        # the plain peer load/store kernel
+        self._mc_grads = int(getattr(self._h_grads, "multicast_ptr", 0) or 0)
+        self._mc_params = int(getattr(self._h_params, "multicast_ptr", 0) or 0)
+        if os.environ.get("LFS_P2P_MULTICAST", "1") == "0" or not (self._mc_grads and self._mc_params):
+            self._mc_grads = self._mc_params = 0
         self.p2p = True
 
     def __del__(self):
@@ -206,15 +213,17 @@ class SplatTrainer:
             if self.p2p:
                 check(self.lib.lfs_adam_step_multi_p2p(self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
                                                        self._h_grads.buffer_ptrs_dev, self._h_params.buffer_ptrs_dev,
-                                                       self._p2p_world, self._p2p_rank, n, seg, lr, bc1, bc2, b1, b2,
-                                                       self.eps, self._stream()))
+                                                       self._mc_grads or None, self._mc_params or None,
+                                                       self.params.data_ptr(), self._p2p_world, self._p2p_rank, n, seg,
+                                                       lr, bc1, bc2, b1, b2, self.eps, self._stream()))
             else:
                 check(self.lib.lfs_adam_step_multi(self.params.data_ptr(), self.exp_avg.data_ptr(),
                                                    self.exp_avg_sq.data_ptr(), self.grads.data_ptr(), n, seg, lr, bc1,
                                                    bc2, b1, b2, self.eps, 1, self._stream()))
         if self.p2p:
-            self._h_params.barrier(channel=1)  # every rank's parameter writes (and gradient clears) have landed
-        if len(runs) != 1 or len(runs[0]) != 6:
+            self._h_params.barrier(channel=1)  # every rank's parameter writes have landed, nobody reads gradients any more
+            self.grads.zero_()
+        elif len(runs) != 1 or len(runs[0]) != 6:
             self.grads.zero_()  # skipped segments still need their gradients cleared
         self.lrs["means"] *= self.means_gamma  # ExponentialLR on group 0 only
 

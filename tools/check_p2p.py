@@ -61,7 +61,7 @@ dist.all_gather(same, res["p2p"][0])
 ident = all(torch.equal(same[0], t) for t in same)
 moved = float((res["p2p"][0] - P0).abs().max())
 if rank == 0:
-    print({"world": world, "max_abs_diff_p2p_vs_nccl": float(diff.max()), "fraction_bit_equal": frac_equal,
+    print({"world": world, "multicast": bool(tr._mc_grads), "max_abs_diff_p2p_vs_nccl": float(diff.max()), "fraction_bit_equal": frac_equal,
            "max_param_change": moved, "ranks_bit_identical_after_p2p": ident,
            "grads_cleared": [res["nccl"][1], res["p2p"][1]]})
     assert moved > 0 and ident and res["nccl"][1] and res["p2p"][1]
