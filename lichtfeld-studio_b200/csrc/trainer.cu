@@ -57,7 +57,7 @@ struct Trainer {
     float *v_means, *v_quats, *v_scales, *v_colors, *v_opac;
     float *act_means, *act_quats, *act_scales; // activated AoS copies for the blend-backward epilogue
     float* loss_partials;
-    float* ssim_maps; // [3 channels][3 maps][H*W]: dL/dmap * (dm/dmu1, dm/dsigma1^2, dm/dsigma12)
+    float* ssim_maps; // [3 channels][H*W] float4: dL/dmap * (dm/dmu1, dm/dsigma1^2, dm/dsigma12, -)
     void *scan_scr, *sort_scr;
     const uint32_t* sorted_keys = nullptr;
     const uint32_t* sorted_vals = nullptr;
@@ -112,7 +112,7 @@ static size_t trainer_carve(Trainer& t, void* base) {
     t.act_quats = c.take<float>(4 * (size_t)N);
     t.act_scales = c.take<float>(3 * (size_t)N);
     t.loss_partials = c.take<float>(2 * (size_t)t.n_tiles + 2);
-    t.ssim_maps = c.take<float>(9 * (size_t)npix);
+    t.ssim_maps = c.take<float>(12 * (size_t)npix);
     t.scan_scr = c.take<char>(scan_scratch_bytes(N > t.n_tiles + 1 ? N : t.n_tiles + 1));
     t.sort_scr = c.take<char>(radix_scratch_bytes(N > t.inst_cap ? N : t.inst_cap));
     return c.total();
@@ -595,10 +595,12 @@ __global__ void __launch_bounds__(256)
     k_ssim_fwd(const float4* __restrict__ pix_state, const void* __restrict__ target, const int fmt, const int W,
                const int H, const float bg_r, const float bg_g, const float bg_b, const float dmap /* -w*lambda/count */,
                float* __restrict__ maps, float* __restrict__ partials) {
-    // one global-load phase for all three channels (the per-channel load -> sync -> conv chain of the first version was
-    // latency bound: 0.28 ms per 1080p view), then the separable convolutions run out of shared memory
-    __shared__ float sX[3][kSsimS][kSsimS], sY[3][kSsimS][kSsimS];
-    __shared__ float xc[kSsimS][kTile][5];
+    // One global-load phase for all three channels, then the separable convolutions run out of shared memory.
+    // Layouts are chosen for wide shared loads: (X, Y) pairs -> one LDS.64 per tap, the four horizontal sums
+    // (mu1, mu2, E[X^2 + Y^2], E[XY]) -> one LDS.128 per tap.  sigma1^2 + sigma2^2 only ever appears as a sum in the
+    // SSIM formula, so X^2 and Y^2 share one convolution (4 instead of the reference's 5, ssim.cu:118-247).
+    __shared__ float2 sXY[3][kSsimS][kSsimS];
+    __shared__ float4 xc[kSsimS][kTile];
     __shared__ float s_red[2][8];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
@@ -618,52 +620,52 @@ __global__ void __launch_bounds__(256)
             Y0 = target_at(target, fmt, npix, i, 0), Y1 = target_at(target, fmt, npix, i, 1);
             Y2 = target_at(target, fmt, npix, i, 2);
         }
-        sX[0][ly][lx] = X0, sX[1][ly][lx] = X1, sX[2][ly][lx] = X2;
-        sY[0][ly][lx] = Y0, sY[1][ly][lx] = Y1, sY[2][ly][lx] = Y2;
+        sXY[0][ly][lx] = make_float2(X0, Y0), sXY[1][ly][lx] = make_float2(X1, Y1), sXY[2][ly][lx] = make_float2(X2, Y2);
     }
     __syncthreads();
     float l1 = 0.f, ss = 0.f;
     for (int c = 0; c < 3; ++c) {
-        for (int t = threadIdx.x; t < kSsimS * kTile; t += 256) { // horizontal 11x1, ssim.cu:118-210
+        for (int t = threadIdx.x; t < kSsimS * kTile; t += 256) { // horizontal 11x1
             const int ly = t >> 4, lx = (t & 15) + kSsimHalo;
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
             for (int d = -kSsimHalo; d <= kSsimHalo; ++d) {
-                const float w = c_ssim_g[d + kSsimHalo], X = sX[c][ly][lx + d], Y = sY[c][ly][lx + d];
-                a0 = fmaf(w, X, a0), a1 = fmaf(w, X * X, a1), a2 = fmaf(w, Y, a2), a3 = fmaf(w, Y * Y, a3);
-                a4 = fmaf(w, X * Y, a4);
+                const float w = c_ssim_g[d + kSsimHalo];
+                const float2 v = sXY[c][ly][lx + d];
+                a0 = fmaf(w, v.x, a0), a1 = fmaf(w, v.y, a1), a2 = fmaf(w, fmaf(v.x, v.x, v.y * v.y), a2);
+                a3 = fmaf(w, v.x * v.y, a3);
             }
-            float* o = xc[ly][t & 15];
-            o[0] = a0, o[1] = a1, o[2] = a2, o[3] = a3, o[4] = a4;
+            xc[ly][t & 15] = make_float4(a0, a1, a2, a3);
         }
         __syncthreads();
         {
-            float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f, o4 = 0.f; // vertical 1x11, :216-247
+            float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f; // vertical 1x11
 #pragma unroll
             for (int d = 0; d < 2 * kSsimHalo + 1; ++d) {
                 const float w = c_ssim_g[d];
-                const float* r = xc[ty + d][tx];
-                o0 = fmaf(w, r[0], o0), o1 = fmaf(w, r[1], o1), o2 = fmaf(w, r[2], o2), o3 = fmaf(w, r[3], o3);
-                o4 = fmaf(w, r[4], o4);
+                const float4 r = xc[ty + d][tx];
+                o0 = fmaf(w, r.x, o0), o1 = fmaf(w, r.y, o1), o2 = fmaf(w, r.z, o2), o3 = fmaf(w, r.w, o3);
             }
             if (px < W && py < H) {
-                const float mu1 = o0, mu2 = o2, s1 = o1 - mu1 * mu1, s2 = o3 - mu2 * mu2, s12 = o4 - mu1 * mu2;
+                const float mu1 = o0, mu2 = o1, s12 = o3 - mu1 * mu2;
                 const float C1 = 0.0001f, C2 = 0.0009f;
-                const float A = mu1 * mu1 + mu2 * mu2 + C1, B = s1 + s2 + C2, Cc = 2.f * mu1 * mu2 + C1, D = 2.f * s12 + C2;
+                const float A = mu1 * mu1 + mu2 * mu2 + C1;
+                const float B = o2 - mu1 * mu1 - mu2 * mu2 + C2; // sigma1^2 + sigma2^2 + C2
+                const float Cc = 2.f * mu1 * mu2 + C1, D = 2.f * s12 + C2;
                 const float iAB = 1.0f / (A * B);
-                const float val = Cc * D * iAB; // :262
+                const float val = Cc * D * iAB; // ssim.cu:262
                 const bool in_crop = crop_all || (px >= 5 && px < W - 5 && py >= 5 && py < H - 5);
                 const float dm = in_crop ? dmap : 0.f;
                 const float d_mu1 = (mu2 * 2.f * D) * iAB - (mu2 * 2.f * Cc) * iAB - (mu1 * 2.f * Cc * D) * iAB / A +
                                     (mu1 * 2.f * Cc * D) * iAB / B; // :269
                 const uint32_t i = (uint32_t)py * W + px;
-                float* m = maps + (size_t)c * 3 * npix;
-                m[i] = dm * d_mu1;
-                m[npix + i] = dm * (-Cc * D) * iAB / B;          // dm/dsigma1^2, :270
-                m[2 * (size_t)npix + i] = dm * (2.f * Cc) * iAB; // dm/dsigma12,  :271
+                // (dL/dmap) * (dm/dmu1, dm/dsigma1^2, dm/dsigma12) interleaved per channel: one 16-B record per pixel
+                reinterpret_cast<float4*>(maps)[(size_t)c * npix + i] =
+                    make_float4(dm * d_mu1, dm * (-Cc * D) * iAB / B, dm * (2.f * Cc) * iAB, 0.f); // :269-271
                 if (in_crop)
                     ss += val;
-                l1 += fabsf(sX[c][ty + kSsimHalo][tx + kSsimHalo] - sY[c][ty + kSsimHalo][tx + kSsimHalo]);
+                const float2 ctr = sXY[c][ty + kSsimHalo][tx + kSsimHalo];
+                l1 += fabsf(ctr.x - ctr.y);
             }
         }
         __syncthreads();
@@ -689,8 +691,8 @@ __global__ void __launch_bounds__(256)
     k_ssim_bwd(const float4* __restrict__ pix_state, const void* __restrict__ target, const int fmt, const int W,
                const int H, const float bg_r, const float bg_g, const float bg_b, const float l1w /* w*(1-lambda)/(3HW) */,
                const float* __restrict__ maps, float4* __restrict__ v_pix) {
-    __shared__ float sD[9][kSsimS][kSsimS]; // [channel * 3 + map], all loaded in one phase
-    __shared__ float xc[kSsimS][kTile][3];
+    __shared__ float4 sD[3][kSsimS][kSsimS]; // per channel: the three derivative maps of a pixel in one 16-B record
+    __shared__ float4 xc[kSsimS][kTile];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
     const int px = x0 + tx, py = y0 + ty;
@@ -703,14 +705,16 @@ __global__ void __launch_bounds__(256)
         Yt[0] = target_at(target, fmt, npix, pi, 0), Yt[1] = target_at(target, fmt, npix, pi, 1);
         Yt[2] = target_at(target, fmt, npix, pi, 2);
     }
+    const float4* m4 = reinterpret_cast<const float4*>(maps);
     for (int t = threadIdx.x; t < kSsimS * kSsimS; t += 256) {
         const int ly = t / kSsimS, lx = t - ly * kSsimS;
         const int gy = y0 + ly - kSsimHalo, gx = x0 + lx - kSsimHalo;
         const bool in = gx >= 0 && gx < W && gy >= 0 && gy < H;
         const uint32_t i = in ? (uint32_t)gy * W + gx : 0u;
-#pragma unroll
-        for (int k = 0; k < 9; ++k)
-            sD[k][ly][lx] = in ? maps[(size_t)k * npix + i] : 0.f;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        sD[0][ly][lx] = in ? __ldg(m4 + i) : z;
+        sD[1][ly][lx] = in ? __ldg(m4 + npix + i) : z;
+        sD[2][ly][lx] = in ? __ldg(m4 + 2 * (size_t)npix + i) : z;
     }
     __syncthreads();
     float g[3] = {0.f, 0.f, 0.f};
@@ -721,11 +725,10 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
             for (int d = -kSsimHalo; d <= kSsimHalo; ++d) {
                 const float w = c_ssim_g[d + kSsimHalo];
-                a0 = fmaf(w, sD[3 * c][ly][lx + d], a0), a1 = fmaf(w, sD[3 * c + 1][ly][lx + d], a1);
-                a2 = fmaf(w, sD[3 * c + 2][ly][lx + d], a2);
+                const float4 v = sD[c][ly][lx + d];
+                a0 = fmaf(w, v.x, a0), a1 = fmaf(w, v.y, a1), a2 = fmaf(w, v.z, a2);
             }
-            float* o = xc[ly][t & 15];
-            o[0] = a0, o[1] = a1, o[2] = a2;
+            xc[ly][t & 15] = make_float4(a0, a1, a2, 0.f);
         }
         __syncthreads();
         if (inside) {
@@ -733,8 +736,8 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
             for (int d = 0; d < 2 * kSsimHalo + 1; ++d) {
                 const float w = c_ssim_g[d];
-                const float* r = xc[ty + d][tx];
-                s0 = fmaf(w, r[0], s0), s1 = fmaf(w, r[1], s1), s2 = fmaf(w, r[2], s2);
+                const float4 r = xc[ty + d][tx];
+                s0 = fmaf(w, r.x, s0), s1 = fmaf(w, r.y, s1), s2 = fmaf(w, r.z, s2);
             }
             const float bgc = c == 0 ? bg_r : (c == 1 ? bg_g : bg_b);
             const float raw = fmaf(st.w, bgc, chan(st, c));
