@@ -31,6 +31,10 @@ extern "C" int lfs_set_option(const char* name, int value) {
         lfs::raster_options().use_tma = value ? 1 : 0;
         return LFS_OK;
     }
+    if (name && std::string(name) == "fwd_variant") {
+        lfs::raster_options().fwd_variant = value;
+        return LFS_OK;
+    }
     if (name && std::string(name) == "bwd_variant") {
         lfs::raster_options().bwd_variant = value;
         return LFS_OK;

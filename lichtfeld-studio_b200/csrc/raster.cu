@@ -205,9 +205,10 @@ __device__ __forceinline__ float poly2(const float dx, const float dy, const flo
     return fmaf(dx, fmaf(dx, cxx, fmaf(dy, cxy, cx)), fmaf(dy, fmaf(dy, cyy, cy), c0));
 }
 
-template <int MODE, bool EWA> // MODE 0: register-staged InstRec, 1: TMA-staged InstRec, 2: fused expansion (GaussRec gather);
-                               // EWA: fastgs-surface records (2-D conic, D == 1), MODE 2 only
-__global__ void __launch_bounds__(kFwdThreads)
+template <int MODE, bool EWA, int MINB = 1> // MODE 0: register-staged InstRec, 1: TMA-staged InstRec, 2: fused expansion
+                                             // (GaussRec gather); EWA: fastgs-surface records (2-D conic, D == 1),
+                                             // MODE 2 only; MINB: minimum resident CTAs per SM (register cap)
+__global__ void __launch_bounds__(kFwdThreads, MINB)
     k_blend_fwd(const RasterBuffers rb, const ViewCam* __restrict__ cams, const uint32_t width, const uint32_t height, const uint32_t tile_w,
                 const uint32_t tile_h, const bool write_ckpt, const float* __restrict__ backgrounds,
                 const uint8_t* __restrict__ masks, float* __restrict__ renders, float* __restrict__ alphas,
@@ -531,7 +532,13 @@ int launch_blend_fwd(const RasterBuffers& rb, const ViewCam* cams_dev, uint32_t 
     if (C == 0 || tile_w == 0 || tile_h == 0)
         return LFS_OK;
     dim3 grid(tile_w * tile_h, C);
-    if (raster_options().fuse_expand)
+    if (raster_options().fuse_expand && raster_options().fwd_variant == 1)
+        k_blend_fwd<2, false, 10><<<grid, kFwdThreads, 0, stream>>>(rb, cams_dev, width, height, tile_w, tile_h, write_ckpt,
+                                                                   backgrounds, masks, renders, alphas, last_ids);
+    else if (raster_options().fuse_expand && raster_options().fwd_variant == 2)
+        k_blend_fwd<2, false, 12><<<grid, kFwdThreads, 0, stream>>>(rb, cams_dev, width, height, tile_w, tile_h, write_ckpt,
+                                                                   backgrounds, masks, renders, alphas, last_ids);
+    else if (raster_options().fuse_expand)
         k_blend_fwd<2, false><<<grid, kFwdThreads, 0, stream>>>(rb, cams_dev, width, height, tile_w, tile_h, write_ckpt,
                                                       backgrounds, masks, renders, alphas, last_ids);
     else if (raster_options().use_tma)

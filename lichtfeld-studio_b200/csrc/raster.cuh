@@ -65,6 +65,7 @@ struct RasterBuffers {
 // Tunables (process-wide; set through lfs_set_option).
 struct RasterOptions {
     int use_tma = 1; // stage InstRec batches with cp.async.bulk + mbarrier (1) or register-staged loads (0)
+    int fwd_variant = 0; // forward blend register cap under test (0: none, 1: 10 CTAs/SM, 2: 12 CTAs/SM)
     int bwd_variant = 0; // backward blend launch shape under test (warps per CTA / register cap), see launch_blend_bwd
     int pre_bwd_split = 1; // trainer: SH / geometry halves of the per-Gaussian backward as two launches (A/B switch)
     int exact_cull = 1; // trainer: drop (tile, Gaussian) instances that provably hold no alpha >= 1/255 (intersect.cuh CullRec)

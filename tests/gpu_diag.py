@@ -416,7 +416,7 @@ def diag_fastgs(n=3000, w=200, h=136, deg=3, seed=11, sigma_px=4.0, with_ref=Tru
     return out
 
 
-def diag_cull_lossless(n=20000, w=640, h=360, deg=1, seed=31, sigma_px=5.0):
+def diag_cull_lossless(n=20000, w=640, h=360, deg=1, seed=31, sigma_px=5.0, capacity=None):
     """Exact tile culling must not change a single bit of the forward: a culled (tile, Gaussian) instance holds no
     pixel with alpha >= 1/255, and contributing pairs keep their order."""
     sc = scene.make_scene(n, 1, w, h, deg, seed=seed, sigma_px=sigma_px)
@@ -424,9 +424,13 @@ def diag_cull_lossless(n=20000, w=640, h=360, deg=1, seed=31, sigma_px=5.0):
     imgs = []
     for cull in (0, 1):
         L.load().lfs_set_option(b"exact_cull", cull)
-        tr = SplatTrainer(n, w, h, deg, DEV, instance_capacity=40 * n)
+        tr = SplatTrainer(n, w, h, deg, DEV, instance_capacity=capacity or 40 * n)
         tr.load_scene(sc)
         img, alpha = tr.forward(sc.viewmats[0], sc.Ks[0], deg, (0.2, 0.1, 0.0), want_image=True)
+        img2, _ = tr.forward(sc.viewmats[0], sc.Ks[0], deg, (0.2, 0.1, 0.0), want_image=True)
+        out[f"deterministic_cull{cull}"] = bool(torch.equal(img, img2))
+        out[f"finite_cull{cull}"] = bool(torch.isfinite(img).all() and (alpha >= 0).all() and (alpha <= 1).all())
+        del tr
         out[f"n_inst_cull{cull}"] = tr.stats()[0]
         imgs.append((img.clone(), alpha.clone()))
     L.load().lfs_set_option(b"exact_cull", 1)

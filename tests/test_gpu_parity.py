@@ -114,6 +114,15 @@ def test_exact_tile_culling_is_lossless():
     assert r["n_inst_cull1"] < 0.95 * r["n_inst_cull0"], r  # and it does remove instances
 
 
+def test_full_size_properties_c3():
+    """BASELINE.json C3 size (1 M Gaussians, 1920x1080, SH 3), size-independent properties: the forward is deterministic,
+    finite, and exact tile culling changes the instance count but not one bit of the image."""
+    r = D.diag_cull_lossless(n=1_000_000, w=1920, h=1080, deg=3, seed=42, sigma_px=3.7, capacity=12_000_000)
+    assert r["image_bit_identical"] and r["deterministic_cull0"] and r["deterministic_cull1"], r
+    assert r["finite_cull0"] and r["finite_cull1"], r
+    assert 5_000_000 < r["n_inst_cull1"] < r["n_inst_cull0"] < 12_000_000, r
+
+
 @pytest.mark.parametrize("case", [dict(), dict(n=1500, w=120, h=100, deg=1, seed=5, sigma_px=7.0),
                                   dict(n=800, w=64, h=48, deg=0, seed=6, sigma_px=3.0)])
 def test_fastgs_forward_backward(case):
