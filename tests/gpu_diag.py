@@ -430,9 +430,10 @@ def diag_cull_lossless(n=20000, w=640, h=360, deg=1, seed=31, sigma_px=5.0, capa
         img2, _ = tr.forward(sc.viewmats[0], sc.Ks[0], deg, (0.2, 0.1, 0.0), want_image=True)
         out[f"deterministic_cull{cull}"] = bool(torch.equal(img, img2))
         out[f"finite_cull{cull}"] = bool(torch.isfinite(img).all() and (alpha >= 0).all() and (alpha <= 1).all())
-        del tr
         out[f"n_inst_cull{cull}"] = tr.stats()[0]
-        imgs.append((img.clone(), alpha.clone()))
+        imgs.append((img, alpha))
+        del tr
+        torch.cuda.empty_cache()
     L.load().lfs_set_option(b"exact_cull", 1)
     out["image_bit_identical"] = bool(torch.equal(imgs[0][0], imgs[1][0]) and torch.equal(imgs[0][1], imgs[1][1]))
     out["image_max_abs_diff"] = float((imgs[0][0] - imgs[1][0]).abs().max())

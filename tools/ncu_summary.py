@@ -15,13 +15,21 @@ rep = sys.argv[1]
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 idx = {h: i for i, h in enumerate(rows[0])}
+units = rows[1]
+# ncu picks one unit per column for the whole report: normalise time to ms and bytes to MB
+SCALE = {'nsecond': 1e-6, 'usecond': 1e-3, 'msecond': 1.0, 'second': 1e3, 'ns': 1e-6, 'us': 1e-3, 'ms': 1.0, 's': 1e3, 'byte': 1e-6, 'Kbyte': 1e-3, 'Mbyte': 1.0,
+         'Gbyte': 1e3}
 out = []
 for r in rows[2:]:
     d = {'id': r[idx['ID']], 'kernel': r[idx['Kernel Name']].split('(')[0].replace('void ', '').replace('lfs::', '')}
     for w in WANT:
         if w in idx:
-            try: d[w] = float(r[idx[w]].replace(',', ''))
-            except ValueError: d[w] = r[idx[w]]
+            try:
+                d[w] = float(r[idx[w]].replace(',', ''))
+                if w.startswith('gpu__time_duration') or w.startswith('dram__bytes'):
+                    d[w] *= SCALE.get(units[idx[w]], 1.0)
+            except ValueError:
+                d[w] = r[idx[w]]
     d['stalls'] = {}
     for s in STALLS:
         k = STALL % s
