@@ -320,9 +320,11 @@ def main():
         line = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "impl": "reference", "n_gpus": a.gpus,
                 "steps": len(vals), "warmup": 0, "ms_per_step": 1e3 / cb["value"] if cb["value"] else None,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"{a.config}: {n} Gaussians, {W}x{H}, SH degree {deg}; CPU port of the "
-                                       "reference path (no CPU implementation of the blend exists in the reference: "
-                                       "tests/test_rasterization.cpp:96-98)", "gaussians": n},
+                "config": {"workload": f"{a.config}: {n} Gaussians, {vpg} views/GPU x {max(world, 1)} GPU of {W}x{H}, "
+                                       f"SH degree {deg}, 3DGUT from-world rasterizer, L1 + fused-SSIM loss (lambda_dssim "
+                                       f"{LAMBDA_DSSIM}); CPU port of the reference path (no CPU implementation of the "
+                                       "blend exists in the reference: tests/test_rasterization.cpp:96-98)",
+                           "gaussians": n, "views_per_step": V, "width": W, "height": H, "sh_degree": deg},
                 "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0, "wall_s": round(time.time() - t_all, 1)}
