@@ -85,8 +85,8 @@ class SplatTrainer:
         self._h_grads = symm_mem.rendezvous(new_g, group)
         self.params, self.grads = new_p, new_g
         # NVSwitch multicast (NVLS) addresses of the same buffers, 0 when the fabric has none.  The in-switch variant
-        # (multimem.ld_reduce / multimem.st) is opt-in with LFS_P2P_MULTICAST=1: it is validated bit-identical on 2 GPUs
-        # (tools/check_p2p.py); the plain peer load/store kernel is the one validated on 8
+        # (multimem.ld_reduce / multimem.st) is opt-in with LFS_P2P_MULTICAST=1: it is validated on 2 and 4 GPUs
+        # (tools/check_p2p.py); the plain peer load/store kernel is the one validated on 2, 4 and 8
         self._mc_grads = int(getattr(self._h_grads, "multicast_ptr", 0) or 0)
         self._mc_params = int(getattr(self._h_params, "multicast_ptr", 0) or 0)
         if os.environ.get("LFS_P2P_MULTICAST", "0") != "1" or not (self._mc_grads and self._mc_params):
