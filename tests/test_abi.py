@@ -62,3 +62,28 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(L._lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(FileNotFoundError):
         L._lib.load()
+
+
+def test_header_is_plain_c99(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 (no C++-isms, no torch / CUDA types) and a C program
+    must link against the library and call a no-compute entry point."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "t.c"
+    src.write_text('#include "lfs_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) { printf("%d %s", lfs_abi_version(), lfs_last_error()); '
+                   'return lfs_set_option("no_such_option", 1) == LFS_ERR_INVALID_ARG ? 0 : 1; }\n')
+    inc = os.path.join(ROOT, "include")
+    r = subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    libdir = os.path.join(ROOT, "lichtfeld-studio_b200")
+    exe = tmp_path / "t"
+    r = subprocess.run([cc, "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-llfs_b200",
+                        f"-Wl,-rpath,{libdir}", "-Wl,-rpath,/usr/local/cuda/lib64"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("1 "), (r.returncode, r.stdout, r.stderr)
