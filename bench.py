@@ -510,8 +510,20 @@ def main():
                 got = [l for l in r.stdout.splitlines() if l.startswith("REFGPU ")]
                 line["reference_gpu"][which] = (json.loads(got[-1][7:]) if got
                                                 else {"error": (r.stderr or r.stdout).strip().splitlines()[-1][:300]})
+            if "error" in line["reference_gpu"].get("fastgs", {}):
+                line["reference_gpu"]["fastgs"]["note"] = (
+                    "the unmodified reference fastgs build returns garbage bucket counts above ~1e5 primitives on this "
+                    "image (profiles/r01_ref_fastgs_diagnosis.txt); it runs, and matches ours, on the small parity cases")
         except Exception as e:
             line["reference_gpu"] = {"error": repr(e)}
+        try:  # the EWA (fastgs) surface of this library on the same workload, op level (forward + backward per view)
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_fastgs.py"), a.config, "2", "2"],
+                               capture_output=True, text=True, timeout=300)
+            got = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            line["fastgs_surface"] = (json.loads(got[-1]) if got
+                                      else {"error": (r.stderr or r.stdout).strip().splitlines()[-1][:300]})
+        except Exception as e:
+            line["fastgs_surface"] = {"error": repr(e)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
