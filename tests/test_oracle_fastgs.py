@@ -79,3 +79,28 @@ def test_backward_is_gradient_of_forward():
         fd = (loss(a, cp) - loss(a, cm)) / (2 * hh)
         an = r["grad_w2c"][rr, cc_]
         assert abs(fd - an) <= 2e-4 * max(1.0, abs(fd), abs(an)), (rr, cc_, fd, an)
+
+
+def test_culling_rules_and_empty_scene():
+    """Edge cases the reference handles in preprocess_cu (kernels_forward.cuh:61-62,75,84,146,176-177,192-193):
+    behind the near plane, beyond the far plane, opacity below 1/255, degenerate quaternion, off-screen -> culled with
+    zero gradients; a scene in which everything is culled renders black with alpha 0."""
+    sc, a, c = _setup(n=40, w=48, h=40, deg=1, seed=9)
+    a = {k: v.copy() for k, v in a.items()}
+    a["opacities_raw"][0] = -20.0            # sigmoid < 1/255
+    a["rotations_raw"][1] = 1e-6             # |q|^2 < 1e-8
+    cam_dir = c["w2c"][2, :3]
+    a["means"][2] = c["cam_pos"] - 5.0 * cam_dir   # behind the camera
+    a["means"][3] = c["cam_pos"] + 1e12 * cam_dir  # beyond far = 1e10
+    a["means"][4] = c["cam_pos"] + 3.0 * cam_dir + 50.0 * c["w2c"][0, :3]  # far off-screen
+    vI, vA = np.ones((3, c["height"], c["width"])), np.zeros((1, c["height"], c["width"]))
+    r = O.fastgs(**a, **c, grad_image=vI, grad_alpha=vA, densification_info=np.zeros((2, 40)), prec=64)
+    for i in range(5):
+        assert r["n_touched"][i] == 0, i
+        assert all(np.all(g[i] == 0) for g in r["grads"].values()), i
+        assert r["densification_info"][0, i] == 0
+    assert r["n_instances"] == int(r["n_touched"].sum()) > 0
+    # everything culled
+    a["opacities_raw"][:] = -20.0
+    r = O.fastgs(**a, **c, prec=64)
+    assert r["n_instances"] == 0 and np.all(r["image"] == 0) and np.all(r["alpha"] == 0)
