@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define LFS_ABI_VERSION 1
+#define LFS_ABI_VERSION 2
 
 typedef enum lfs_status {
     LFS_OK = 0,
@@ -165,17 +165,30 @@ int lfs_adam_step(float* param, float* exp_avg, float* exp_avg_sq, const float* 
  * the same pass (the reference's zero_grad(set_to_none) + torch::zeros of the next backward).
  * seg_begin_host [n_segments+1], lr_host/bc1_rcp_host/bc2_sqrt_rcp_host [n_segments] are HOST arrays,
  * n_segments <= 16. */
+/* Optional regularisers folded into the update (no extra pass over the parameters): the mcmc configuration adds
+ * scale_reg * mean(exp(scaling_raw)) and opacity_reg * mean(sigmoid(opacity_raw)) to the loss of every iteration
+ * (src/training/trainer.cpp:132-158).  Their gradients depend on the parameter alone, so segment s adds
+ *   kind 1: coef * exp(p)        kind 2: coef * sigmoid(p) * (1 - sigmoid(p))        kind 0: nothing
+ * to the (summed) gradient of every element before the Adam update; coef = weight * n_views / n_elements_of_the_mean.
+ * Planar arenas pad every plane to plane_elems floats: only the first n_valid elements of a plane are regularised. */
+typedef struct lfs_adam_reg {
+    int kind[16];
+    float coef[16];
+    int64_t plane_elems;
+    int64_t n_valid;
+} lfs_adam_reg;
 int lfs_adam_step_multi(float* params, float* exp_avg, float* exp_avg_sq, float* grads, int n_segments,
                         const int64_t* seg_begin_host, const float* lr_host, const float* bc1_rcp_host,
                         const float* bc2_sqrt_rcp_host, float beta1, float beta2, float eps, int zero_grad,
-                        void* stream);
+                        const lfs_adam_reg* reg /* or NULL */, void* stream);
 
 /* Multi-GPU form of lfs_adam_step_multi: reduce-scatter + Adam + all-gather fused in one kernel over
  * NVLink peer memory, replacing ncclAllReduce(gradient arena) + a full Adam on every rank.  grads_peers_dev /
  * params_peers_dev are DEVICE arrays of `world` pointers to every rank's (peer-mapped) gradient / parameter arena, e.g.
- * torch.distributed._symmetric_memory buffer_ptrs_dev; exp_avg / exp_avg_sq are this rank's.  This rank reduces and
- * updates slice `rank` of [seg_begin[0], seg_begin[n]) (split evenly in 16-byte units), writes the new parameters to all
- * ranks.  When grads_multicast / params_multicast (NVSwitch multicast addresses of the same buffers, e.g. symmetric
+ * torch.distributed._symmetric_memory buffer_ptrs_dev; exp_avg / exp_avg_sq are this rank's.  Ownership is fixed per
+ * arena element: 16-byte unit i (absolute, from the start of the arena) belongs to rank (i / 1024) % world, whatever
+ * segments a call covers -- a rank holds valid Adam moments only for the elements it owns, and it reduces, updates and
+ * broadcasts exactly those of [seg_begin[0], seg_begin[n]).  When grads_multicast / params_multicast (NVSwitch multicast addresses of the same buffers, e.g. symmetric
  * memory multicast_ptr; NULL if unsupported) are given, the reduction happens inside the switch (multimem.ld_reduce) and
  * the parameters are broadcast with one multimem.st; params_local is then this rank's own arena.  The caller issues a
  * stream-ordered barrier over all ranks before (all backward passes finished) and after (all parameter writes landed)
@@ -184,7 +197,13 @@ int lfs_adam_step_multi_p2p(float* exp_avg, float* exp_avg_sq, const void* grads
                             const float* grads_multicast, float* params_multicast, float* params_local, int world,
                             int rank, int n_segments, const int64_t* seg_begin_host, const float* lr_host,
                             const float* bc1_rcp_host, const float* bc2_sqrt_rcp_host, float beta1, float beta2,
-                            float eps, void* stream);
+                            float eps, const lfs_adam_reg* reg /* or NULL */, void* stream);
+/* Ownership rule of lfs_adam_step_multi_p2p, host-only (no CUDA call): the rank that keeps the Adam moments of the arena
+ * element `float_index`, and the chunks (each *chunk_floats floats long, chunk c covering floats [c*chunk_floats, ...))
+ * of [begin_float, end_float) that `rank` owns: first_chunk, first_chunk + world, ... (n_chunks of them). */
+int lfs_adam_p2p_owner(int64_t float_index, int world);
+int lfs_adam_p2p_owned_chunks(int64_t begin_float, int64_t end_float, int world, int rank, int64_t* first_chunk,
+                              int64_t* n_chunks, int64_t* chunk_floats);
 
 /* ---------------------------------------------------------------------------------------------------------
  * small per-Gaussian ops of the densification strategies (off the steady-state hot path)
@@ -302,6 +321,16 @@ int lfs_trainer_view_set_grad(void* trainer, const float* v_image, const float* 
 int lfs_trainer_view_backward(void* trainer, const float* params_arena, float* grads_arena, void* stream);
 /* blocks on `stream`; returns LFS_ERR_CAPACITY if the last forward overflowed instance_capacity */
 int lfs_trainer_stats(void* trainer, uint64_t* n_instances, uint64_t* n_buckets, void* stream);
+/* Non-blocking overflow check for training loops: every forward records the largest instance count any view has needed
+ * so far and copies it to pinned host memory; this call only reads that word.  Returns LFS_ERR_CAPACITY as soon as a view
+ * whose instances did not fit (its farthest instances were dropped) has been observed -- call it once per step. */
+int lfs_trainer_poll_capacity(void* trainer, uint64_t* max_instances_seen /* or NULL */);
+/* Diagnostics / tests: copies one internal per-view buffer of the last forward into a caller DEVICE buffer (async on
+ * `stream`; at most dst_bytes).  which: 0 tile_off int32[n_tiles+1] | 1 n_contrib int32[H*W] | 2 pix_state float4[H*W]
+ * (rgb before background, T) | 3 sorted instance -> Gaussian id uint32[n_instances] | 4 sorted instance tile keys
+ * uint32[n_instances] | 5 bucket_off uint32[n_tiles+1] | 6 tile_max_contrib uint32[n_tiles].  Returns the number of bytes
+ * of the full buffer through *full_bytes (may be NULL). */
+int lfs_trainer_debug_copy(void* trainer, int which, void* dst, uint64_t dst_bytes, uint64_t* full_bytes, void* stream);
 
 /* Per-stage device timing of the view step with CUDA events on the launching stream (bench.py roofline).
  * Stages: 0 preprocess_fwd | 1 depth sort + scan + emit + tile sort + offsets | 2 bucket offsets + expand |

@@ -14,6 +14,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "liblfs_b200.so")
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 
+ABI_VERSION = 2  # LFS_ABI_VERSION of include/lfs_b200.h
 LFS_OK = 0
 LFS_ERR_UNSUPPORTED = -2
 LFS_ERR_CAPACITY = -5
@@ -66,6 +67,12 @@ class TrainerDesc(C.Structure):
     ]
 
 
+class AdamReg(C.Structure):
+    """lfs_adam_reg: regulariser gradients folded into the Adam step (include/lfs_b200.h)."""
+
+    _fields_ = [("kind", C.c_int * 16), ("coef", C.c_float * 16), ("plane_elems", C.c_int64), ("n_valid", C.c_int64)]
+
+
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_int, C.c_size_t)
 
 _vp, _u32, _i32, _i64, _f, _sz = C.c_void_p, C.c_uint32, C.c_int32, C.c_int64, C.c_float, C.c_size_t
@@ -111,9 +118,10 @@ SIGNATURES = {
     "lfs_adam_step_multi": (
         C.c_int,
         [_vp, _vp, _vp, _vp, C.c_int, C.POINTER(_i64), C.POINTER(_f), C.POINTER(_f), C.POINTER(_f), _f, _f, _f,
-         C.c_int, _vp],
+         C.c_int, C.POINTER(AdamReg), _vp],
     ),
-    "lfs_adam_step_multi_p2p": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _f, _f, _f, _vp]),
+    "lfs_adam_step_multi_p2p": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp,
+                                          _f, _f, _f, C.POINTER(AdamReg), _vp]),
     "lfs_quats_to_rotmats": (C.c_int, [_vp, _u32, _vp, _vp]),
     "lfs_relocation": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _u32, _vp, _vp, _vp]),
     "lfs_add_noise": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _f, _u32, _vp]),
@@ -132,6 +140,11 @@ SIGNATURES = {
     "lfs_trainer_set_profile": (C.c_int, [_vp, C.c_int]),
     "lfs_trainer_get_profile": (C.c_int, [_vp, C.POINTER(_f), C.POINTER(C.c_int)]),
     "lfs_trainer_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), _vp]),
+    "lfs_adam_p2p_owner": (C.c_int, [C.c_int64, C.c_int]),
+    "lfs_adam_p2p_owned_chunks": (C.c_int, [C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64),
+                                            C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "lfs_trainer_poll_capacity": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
+    "lfs_trainer_debug_copy": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64, C.POINTER(C.c_uint64), _vp]),
 }
 
 _lib = None
@@ -164,7 +177,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if lib.lfs_abi_version() != 1:
+        if lib.lfs_abi_version() != ABI_VERSION:
             raise RuntimeError("lfs_b200 ABI version mismatch")
         # tuning switches for A/B measurements, e.g. LFS_OPTIONS="blend_fused=0,blend_tma=1" (see lfs_set_option)
         for item in filter(None, os.environ.get("LFS_OPTIONS", "").split(",")):

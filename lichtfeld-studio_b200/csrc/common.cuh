@@ -44,7 +44,7 @@ void count_launch(int n = 1);
 
 static inline unsigned div_up(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
 static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
-constexpr int kNumSMs = 148;     // B200
+int num_sms();                   // SM count of the current device (queried once per device; 148 on B200)
 constexpr int kTile = 16;        // tile edge in pixels (reference constant, rasterizer.cpp:180)
 constexpr int kTilePix = kTile * kTile;
 constexpr int kBucket = 32;      // gaussians per backward bucket (one warp)

@@ -548,7 +548,7 @@ extern "C" int lfs_fastgs_forward(const float* means, const float* scales_raw, c
     in_b = 0;
     if (n_inst > 0) {
         const unsigned want = div_up(N, 256);
-        const unsigned grid = want < (unsigned)(kNumSMs * 16) ? want : (unsigned)(kNumSMs * 16);
+        const unsigned grid = want < (unsigned)(num_sms() * 16) ? want : (unsigned)(num_sms() * 16);
         k_fg_emit<<<grid, 256, 0, stream>>>(perm, P.off, N, P.rects, P.counts, P.gauss, tile_w, n_inst, I.tk_a, I.tv_a);
         LFS_LAUNCH_OK("k_fg_emit");
         rc = radix_sort_pairs(I.tk_a, I.tv_a, I.tk_b, I.tv_b, n_inst, nullptr, 0, tile_key_bits(n_tiles), I.sort_scr, &in_b,

@@ -96,7 +96,7 @@ int launch_emit_instances(const uint32_t* perm, const uint32_t* off, uint32_t n_
     if (n_cap == 0 || n_gauss == 0)
         return LFS_OK;
     const unsigned want = div_up(n_gauss, kIsThreads);
-    const unsigned grid = want < (unsigned)(kNumSMs * 16) ? want : (unsigned)(kNumSMs * 16);
+    const unsigned grid = want < (unsigned)(num_sms() * 16) ? want : (unsigned)(num_sms() * 16);
     k_emit_instances<<<grid, kIsThreads, 0, stream>>>(perm, off, n_gauss, rects, tile_w, id_offset, n_cap, n_dev,
                                                       tile_keys, vals);
     LFS_LAUNCH_OK("k_emit_instances");
@@ -145,7 +145,7 @@ int launch_emit_instances_cull(const uint32_t* perm, const uint32_t* off, uint32
     if (n_cap == 0 || n_gauss == 0)
         return LFS_OK;
     const unsigned want = div_up(n_gauss, kIsThreads);
-    const unsigned grid = want < (unsigned)(kNumSMs * 16) ? want : (unsigned)(kNumSMs * 16);
+    const unsigned grid = want < (unsigned)(num_sms() * 16) ? want : (unsigned)(num_sms() * 16);
     k_emit_instances_cull<<<grid, kIsThreads, 0, stream>>>(perm, off, n_gauss, rects, counts, cull, tile_w, n_cap, n_dev,
                                                            tile_keys, vals);
     LFS_LAUNCH_OK("k_emit_instances_cull");
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(kIsThreads)
 int launch_tile_offsets(const uint32_t* sorted_tile_keys, uint32_t n_cap, const uint32_t* n_dev, uint32_t n_tiles,
                         int32_t* offsets, cudaStream_t stream) {
     const unsigned want = div_up(n_cap > n_tiles + 1 ? n_cap : n_tiles + 1, kIsThreads);
-    const unsigned grid = want < (unsigned)(kNumSMs * 16) ? want : (unsigned)(kNumSMs * 16);
+    const unsigned grid = want < (unsigned)(num_sms() * 16) ? want : (unsigned)(num_sms() * 16);
     k_tile_offsets<<<grid, kIsThreads, 0, stream>>>(sorted_tile_keys, n_cap, n_dev, n_tiles, offsets);
     LFS_LAUNCH_OK("k_tile_offsets");
     return LFS_OK;
@@ -314,7 +314,7 @@ extern "C" int lfs_intersect_tile(const float* means2d, const int32_t* radii, co
             return LFS_ERR_ALLOC;
         }
         const unsigned want = div_up(total, kIsThreads);
-        const unsigned grid = want < (unsigned)(kNumSMs * 16) ? want : (unsigned)(kNumSMs * 16);
+        const unsigned grid = want < (unsigned)(num_sms() * 16) ? want : (unsigned)(num_sms() * 16);
         k_emit_unsorted<<<grid, kIsThreads, 0, stream>>>(off, n, N, rects, depths, tile_width, tnb, total, ids, flat);
         LFS_LAUNCH_OK("k_emit_unsorted");
         *isect_ids = ids;

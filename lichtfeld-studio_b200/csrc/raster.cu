@@ -123,7 +123,7 @@ int launch_expand_instances(const RasterBuffers& rb, const ViewCam* cams_dev, ui
     if (n_inst_cap == 0)
         return LFS_OK;
     const unsigned want = div_up(n_inst_cap, kExThreads);
-    const unsigned grid = want < (unsigned)(kNumSMs * 32) ? want : (unsigned)(kNumSMs * 32);
+    const unsigned grid = want < (unsigned)(num_sms() * 32) ? want : (unsigned)(num_sms() * 32);
     k_expand_instances<<<grid, kExThreads, 0, stream>>>(rb.gauss, rb.inst_gid, rb.tile_off, sorted_tile_keys, cams_dev,
                                                         n_tiles_per_cam, tile_w, C, n_inst_cap, n_inst_dev, rb.inst);
     LFS_LAUNCH_OK("k_expand_instances");

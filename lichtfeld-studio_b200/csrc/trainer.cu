@@ -45,7 +45,7 @@ struct Trainer {
     CullRec* cull;
     int32_t* counts;
     uint32_t *dk_a, *dk_b, *pm_a, *pm_b, *off;
-    uint32_t* n_inst; // [4] device counters: n_inst, n_buckets, overflow flag
+    uint32_t* n_inst; // [4] device counters: n_inst, n_buckets, high-water mark of n_inst since creation
     uint32_t *tk_a, *tk_b, *tv_a, *tv_b;
     int32_t* tile_off;
     uint32_t *bucket_off, *bucket_counts, *bucket_tile, *tile_max;
@@ -812,6 +812,12 @@ __global__ void __launch_bounds__(256)
         alpha[i] = 1.0f - s.w;
 }
 
+// n_inst[2] = max over all forwards of the instance count the view WANTED (n_inst[0], may exceed the capacity)
+__global__ void k_high_water(uint32_t* __restrict__ n_inst) {
+    if (n_inst[0] > n_inst[2])
+        n_inst[2] = n_inst[0];
+}
+
 } // namespace lfs
 
 // ==========================================================================================================
@@ -864,6 +870,8 @@ extern "C" void* lfs_trainer_create(const lfs_trainer_desc* d) {
     cudaMemset(t->n_inst, 0, sizeof(uint32_t) * 4);
     if (cudaMallocHost(&t->stats_host, sizeof(uint32_t) * 4) != cudaSuccess)
         t->stats_host = nullptr;
+    else
+        t->stats_host[0] = t->stats_host[1] = t->stats_host[2] = t->stats_host[3] = 0;
     return t;
 }
 
@@ -934,6 +942,8 @@ extern "C" int lfs_trainer_view_forward(void* h, const float* params_arena, cons
                             t->scan_scr, stream);
     if (rc)
         return rc;
+    k_high_water<<<1, 1, 0, stream>>>(t->n_inst);
+    LFS_LAUNCH_OK("k_high_water");
     if (exact_cull)
         rc = launch_emit_instances_cull(perm, t->off, N, t->rects, t->counts, t->cull, t->tile_w, t->inst_cap, t->n_inst,
                                         t->tk_a, t->tv_a, stream);
@@ -986,7 +996,7 @@ extern "C" int lfs_trainer_view_forward(void* h, const float* params_arena, cons
         LFS_LAUNCH_OK("k_export_image");
     }
     if (t->stats_host)
-        LFS_CUDA_OK(cudaMemcpyAsync(t->stats_host, t->n_inst, sizeof(uint32_t) * 2, cudaMemcpyDeviceToHost, stream));
+        LFS_CUDA_OK(cudaMemcpyAsync(t->stats_host, t->n_inst, sizeof(uint32_t) * 3, cudaMemcpyDeviceToHost, stream));
     return LFS_OK;
 }
 
@@ -996,7 +1006,7 @@ extern "C" int lfs_trainer_view_loss_l1(void* h, const void* target, int target_
     cudaStream_t stream = (cudaStream_t)stream_;
     LFS_CHECK_ARG(t && target, "trainer_view_loss_l1: null pointer");
     LFS_CHECK_ARG(target_format >= 0 && target_format <= 2, "trainer_view_loss_l1: bad target format");
-    const unsigned grid = t->n_tiles < (unsigned)(kNumSMs * 8) ? t->n_tiles : (unsigned)(kNumSMs * 8);
+    const unsigned grid = t->n_tiles < (unsigned)(num_sms() * 8) ? t->n_tiles : (unsigned)(num_sms() * 8);
     k_loss_l1<<<grid, 256, 0, stream>>>(t->pix_state, target, target_format, t->d.width, t->d.height, t->bg[0], t->bg[1],
                                         t->bg[2], scale, t->v_pix, t->loss_partials);
     LFS_LAUNCH_OK("k_loss_l1");
@@ -1131,6 +1141,54 @@ extern "C" int lfs_trainer_get_profile(void* h, float* mean_ms, int* counts) {
         if (counts)
             counts[i] = t->acc_n[i];
     }
+    return LFS_OK;
+}
+
+// Non-blocking: looks at the high-water mark the forwards copy to pinned host memory.  It only ever grows, so a view that
+// overflowed is reported by every later call once its copy has completed (at the latest after the next synchronisation).
+extern "C" int lfs_trainer_poll_capacity(void* h, uint64_t* max_instances_seen) {
+    Trainer* t = static_cast<Trainer*>(h);
+    LFS_CHECK_ARG(t, "trainer_poll_capacity: null handle");
+    const uint32_t hw = t->stats_host ? *const_cast<volatile uint32_t*>(t->stats_host + 2) : 0u;
+    if (max_instances_seen)
+        *max_instances_seen = hw;
+    if (hw > t->inst_cap) {
+        set_error("trainer: a view needed %u tile instances, capacity is %u: its farthest instances were dropped; "
+                  "recreate the trainer with a larger instance_capacity", hw, t->inst_cap);
+        return LFS_ERR_CAPACITY;
+    }
+    return LFS_OK;
+}
+
+extern "C" int lfs_trainer_debug_copy(void* h, int which, void* dst, uint64_t dst_bytes, uint64_t* full_bytes,
+                                      void* stream_) {
+    Trainer* t = static_cast<Trainer*>(h);
+    LFS_CHECK_ARG(t, "trainer_debug_copy: null handle");
+    const uint64_t npix = (uint64_t)t->d.width * t->d.height;
+    uint32_t n_inst = 0;
+    if (which == 3 || which == 4) {
+        LFS_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream_));
+        LFS_CUDA_OK(cudaMemcpy(&n_inst, t->n_inst, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        n_inst = n_inst < t->inst_cap ? n_inst : t->inst_cap;
+    }
+    const void* src = nullptr;
+    uint64_t bytes = 0;
+    switch (which) {
+    case 0: src = t->tile_off, bytes = 4ull * (t->n_tiles + 1); break;
+    case 1: src = t->n_contrib, bytes = 4ull * npix; break;
+    case 2: src = t->pix_state, bytes = 16ull * npix; break;
+    case 3: src = t->sorted_vals, bytes = 4ull * n_inst; break;
+    case 4: src = t->sorted_keys, bytes = 4ull * n_inst; break;
+    case 5: src = t->bucket_off, bytes = 4ull * (t->n_tiles + 1); break;
+    case 6: src = t->tile_max, bytes = 4ull * t->n_tiles; break;
+    default: LFS_CHECK_ARG(false, "trainer_debug_copy: unknown buffer %d", which);
+    }
+    LFS_CHECK_ARG(src != nullptr, "trainer_debug_copy: no forward has been run");
+    if (full_bytes)
+        *full_bytes = bytes;
+    const uint64_t n = bytes < dst_bytes ? bytes : dst_bytes;
+    if (dst && n)
+        LFS_CUDA_OK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream_));
     return LFS_OK;
 }
 

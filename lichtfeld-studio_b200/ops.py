@@ -30,7 +30,24 @@ def _p(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 def _stream() -> int:
+    """Current torch stream of the CURRENT device; every op runs under _on_tensor_device, which makes the device of its
+    first tensor argument current (the reference's ops do the same with a DEVICE_GUARD, gsplat/Common.h:18-19)."""
     return torch.cuda.current_stream().cuda_stream
+
+
+def _on_tensor_device(fn):
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = next((a.device for a in list(args) + list(kwargs.values()) if isinstance(a, torch.Tensor) and a.is_cuda),
+                   None)
+        if dev is None:
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+
+    return wrapper
 
 
 class _Alloc:
@@ -57,6 +74,7 @@ class _Alloc:
         return t[off:off + nbytes].view(dtype)[:numel]
 
 
+@_on_tensor_device
 def projection_ut_3dgs_fused(means, quats, scales, opacities, viewmats0, viewmats1, Ks, image_width, image_height,
                              eps2d, near_plane, far_plane, radius_clip, calc_compensations, camera_model=PINHOLE,
                              ut_params: Optional[UTParams] = None, rs_type=SHUTTER_GLOBAL, radial_coeffs=None,
@@ -82,6 +100,7 @@ def projection_ut_3dgs_fused(means, quats, scales, opacities, viewmats0, viewmat
     return radii, means2d, depths, conics, comp
 
 
+@_on_tensor_device
 def spherical_harmonics_fwd(degrees_to_use: int, dirs, coeffs, masks=None):
     """gsplat::spherical_harmonics_fwd (gsplat/Ops.h:12-17). dirs [...,3], coeffs [...,K,3] -> colors [...,3]."""
     lib = load()
@@ -98,6 +117,7 @@ def spherical_harmonics_fwd(degrees_to_use: int, dirs, coeffs, masks=None):
     return colors
 
 
+@_on_tensor_device
 def spherical_harmonics_bwd(K: int, degrees_to_use: int, dirs, coeffs, masks, v_colors, compute_v_dirs: bool):
     """gsplat::spherical_harmonics_bwd (gsplat/Ops.h:18-25) -> (v_coeffs, v_dirs or None)."""
     lib = load()
@@ -114,6 +134,7 @@ def spherical_harmonics_bwd(K: int, degrees_to_use: int, dirs, coeffs, masks, v_
     return v_coeffs, v_dirs
 
 
+@_on_tensor_device
 def intersect_tile(means2d, radii, depths, camera_ids, gaussian_ids, C_: int, tile_size: int, tile_width: int,
                    tile_height: int, sort: bool = True):
     """gsplat::intersect_tile (gsplat/Ops.h:28-38) -> (tiles_per_gauss, isect_ids, flatten_ids)."""
@@ -135,7 +156,7 @@ def intersect_tile(means2d, radii, depths, camera_ids, gaussian_ids, C_: int, ti
                 torch.empty((0,), dtype=torch.int32, device=dev))
     isect_ids = al.tensor(_lib_tag("ISECT"), torch.int64, n)
     flatten_ids = al.tensor(_lib_tag("FLAT"), torch.int32, n)
-    torch.cuda.current_stream().synchronize()  # scratch (tag 0) is dropped when `al` dies
+    # scratch (tag 0) is dropped when `al` dies: the caching allocator frees it in stream order, no host sync needed
     return tiles_per_gauss, isect_ids, flatten_ids
 
 
@@ -143,6 +164,7 @@ def _lib_tag(name: str) -> int:
     return {"SCRATCH": 0, "ISECT": 1, "FLAT": 2}[name]
 
 
+@_on_tensor_device
 def intersect_offset(isect_ids, C_: int, tile_width: int, tile_height: int):
     """gsplat::intersect_offset (gsplat/Ops.h:39-43) -> offsets [C, tile_height, tile_width] int32."""
     lib = load()
@@ -153,6 +175,7 @@ def intersect_offset(isect_ids, C_: int, tile_width: int, tile_height: int):
     return offsets
 
 
+@_on_tensor_device
 def rasterize_to_pixels_from_world_3dgs_fwd(means, quats, scales, colors, opacities, backgrounds, masks,
                                             image_width, image_height, tile_size, viewmats0, viewmats1, Ks,
                                             camera_model=PINHOLE, ut_params: Optional[UTParams] = None,
@@ -182,10 +205,10 @@ def rasterize_to_pixels_from_world_3dgs_fwd(means, quats, scales, colors, opacit
         image_height, tile_size, _p(viewmats0), _p(viewmats1), _p(Ks), camera_model, C.byref(ut), rs_type,
         _p(radial_coeffs), _p(tangential_coeffs), _p(thin_prism_coeffs), _p(tile_offsets), _p(flatten_ids),
         flatten_ids.numel(), al.cb, None, _p(renders), _p(alphas), _p(last_ids), _stream()))
-    torch.cuda.current_stream().synchronize()
     return renders, alphas, last_ids
 
 
+@_on_tensor_device
 def rasterize_to_pixels_from_world_3dgs_bwd(means, quats, scales, colors, opacities, backgrounds, masks,
                                             image_width, image_height, tile_size, viewmats0, viewmats1, Ks,
                                             camera_model=PINHOLE, ut_params: Optional[UTParams] = None,
@@ -223,10 +246,10 @@ def rasterize_to_pixels_from_world_3dgs_bwd(means, quats, scales, colors, opacit
         _p(radial_coeffs), _p(tangential_coeffs), _p(thin_prism_coeffs), _p(tile_offsets), _p(flatten_ids),
         flatten_ids.numel(), _p(render_alphas), _p(last_ids), _p(v_render_colors), _p(v_render_alphas), al.cb, None,
         _p(v_means), _p(v_quats), _p(v_scales), _p(v_colors), _p(v_opacities), _stream()))
-    torch.cuda.current_stream().synchronize()
     return v_means, v_quats, v_scales, v_colors, v_opacities
 
 
+@_on_tensor_device
 def adam_step(param, exp_avg, exp_avg_sq, param_grad, lr, beta1, beta2, eps, bias_correction1_rcp,
               bias_correction2_sqrt_rcp):
     """fast_gs::optimizer::adam_step_wrapper (fastgs/optimizer/include/adam_api.h:11-21); in place."""
@@ -237,6 +260,7 @@ def adam_step(param, exp_avg, exp_avg_sq, param_grad, lr, beta1, beta2, eps, bia
                             eps, bias_correction1_rcp, bias_correction2_sqrt_rcp, _stream()))
 
 
+@_on_tensor_device
 def quats_to_rotmats(quats):
     """gsplat::quats_to_rotmats (gsplat/Ops.h:46-48): [N,4] -> [N,3,3]."""
     lib = load()
@@ -246,6 +270,7 @@ def quats_to_rotmats(quats):
     return out
 
 
+@_on_tensor_device
 def relocation(opacities, scales, ratios, binoms, n_max: int):
     """gsplat::relocation (gsplat/Ops.h:52-57) -> (new_opacities [N], new_scales [N,3])."""
     lib = load()
@@ -256,6 +281,7 @@ def relocation(opacities, scales, ratios, binoms, n_max: int):
     return new_op, new_sc
 
 
+@_on_tensor_device
 def add_noise(raw_opacities, raw_scales, raw_quats, noise, means, current_lr: float) -> None:
     """gsplat::add_noise (gsplat/Ops.h:59-65); means updated in place."""
     lib = load()
@@ -281,6 +307,7 @@ class FastGSContext:
         return t.data_ptr() + off
 
 
+@_on_tensor_device
 def fastgs_forward(means, scales_raw, rotations_raw, opacities_raw, sh_coefficients_0, sh_coefficients_rest, w2c,
                    cam_position, active_sh_bases: int, width: int, height: int, focal_x: float, focal_y: float,
                    center_x: float, center_y: float, near_plane: float, far_plane: float):
@@ -309,6 +336,7 @@ def fastgs_forward(means, scales_raw, rotations_raw, opacities_raw, sh_coefficie
     return image, alpha, ctx
 
 
+@_on_tensor_device
 def fastgs_backward(ctx: FastGSContext, grad_image, grad_alpha, means, scales_raw, rotations_raw, sh_coefficients_rest,
                     w2c, cam_position, densification_info=None, want_w2c_grad: bool = False):
     """fast_gs::rasterization::backward_wrapper (rasterization_api.h:46-75) -> (grad_means, grad_scales_raw,

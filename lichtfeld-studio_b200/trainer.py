@@ -33,7 +33,8 @@ def default_lrs(scene_scale: float = 1.0) -> dict:
 class SplatTrainer:
     def __init__(self, n_gaussians: int, width: int, height: int, sh_degree_max: int = 3, device="cuda:0",
                  instance_capacity: int = 0, lrs: Optional[dict] = None, betas=(0.9, 0.999), eps: float = 1e-15,
-                 iterations: int = 30000, eps2d=0.3, near_plane=0.01, far_plane=1e4, radius_clip=0.0):
+                 iterations: int = 30000, eps2d=0.3, near_plane=0.01, far_plane=1e4, radius_clip=0.0,
+                 scale_reg: float = 0.0, opacity_reg: float = 0.0):
         self.lib = load()
         self.device = torch.device(device)
         self.N, self.W, self.H, self.deg_max = n_gaussians, width, height, sh_degree_max
@@ -41,10 +42,8 @@ class SplatTrainer:
         self.Np = (n_gaussians + 3) // 4 * 4
         self.desc = TrainerDesc(n_gaussians, sh_degree_max, width, height, eps2d, near_plane, far_plane, radius_clip,
                                 UTParams.default(), instance_capacity)
-        with torch.cuda.device(self.device):
-            self.h = self.lib.lfs_trainer_create(C.byref(self.desc))
-        if not self.h:
-            raise _lib.LfsError(-4, self.lib.lfs_last_error().decode())
+        self.h = None
+        self._create_handle()
         n_floats = int(self.lib.lfs_trainer_arena_floats(C.byref(self.desc)))
         assert n_floats == (11 + 3 * self.K) * self.Np
         mk = lambda: torch.zeros(n_floats, dtype=torch.float32, device=self.device)
@@ -57,6 +56,10 @@ class SplatTrainer:
             self.seg_begin.append(self.seg_begin[-1] + p * self.Np)
         self.lrs = dict(lrs or default_lrs())
         self.betas, self.eps = betas, eps
+        # mcmc regularisers (eval/mcmc_optimization_params.json: 0.01 each; src/training/trainer.cpp:132-158), folded into
+        # the Adam step; _views_since_step counts the views whose loss they belong to (the reference adds them per view)
+        self.scale_reg, self.opacity_reg = float(scale_reg), float(opacity_reg)
+        self._views_since_step = 0
         self.step_count = [0] * 6
         self.iteration = 0
         self.means_gamma = math.pow(0.01, 1.0 / iterations)  # strategy_utils.cpp:47-55 (means group only)
@@ -66,6 +69,46 @@ class SplatTrainer:
         self._tgt_free = [torch.cuda.Event() for _ in range(2)]
         self._loss_pinned = torch.zeros(1, dtype=torch.float32).pin_memory()
         self.p2p = False
+
+    def _create_handle(self) -> None:
+        old, self.h = self.h, None
+        if old:
+            self.lib.lfs_trainer_destroy(old)
+        with torch.cuda.device(self.device):
+            self.h = self.lib.lfs_trainer_create(C.byref(self.desc))
+        if not self.h:
+            raise _lib.LfsError(-4, self.lib.lfs_last_error().decode())
+
+    # ---- instance capacity (tile-Gaussian pairs per view) ---------------------------------------------------------
+    @property
+    def instance_capacity(self) -> int:
+        return int(self.lib.lfs_trainer_instance_capacity(self.h))
+
+    def poll_capacity(self) -> int:
+        """Non-blocking: raises LfsError(LFS_ERR_CAPACITY) once a view whose tile instances did not fit has been seen
+        (lfs_trainer_poll_capacity).  forward() / train_step() call it, so an overflow never goes unnoticed for more than
+        one step.  Returns the largest per-view instance count observed so far."""
+        hw = C.c_uint64(0)
+        check(self.lib.lfs_trainer_poll_capacity(self.h, C.byref(hw)))
+        return int(hw.value)
+
+    def ensure_capacity(self, viewmats, Ks, active_sh_degree: Optional[int] = None, headroom: float = 1.25) -> int:
+        """Blocking calibration (outside any timed region): renders the given views once, and if one of them needs more
+        tile instances than the scratch holds -- or the scratch is more than twice too large -- re-creates the per-view
+        scratch with `headroom` x the largest need.  Parameters / optimiser state live in torch tensors and survive."""
+        need = 0
+        for vm, K in zip(viewmats, Ks):
+            self._forward_unchecked(vm, K, active_sh_degree)
+            n_inst, n_b = C.c_uint64(0), C.c_uint64(0)
+            self.lib.lfs_trainer_stats(self.h, C.byref(n_inst), C.byref(n_b), self._stream())  # overflow is expected here
+            need = max(need, int(n_inst.value))
+        cap = self.instance_capacity
+        if need > cap or cap > 2 * need + (1 << 20):
+            self.desc.instance_capacity = int(need * headroom) + (1 << 16)
+            torch.cuda.current_stream(self.device).synchronize()
+            self._create_handle()
+            torch.cuda.empty_cache()
+        return need
 
     # ---- multi-GPU: peer-mapped arenas for the fused reduce-scatter + Adam + all-gather step -----------------------
     def enable_p2p(self, group=None) -> None:
@@ -135,6 +178,11 @@ class SplatTrainer:
     # ---- one view ----------------------------------------------------------------------------------------
     def forward(self, viewmat: np.ndarray, K: np.ndarray, active_sh_degree: Optional[int] = None,
                 bg: Sequence[float] = (0.0, 0.0, 0.0), want_image: bool = False):
+        self.poll_capacity()
+        return self._forward_unchecked(viewmat, K, active_sh_degree, bg, want_image)
+
+    def _forward_unchecked(self, viewmat: np.ndarray, K: np.ndarray, active_sh_degree: Optional[int] = None,
+                           bg: Sequence[float] = (0.0, 0.0, 0.0), want_image: bool = False):
         vm = np.ascontiguousarray(viewmat, dtype=np.float32).reshape(16)
         kk = np.ascontiguousarray(K, dtype=np.float32).reshape(9)
         bgc = (C.c_float * 3)(*[float(b) for b in bg])
@@ -168,6 +216,7 @@ class SplatTrainer:
     def backward(self) -> None:
         check(self.lib.lfs_trainer_view_backward(self.h, self.params.data_ptr(), self.grads.data_ptr(),
                                                  self._stream()))
+        self._views_since_step += 1
 
     def stats(self):
         n_inst, n_b = C.c_uint64(0), C.c_uint64(0)
@@ -186,8 +235,29 @@ class SplatTrainer:
         return {k: float(ms[i]) for i, k in enumerate(self.PROF_STAGES)}
 
     # ---- optimiser (FusedAdam::step mirror) -----------------------------------------------------------------
-    def adam_step(self) -> None:
+    def _adam_reg(self, run, n_views: int):
+        """lfs_adam_reg for one run of consecutive groups: d/dp of scale_reg * mean(exp(scaling_raw)) and
+        opacity_reg * mean(sigmoid(opacity_raw)), once per view of the (global) batch."""
+        if (self.scale_reg == 0.0 and self.opacity_reg == 0.0) or n_views == 0:
+            return None
+        reg = _lib.AdamReg()
+        reg.plane_elems, reg.n_valid = self.Np, self.N
+        used = False
+        for k, g in enumerate(run):
+            name = GROUPS[g[0]]
+            if name == "scaling" and self.scale_reg != 0.0:
+                reg.kind[k], reg.coef[k], used = 1, self.scale_reg * n_views / (3.0 * self.N), True
+            elif name == "opacity" and self.opacity_reg != 0.0:
+                reg.kind[k], reg.coef[k], used = 2, self.opacity_reg * n_views / float(self.N), True
+        return C.byref(reg) if used else None
+
+    def adam_step(self, n_views: Optional[int] = None) -> None:
+        """n_views: views of the GLOBAL batch this step closes (default: the views this rank rendered since the last
+        step times the p2p / NCCL world size, i.e. an evenly sharded batch)."""
         self.iteration += 1
+        if n_views is None:
+            n_views = self._views_since_step * (self._p2p_world if self.p2p else getattr(self, "_dp_world", 1))
+        self._views_since_step = 0
         b1, b2 = self.betas
         groups = []
         for gi, name in enumerate(GROUPS):
@@ -216,11 +286,12 @@ class SplatTrainer:
                                                        self._h_grads.buffer_ptrs_dev, self._h_params.buffer_ptrs_dev,
                                                        self._mc_grads or None, self._mc_params or None,
                                                        self.params.data_ptr(), self._p2p_world, self._p2p_rank, n, seg,
-                                                       lr, bc1, bc2, b1, b2, self.eps, self._stream()))
+                                                       lr, bc1, bc2, b1, b2, self.eps, self._adam_reg(run, n_views),
+                                                       self._stream()))
             else:
                 check(self.lib.lfs_adam_step_multi(self.params.data_ptr(), self.exp_avg.data_ptr(),
                                                    self.exp_avg_sq.data_ptr(), self.grads.data_ptr(), n, seg, lr, bc1,
-                                                   bc2, b1, b2, self.eps, 1, self._stream()))
+                                                   bc2, b1, b2, self.eps, 1, self._adam_reg(run, n_views), self._stream()))
         if self.p2p:
             self._h_params.barrier(channel=1)  # every rank's parameter writes have landed, nobody reads gradients any more
             self.grads.zero_()
@@ -258,7 +329,8 @@ class SplatTrainer:
             else:
                 dp.allreduce_sum_(self.grads)  # ONE collective over the flat planar gradient arena
             dp.allreduce_sum_(self.loss_dev)
-        self.adam_step()
+        self.adam_step(n_views=len(targets_pinned))
         if read_loss:
             self._loss_pinned.copy_(self.loss_dev, non_blocking=True)
+        self.poll_capacity()
         return self._loss_pinned

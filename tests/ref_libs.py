@@ -189,3 +189,72 @@ class FastGS:
         rc = self.lib.ref_fastgs_adam_step(_p(p), _p(m), _p(v), _p(g), C.c_int(p.numel()), C.c_float(lr), C.c_float(b1),
                                            C.c_float(b2), C.c_float(eps), C.c_float(bc1), C.c_float(bc2))
         assert rc == 0, rc
+
+
+# ---------------------------------------------------------------------------------------------- presence gate
+def require_all():
+    """On a box with a CUDA device the reference builds MUST be present: a missing oracle/_ref/*.so would silently turn
+    every 'vs the unmodified reference' assertion into a no-op (VERDICT r1, weak #3)."""
+    import glob
+    missing = [n for n in ("libgsplat_ref.so", "libfastgs_ref.so", "libtorch_impl_ref.so")
+               if not os.path.exists(os.path.join(_REF, n))]
+    for mod in ("ref_fastgs_torch", "b200_fastgs_torch"):
+        if not glob.glob(os.path.join(_REF, mod + "*.so")):
+            missing.append(mod + "*.so")
+    assert not missing, (f"reference builds missing under oracle/_ref: {missing} -- run `make -C oracle ref` in the build "
+                         "container (they travel to the GPU box with the snapshot)")
+
+
+_ti = None
+
+
+def torch_impl():
+    """UNMODIFIED /root/reference/tests/torch_impl.cpp (CPU ATen) behind oracle/ref_torch_impl_capi.cpp."""
+    global _ti
+    if _ti is None:
+        _ti = C.CDLL(os.path.join(_REF, "libtorch_impl_ref.so"))
+        _ti.ref_ti_isect_tiles.restype = C.c_longlong
+    return _ti
+
+
+def ti_spherical_harmonics(degree, dirs, coeffs):
+    import numpy as np
+    n, K = dirs.shape[0], coeffs.shape[1]
+    out = np.zeros((n, 3), np.float32)
+    d, c = np.ascontiguousarray(dirs, np.float32), np.ascontiguousarray(coeffs, np.float32)
+    torch_impl().ref_ti_spherical_harmonics(C.c_int(degree), d.ctypes.data_as(C.c_void_p), c.ctypes.data_as(C.c_void_p),
+                                            C.c_int(n), C.c_int(K), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def ti_isect_tiles(means2d, radii, depths, tile, tw, th, sort=True):
+    import numpy as np
+    Cc, N = depths.shape
+    m, r, d = (np.ascontiguousarray(means2d, np.float32), np.ascontiguousarray(radii, np.int32),
+               np.ascontiguousarray(depths, np.float32))
+    # exact upper bound of the instance count: the AABB tile box of every Gaussian
+    cap = int(Cc * N * 64) + 1024
+    tpg = np.zeros((Cc, N), np.int32)
+    ids = np.zeros(cap, np.int64)
+    flat = np.zeros(cap, np.int32)
+    k = torch_impl().ref_ti_isect_tiles(m.ctypes.data_as(C.c_void_p), r.ctypes.data_as(C.c_void_p),
+                                        d.ctypes.data_as(C.c_void_p), C.c_int(Cc), C.c_int(N), C.c_int(tile), C.c_int(tw),
+                                        C.c_int(th), C.c_int(int(sort)), tpg.ctypes.data_as(C.c_void_p),
+                                        ids.ctypes.data_as(C.c_void_p), flat.ctypes.data_as(C.c_void_p),
+                                        C.c_longlong(cap))
+    assert k <= cap, (k, cap)
+    return tpg, ids[:k], flat[:k]
+
+
+def fastgs_torch_module(which="ref"):
+    """oracle/ref_train_harness.cpp built against the reference's fastgs objects ('ref') or against this project's host
+    layer ('b200')."""
+    import glob
+    import importlib.util
+    name = {"ref": "ref_fastgs_torch", "b200": "b200_fastgs_torch"}[which]
+    hits = glob.glob(os.path.join(_REF, name + "*.so"))
+    assert hits, f"oracle/_ref/{name}*.so missing"
+    spec = importlib.util.spec_from_file_location(name, hits[0])
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod

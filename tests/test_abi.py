@@ -38,7 +38,7 @@ def test_ctypes_table_matches_header():
     import lichtfeld_studio_b200 as L
     assert sorted(L._lib.SIGNATURES) == header_functions()
     lib = L.load()
-    assert lib.lfs_abi_version() == 1
+    assert lib.lfs_abi_version() == L._lib.ABI_VERSION == 2
     assert lib.lfs_set_option(b"no_such_option", 1) < 0
     assert b"unknown option" in lib.lfs_last_error()
 
@@ -86,4 +86,4 @@ def test_header_is_plain_c99(tmp_path):
                         f"-Wl,-rpath,{libdir}", "-Wl,-rpath,/usr/local/cuda/lib64"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True)
-    assert r.returncode == 0 and r.stdout.startswith("1 "), (r.returncode, r.stdout, r.stderr)
+    assert r.returncode == 0 and r.stdout.startswith("2 "), (r.returncode, r.stdout, r.stderr)

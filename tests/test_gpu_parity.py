@@ -22,6 +22,7 @@ import gpu_diag as D  # noqa: E402
 def _need_cuda():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
+    D.R.require_all()  # a missing oracle/_ref/*.so must fail, not silently drop the 'vs reference' assertions
 
 
 def test_projection_ut():
@@ -62,7 +63,9 @@ def test_rasterize_fwd_bwd(tma, fused):
     if "ref_fwd_rgb_rel" in r:
         assert r["ref_fwd_rgb_rel"] <= 1e-4 and r["ref_fwd_alpha_rel"] <= 1e-4, r
         for k in ("v_means", "v_quats", "v_scales", "v_colors", "v_opacities"):
-            assert r[f"ref_bwd_{k}_rel"] <= 2e-3, (k, r)
+            # 1e-3 against the oracle above; against the reference's own fp32 backward (which is itself up to 3e-4 from
+            # the double oracle: ref_vs_oracle_bwd_*_rel) the sum of both distances is allowed
+            assert r[f"ref_bwd_{k}_rel"] <= 1e-3 + r[f"ref_vs_oracle_bwd_{k}_rel"], (k, r)
 
 
 def test_rasterize_dense_no_background():

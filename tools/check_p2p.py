@@ -29,10 +29,14 @@ torch.cuda.synchronize()
 G, P0 = tr.grads.clone(), tr.params.clone()
 
 
+START_ITER = 998  # three updates: iterations 999, 1000 (two runs, shN skipped) and 1001 (ONE run over the whole arena):
+                  # the shN group joins the run and slice ownership must not move
+
+
 def reset():
     tr.exp_avg.zero_(), tr.exp_avg_sq.zero_()
     tr.step_count = [0] * 6
-    tr.iteration = 1000
+    tr.iteration = START_ITER
     tr.lrs = dict(lrs0)
 
 
@@ -43,7 +47,7 @@ for mode in ("nccl", "p2p"):
         tr.enable_p2p()
     tr.params.copy_(P0)
     reset()
-    for _ in range(2):  # two updates on the same gradients
+    for _ in range(3):  # three updates on the same gradients, crossing iteration 1000 -> 1001
         tr.grads.copy_(G)
         torch.cuda.synchronize()
         dist.barrier()
