@@ -14,7 +14,9 @@ One JSON line is printed by rank 0 (see the contract in the task statement): `va
 images already resident in HBM; `e2e` = the same through SplatTrainer.train_step with pinned HOST uint8 targets
 (H2D per view, D2H of the loss per step); `roofline` = blend-backward kernel, algorithmic bytes (172 I + 24 P per
 view) over its CUDA-event time against MEASURED_PEAKS.json; `cpu_baseline` = the CPU oracle
-port timed on a bounded crop of the same workload.
+port timed on whole views of the same workload (bounded sample: one to three views); `reference_gpu` = the reference's
+own training step (its autograd Functions, fused SSIM and FusedAdam, compiled unchanged) on its own CUDA backends, timed
+in child processes beside ours.  --config C4 = 32 views with the mcmc regularisers; --scaling strong = fixed total views.
 """
 from __future__ import annotations
 
@@ -49,7 +51,9 @@ def parse():
                          "local Adam (nccl); auto = p2p when symmetric memory can be set up")
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / reference_gpu legs")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
-    ap.add_argument("--ref-gpu-leg", default="", choices=["", "fastgs", "gsplat"], help=argparse.SUPPRESS)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = --views-per-gpu views on every GPU; strong = the config's total view count "
+                         "(8 for C3, 32 for C4) split over the GPUs")
     return ap.parse_args()
 
 
@@ -102,8 +106,10 @@ def measured_peak_gbs():
 
 # ------------------------------------------------------------------------------------------------------------------
 def cpu_reference_leg(scene_obj, seconds: float):
-    """The reference's path restated on the CPU (oracle port, OpenMP over all host cores) on a bounded crop of the
-    same workload: one view of the full Gaussian set, a centred crop window of the 1080p image, fwd + bwd."""
+    """The reference's path restated on the CPU (oracle port, OpenMP over all host cores) on a BOUNDED SAMPLE of the same
+    workload: whole views (every Gaussian, every pixel of the 1920x1080 image; forward + L1/SSIM loss + backward) until
+    `seconds` have passed -- at least one, at most three.  No crop and no extrapolation: value = views / time.  Adam is
+    not included (it is < 1 % of a CPU view)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import numpy as np
 
@@ -112,177 +118,46 @@ def cpu_reference_leg(scene_obj, seconds: float):
     sc = scene_obj
     cores = os.cpu_count() or 1
     W, H = sc.width, sc.height
-    cw, ch = min(W, 256), min(H, 144)
-    x0, y0 = (W - cw) // 2 // 16 * 16, (H - ch) // 2 // 16 * 16
-    K = sc.Ks[0].copy()
-    K[0, 2] -= x0
-    K[1, 2] -= y0
     raw = dict(means=sc.means, sh0=sc.sh0, shN=sc.shN, scaling=sc.scaling, rotation=sc.rotation, opacity=sc.opacity)
-    tgt = np.zeros((ch, cw, 3), np.uint8)
+    tgt = np.zeros((H, W, 3), np.uint8)
     t0 = time.time()
     reps = 0
     while True:
-        O.view_loss_grads(raw, sc.viewmats[0], K, cw, ch, sc.sh_degree, (0.0, 0.0, 0.0), target=tgt, prec=32,
+        v = reps % sc.viewmats.shape[0]
+        O.view_loss_grads(raw, sc.viewmats[v], sc.Ks[v], W, H, sc.sh_degree, (0.0, 0.0, 0.0), target=tgt, prec=32,
                           lambda_dssim=LAMBDA_DSSIM)
         reps += 1
         if time.time() - t0 > seconds or reps >= 3:
             break
     dt = (time.time() - t0) / reps
-    frac = (cw * ch) / float(W * H)
-    # per-Gaussian work (projection / SH) is paid in full by the crop; pixel work scales with the crop area:
-    # views/s is reported for the crop as if it were the image (an upper bound for the CPU path)
-    return {"value": frac / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"1 view, all {sc.n} Gaussians, centred {cw}x{ch} crop of {W}x{H} ({frac:.4f} of the pixels), "
-                      f"fwd + L1/SSIM loss + bwd, {reps} reps, {dt:.2f} s each; value = crop fraction / time"}
+    return {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{reps} whole view(s): all {sc.n} Gaussians, all {W}x{H} pixels, fwd + L1/SSIM loss + bwd, "
+                      f"{dt:.2f} s per view (no crop, no extrapolation; the Adam step is not in the sample)"}
 
 
-def reference_gpu_leg(sc, steps: int, warmup: int, device):
-    """UNMODIFIED reference fastgs CUDA path (oracle/_ref/libfastgs_ref.so) on the same scene, cameras and loss:
-    per view forward -> L1 gradient (torch) -> backward, then its 6 Adam launches.  Reported beside our number as
-    the north_star asks; it is a baseline, never part of the product path."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import numpy as np
-    import torch
-
-    import ref_libs as R
-    if not R.have_fastgs():
-        return {"unavailable": "oracle/_ref/libfastgs_ref.so not present"}
-    fg = R.FastGS()
-    T = lambda x: torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float32, device=device)
-    P = dict(means=T(sc.means), scales=T(sc.scaling), rot=T(sc.rotation), op=T(sc.opacity), sh0=T(sc.sh0),
-             shN=T(sc.shN))
-    state = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in P.items()}
-    lrs = dict(means=0.00016, sh0=0.0025, shN=0.0025 / 20, scales=0.005, rot=0.001, op=0.05)
-    W, H = sc.width, sc.height
-    V = sc.viewmats.shape[0]
-    from lichtfeld_studio_b200 import scene as S
-    tg = [torch.as_tensor(S.make_target(v, W, H)).to(device).permute(2, 0, 1).float().div_(255.0).contiguous()
-          for v in range(min(V, 8))]
-    cams = []
-    for v in range(V):
-        w2c = T(sc.viewmats[v])
-        campos = T(np.linalg.inv(sc.viewmats[v].astype(np.float64))[:3, 3])
-        cams.append((w2c, campos, float(sc.Ks[v, 0, 0]), float(sc.Ks[v, 1, 1]), float(sc.Ks[v, 0, 2]),
-                     float(sc.Ks[v, 1, 2])))
-    nb = (sc.sh_degree + 1) ** 2
-    scale = 1.0 / (3.0 * W * H)
-
-    def step(t):
-        acc = None
-        for v in range(V):
-            w2c, campos, fx, fy, cx, cy = cams[v]
-            img, alpha, _ = fg.forward(P["means"], P["scales"], P["rot"], P["op"], P["sh0"], P["shN"], w2c, campos, nb,
-                                       W, H, fx, fy, cx, cy)
-            gimg = torch.sign(img - tg[v % len(tg)]) * scale
-            galpha = torch.zeros_like(alpha)
-            g = fg.backward(gimg, galpha, img, alpha, P["means"], P["scales"], P["rot"], P["shN"], w2c, campos, nb, W,
-                            H, fx, fy, cx, cy)
-            if acc is None:
-                acc = g
-            else:
-                for k in ("means", "scales", "rot", "op", "sh0", "shN"):
-                    acc[k] += g[k]
-        bc1, bc2 = 1.0 / (1.0 - 0.9 ** t), 1.0 / (1.0 - 0.999 ** t) ** 0.5
-        for k in ("means", "sh0", "shN", "scales", "rot", "op"):
-            fg.adam_step(P[k], state[k][0], state[k][1], acc[k], lrs[k], 0.9, 0.999, 1e-15, bc1, bc2)
-
-    for i in range(warmup):
-        step(i + 1)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(steps):
-        step(warmup + i + 1)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
-    return {"impl": "reference fastgs (EWA) CUDA build, unmodified, sm_100a, --use_fast_math", "value": V / ms * 1e3,
-            "unit": UNIT, "ms_per_step": ms, "views_per_step": V,
-            "note": "targets resident in HBM; loss gradient by torch elementwise ops; includes its 3 blocking D2H reads"}
-
-
-def reference_gsplat_gpu_leg(sc, steps: int, warmup: int, device):
-    """UNMODIFIED reference gsplat (3DGUT) CUDA path (oracle/_ref/libgsplat_ref.so, built against oracle/glm_shim):
-    per view projection_ut -> SH fwd -> intersect_tile (+CUB sort) -> intersect_offset -> rasterize fwd -> L1
-    gradient -> rasterize bwd -> SH bwd, i.e. the kernel sequence of src/training/rasterization/rasterizer.cpp:208-360
-    and its autograd backward, with the SplatData activations done by torch as the reference does; then the
-    reference's 6 fused-Adam launches.  The torch autograd bookkeeping of the reference is NOT included (this is a
-    lower bound of the reference's step time)."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import numpy as np
-    import torch
-
-    import ref_libs as R
-    if not R.have_gsplat():
-        return {"unavailable": "oracle/_ref/libgsplat_ref.so not present"}
-    T = lambda x: torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float32, device=device)
-    P = dict(means=T(sc.means), sh0=T(sc.sh0), shN=T(sc.shN), scales=T(sc.scaling), rot=T(sc.rotation), op=T(sc.opacity))
-    W, H, deg = sc.width, sc.height, sc.sh_degree
-    V = sc.viewmats.shape[0]
-    tw, th = (W + 15) // 16, (H + 15) // 16
-    from lichtfeld_studio_b200 import scene as S
-    tg = [torch.as_tensor(S.make_target(v, W, H)).to(device).float().div_(255.0).contiguous() for v in range(min(V, 8))]
-    cams = [(T(sc.viewmats[v:v + 1]), T(sc.Ks[v:v + 1]),
-             T(np.linalg.inv(sc.viewmats[v].astype(np.float64))[:3, 3])) for v in range(V)]
-    scale = 1.0 / (3.0 * W * H)
-    fg = R.FastGS() if R.have_fastgs() else None
-    state = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in P.items()}
-    lrs = dict(means=0.00016, sh0=0.0025, shN=0.0025 / 20, scales=0.005, rot=0.001, op=0.05)
-    n_isects = []
-
-    def step(t):
-        acc = {k: torch.zeros_like(v) for k, v in P.items()}
-        for v in range(V):
-            vm, K, campos = cams[v]
-            # SplatData getters (src/core/splat_data.cpp:267-286)
-            opac = torch.sigmoid(P["op"]).squeeze(-1)
-            scl = torch.exp(P["scales"])
-            quat = torch.nn.functional.normalize(P["rot"], dim=-1)
-            shs = torch.cat([P["sh0"], P["shN"]], dim=1).contiguous()
-            radii, m2d, dep, con, _ = R.projection_ut(P["means"], quat, scl, opac, vm, K, W, H)
-            dirs = (P["means"] - campos[None]).contiguous()
-            masks = (radii[0] > 0).all(-1).contiguous()
-            cols = R.sh_fwd(deg, dirs, shs, masks)
-            colors = torch.clamp_min(cols + 0.5, 0.0)
-            _, ids, flat = R.intersect_tile(m2d, radii, dep, 16, tw, th, True)
-            offs = R.intersect_offset(ids, 1, tw, th)
-            if len(n_isects) < V:
-                n_isects.append(int(flat.numel()))
-            ren, al, li = R.raster_fwd(P["means"], quat, scl, colors[None].contiguous(), opac[None].contiguous(), None,
-                                       W, H, 16, vm, K, offs, flat)
-            v_ren = (torch.sign(ren[0] - tg[v % len(tg)]) * scale)[None].contiguous()
-            v_al = torch.zeros_like(al)
-            vmn, vq, vs, vc, vo = R.raster_bwd(P["means"], quat, scl, colors[None].contiguous(), opac[None].contiguous(),
-                                               None, W, H, 16, vm, K, offs, flat, al, li, v_ren, v_al)
-            vcol = vc[0] * (cols + 0.5 >= 0)
-            v_shs, v_dirs = R.sh_bwd(deg, dirs, shs, vcol.contiguous(), masks, True)
-            # activation VJPs (what torch autograd does for the reference)
-            acc["means"] += vmn + v_dirs
-            acc["sh0"] += v_shs[:, :1]
-            acc["shN"] += v_shs[:, 1:]
-            acc["scales"] += vs * scl
-            dq = (vq * quat).sum(-1, keepdim=True)
-            acc["rot"] += (vq - dq * quat) / P["rot"].norm(dim=-1, keepdim=True).clamp_min(1e-12)
-            acc["op"] += (vo[0] * opac * (1 - opac))[:, None]
-        bc1, bc2 = 1.0 / (1.0 - 0.9 ** t), 1.0 / (1.0 - 0.999 ** t) ** 0.5
-        for k in ("means", "sh0", "shN", "scales", "rot", "op"):
-            if fg is not None:
-                fg.adam_step(P[k], state[k][0], state[k][1], acc[k].contiguous(), lrs[k], 0.9, 0.999, 1e-15, bc1, bc2)
-
-    for i in range(warmup):
-        step(i + 1)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(steps):
-        step(warmup + i + 1)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
-    return {"impl": "reference gsplat (3DGUT) CUDA kernels, unmodified, built against oracle/glm_shim, sm_100a, "
-                    "--use_fast_math; kernel sequence of rasterizer.cpp without the autograd bookkeeping",
-            "value": V / ms * 1e3, "unit": UNIT, "ms_per_step": ms, "views_per_step": V,
-            "instances_per_view": float(np.mean(n_isects)) if n_isects else None}
+def reference_gpu_leg(path: str, config: str, n_gaussians: int, views: int, steps: int):
+    """The reference's OWN training step on the same scene, cameras, loss and batch structure, in a child process:
+    tools/ref_train.py drives oracle/ref_train_harness.cpp, i.e. the reference's FastGSRasterize (path 'fastgs') or
+    SphericalHarmonicsFunction / fully_fused_projection_with_ut / GUTRasterizationFunction (path 'gut') autograd
+    Functions, its fused_ssim and its FusedAdam, all compiled UNCHANGED, on the reference's own CUDA backends.  A
+    baseline timed beside ours as the north_star asks -- never part of the product path."""
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "ref_train.py"), "--module", "ref", "--path", path, "--config",
+           config, "--views", str(views), "--steps", str(max(2, min(steps, 4))), "--warmup", "1"]
+    if n_gaussians:
+        cmd += ["--n-gaussians", str(n_gaussians)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    except subprocess.TimeoutExpired:
+        return {"error": "timeout after 900 s"}
+    got = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    if got:
+        d = json.loads(got[-1])
+        if "value" not in d:
+            d["error"] = ("the reference's forward_wrapper returned an implausible result on its first call "
+                          "(profiles/r02_ref_fastgs_root_cause.txt)")
+        return d
+    tail = (r.stderr or r.stdout).strip().splitlines()
+    return {"error": tail[-1][:300] if tail else f"exit code {r.returncode}"}
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -296,35 +171,45 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cfg_n, cfg_v, W, H, deg = S.CONFIGS[a.config]
     n = a.n_gaussians or cfg_n
-    vpg = a.views_per_gpu or (8 if a.config in ("C3", "C4") else cfg_v)
-    V = vpg * max(world, 1)
-
-    if a.ref_gpu_leg:  # child process: time the unmodified reference CUDA build and print one JSON object
-        import torch
-        sc = S.make_scene(n, vpg, W, H, deg, seed=42)
-        fn = reference_gpu_leg if a.ref_gpu_leg == "fastgs" else reference_gsplat_gpu_leg
-        print("REFGPU " + json.dumps(fn(sc, max(2, min(a.steps, 4)), 1, torch.device("cuda:0"))))
-        return 0
+    # C3 = 8 views per step on ONE GPU (BASELINE.json configs[2]); C4 = 32 views on 8 GPUs (configs[3]: 4 per GPU) with
+    # eval/mcmc_optimization_params.json (opacity_reg = scale_reg = 0.01, src/training/trainer.cpp:132-158)
+    base_vpg = {"C3": 8, "C4": 4}.get(a.config, cfg_v)
+    if a.scaling == "strong":
+        V = a.views_per_gpu * max(world, 1) if a.views_per_gpu else cfg_v
+        V = max(V, world)
+        vpg = (V + world - 1) // max(world, 1)
+    else:
+        vpg = a.views_per_gpu or base_vpg
+        V = vpg * max(world, 1)
+    mcmc = a.config == "C4"
+    scale_reg = opacity_reg = 0.01 if mcmc else 0.0
+    workload = (f"{a.config}: {n} Gaussians, {V} views per step ({a.scaling} scaling: {vpg} per GPU x {max(world, 1)} GPU) of "
+                f"{W}x{H}, SH degree {deg}, 3DGUT from-world rasterizer, L1 + fused-SSIM loss (lambda_dssim {LAMBDA_DSSIM}), "
+                + ("eval/mcmc_optimization_params.json (opacity_reg = scale_reg = 0.01 folded into the Adam step)" if mcmc
+                   else "eval/default_optimization_params.json lrs"))
 
     if a.impl == "reference":
-        # reference arm (tier rule): the reference's path on the box's host cores -- rank 0 only
+        # reference arm (tier rule): the reference's path on the box's host cores -- rank 0 only.  One "step" of this arm
+        # is a bounded sample of the workload: ONE whole view (all Gaussians, all pixels) instead of the batch.
         if rank != 0:
             return 0
         sc = S.make_scene(n, 1, W, H, deg, seed=42)
         t_all = time.time()
-        vals = []
-        for _ in range(max(1, min(a.steps, 3))):
-            vals.append(cpu_reference_leg(sc, max(5.0, min(a.cpu_seconds, 30.0)) / 3.0))
+        k = max(1, min(a.steps, 3))
+        for _ in range(min(a.warmup, 1)):
+            cpu_reference_leg(sc, 0.0)
+        vals = [cpu_reference_leg(sc, 0.0) for _ in range(k)]
         cb = dict(vals[-1])
         cb["value"] = statistics.median(v["value"] for v in vals)
+        cb["sample"] = f"{k} step(s) of ONE whole view each (all {n} Gaussians, all {W}x{H} pixels, fwd + L1/SSIM loss + bwd); " \
+                       f"value = 1 view / median step time; no crop, no extrapolation"
         line = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "impl": "reference", "n_gpus": a.gpus,
-                "steps": len(vals), "warmup": 0, "ms_per_step": 1e3 / cb["value"] if cb["value"] else None,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"{a.config}: {n} Gaussians, {vpg} views/GPU x {max(world, 1)} GPU of {W}x{H}, "
-                                       f"SH degree {deg}, 3DGUT from-world rasterizer, L1 + fused-SSIM loss (lambda_dssim "
-                                       f"{LAMBDA_DSSIM}); CPU port of the reference path (no CPU implementation of the "
-                                       "blend exists in the reference: tests/test_rasterization.cpp:96-98)",
-                           "gaussians": n, "views_per_step": V, "width": W, "height": H, "sh_degree": deg},
+                "steps": k, "warmup": min(a.warmup, 1), "ms_per_step": 1e3 / cb["value"] if cb["value"] else None,
+                "views_per_step": 1, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": workload + "; CPU port of the reference path (the reference has no CPU implementation "
+                                                  "of the blend: tests/test_rasterization.cpp:96-98), one view per step",
+                           "gaussians": n, "views_per_step": 1, "width": W, "height": H, "sh_degree": deg},
                 "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0, "wall_s": round(time.time() - t_all, 1)}
@@ -342,26 +227,12 @@ def main():
     sc = S.make_scene(n, V, W, H, deg, seed=42)
     my_views = list(range(rank, V, world))
 
-    tr = SplatTrainer(n, W, H, deg, device)
+    tr = SplatTrainer(n, W, H, deg, device, scale_reg=scale_reg, opacity_reg=opacity_reg)
     tr.load_scene(sc)
     tr.iteration = 1000  # steady state: the reference skips the shN group only for iteration <= 1000
-    # capacity calibration (one forward per local view, with sync) -- outside every timed region
-    need = 0
-    for v in my_views:
-        tr.forward(sc.viewmats[v], sc.Ks[v], deg)
-        try:
-            ni, _ = tr.stats()
-        except Exception:
-            ni = int(tr.lib.lfs_trainer_instance_capacity(tr.h)) * 2
-        need = max(need, ni)
-    cap = int(tr.lib.lfs_trainer_instance_capacity(tr.h))
-    if need > cap or cap > 2 * need + (1 << 20):
-        new_cap = int(need * 1.25) + (1 << 16)
-        del tr
-        torch.cuda.empty_cache()
-        tr = SplatTrainer(n, W, H, deg, device, instance_capacity=new_cap)
-        tr.load_scene(sc)
-        tr.iteration = 1000
+    tr._dp_world = world
+    # capacity calibration (one blocking forward per local view) -- outside every timed region
+    tr.ensure_capacity([sc.viewmats[v] for v in my_views], [sc.Ks[v] for v in my_views], deg)
     n_inst_per_view = []
     for v in my_views:
         tr.forward(sc.viewmats[v], sc.Ks[v], deg)
@@ -376,7 +247,7 @@ def main():
                 dp_mode = ("fused reduce-scatter + Adam + all-gather in one kernel (lfs_adam_step_multi_p2p), " +
                            ("NVSwitch multicast: multimem.ld_reduce / multimem.st" if tr._mc_grads
                             else "NVLink peer loads / stores"))
-            except Exception as e:  # symmetric memory unavailable on this box: the NCCL path is the validated default
+            except Exception as e:  # symmetric memory unavailable on this box: the NCCL path is the validated fallback
                 if a.dp == "p2p":
                     raise
                 dp_mode += f" (p2p unavailable: {type(e).__name__})"
@@ -404,7 +275,7 @@ def main():
                 tr._h_grads.barrier(channel=0)
             else:
                 dist.all_reduce(tr.grads, op=dist.ReduceOp.SUM)
-        tr.adam_step()
+        tr.adam_step(n_views=V)
 
     def step_e2e():
         tr.train_step(sc.viewmats, sc.Ks, targets_host, bg, deg, world, rank, read_loss=True)
@@ -435,7 +306,9 @@ def main():
     clk = clocks.stop() if rank == 0 else {}
     ms_e2e, _ = timed(step_e2e, a.steps, max(1, a.warmup))
 
-    # per-kernel timing for the roofline (profiling pass, outside the timed regions)
+    # per-kernel timing for the roofline: a PROFILING pass outside the timed regions.  Every stage is bracketed by CUDA
+    # events and the backward blocks on the stream, so consecutive views do not overlap here: the stage times sum to a
+    # little more than ms_per_step / views (in the timed run the tail of a view overlaps the head of the next).
     tr.set_profile(True)
     for _ in range(2):
         step_resident()
@@ -457,24 +330,26 @@ def main():
     achieved = bwd_bytes / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 else 0.0
     h2d = sum(int(targets_host[v].numel()) for v in my_views) + len(my_views) * (16 + 9) * 4
     # DRAM traffic of the same kernel from the committed `ncu --set full` capture of tools/profile_view.py on this
-    # workload (profiles/r01_ncu_full_final.json; ncu cannot run inside a timed bench)
+    # workload (ncu cannot run inside a timed bench): newest profiles/rNN_ncu_full*.json that has the kernel
     traffic, traffic_src = None, None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_full_final.json")) as f:
-            for k in json.load(f):
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full*.json")), reverse=True):
+        try:
+            for k in json.load(open(path)):
                 if k["kernel"].startswith("k_blend_bwd"):
                     traffic = (k["dram__bytes_read.sum"] + k["dram__bytes_write.sum"]) * 1e6  # ncu reports Mbyte
-                    traffic_src = "profiles/r01_ncu_full_final.json (dram__bytes_read.sum + dram__bytes_write.sum)"
+                    traffic_src = f"profiles/{os.path.basename(path)} (dram__bytes_read.sum + dram__bytes_write.sum)"
                     break
-    except (OSError, KeyError, ValueError):
-        pass
+        except (OSError, KeyError, ValueError, TypeError):
+            continue
+        if traffic is not None:
+            break
+    arena_bytes = int(tr.params.numel()) * 4
     line = {
         "metric": METRIC, "value": V / ms_step * 1e3, "unit": UNIT, "n_gpus": world, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{a.config}: {n} Gaussians, {vpg} views/GPU x {world} GPU of {W}x{H}, SH degree {deg}, "
-                               "3DGUT from-world rasterizer, L1 + fused-SSIM loss (lambda_dssim 0.2), eval/default_optimization_params.json lrs",
-                   "gaussians": n, "views_per_step": V, "width": W, "height": H, "sh_degree": deg,
+        "config": {"workload": workload, "gaussians": n, "views_per_step": V, "width": W, "height": H, "sh_degree": deg,
                    "parallelism": f"view-sharded dp{world}: {dp_mode}",
                    "instances_per_view": I, "l2": "per-step working set (params+grads+Adam state+records) >= 1 GB, "
                                                   "larger than the 126 MB L2: no flush needed"},
@@ -486,34 +361,36 @@ def main():
         "gpu_launches": launches,
         "roofline": {"kernel": "k_blend_bwd", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
-                         "peak_source": peak_src,
-                     "algorithmic_bytes": bwd_bytes, "launch_ms": bwd_ms,
-                     "note": "algorithmic bytes = 172*I + 24*P per view (BASELINE.md s5); the kernel is FP32/SFU "
-                             "bound, not HBM bound (SURVEY s7 'roofline honesty')"},
+                     "peak_source": peak_src, "algorithmic_bytes": bwd_bytes, "launch_ms": bwd_ms,
+                     "note": "algorithmic bytes = 172*I + 24*P per view (BASELINE.md s5); the kernel is FP32/SFU and "
+                             "latency bound, not HBM bound (SURVEY s7 'roofline honesty')"},
         "stage_ms_per_view": prof,
+        "stage_ms_note": "profiling pass with a blocking event pair per stage (views do not overlap): the sum exceeds "
+                         "ms_per_step / views_per_gpu by the overlap the timed run gets",
         "stage_roofline": {"blend_fwd_GBps": fwd_bytes / (prof.get("blend_fwd", 0) * 1e-3) / 1e9
                            if prof.get("blend_fwd", 0) > 0 else None},
     }
+    if world > 1:
+        # exchange step: every rank sends / receives (W-1)/W of the gradient arena (reduce-scatter) and of the parameter
+        # arena (all-gather); the multicast variant receives 1/W of the gradients (reduced in the switch)
+        line["nvlink"] = {"arena_bytes": arena_bytes,
+                          "bytes_per_rank_per_step": 2.0 * (world - 1) / world * arena_bytes,
+                          "note": "2 (W-1)/W x arena per rank per step (reduce-scatter + all-gather), the same volume an "
+                                  "ncclAllReduce moves"}
     if not a.no_extras and world == 1:
         try:
             line["cpu_baseline"] = cpu_reference_leg(S.make_scene(n, 1, W, H, deg, seed=42), a.cpu_seconds)
         except Exception as e:
             line["cpu_baseline"] = {"error": repr(e)}
-        try:  # separate process: a fault inside the reference build must not take the bench down
+        try:  # separate processes: a fault inside a reference build must not take the bench down
             del tr
             torch.cuda.empty_cache()
             line["reference_gpu"] = {}
-            for which in ("gsplat", "fastgs"):
-                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--ref-gpu-leg", which, "--config",
-                                    a.config, "--n-gaussians", str(a.n_gaussians), "--views-per-gpu", str(vpg),
-                                    "--steps", str(a.steps)], capture_output=True, text=True, timeout=600)
-                got = [l for l in r.stdout.splitlines() if l.startswith("REFGPU ")]
-                line["reference_gpu"][which] = (json.loads(got[-1][7:]) if got
-                                                else {"error": (r.stderr or r.stdout).strip().splitlines()[-1][:300]})
-            if "error" in line["reference_gpu"].get("fastgs", {}):
-                line["reference_gpu"]["fastgs"]["note"] = (
-                    "the unmodified reference fastgs build returns garbage bucket counts above ~1e5 primitives on this "
-                    "image (profiles/r01_ref_fastgs_diagnosis.txt); it runs, and matches ours, on the small parity cases")
+            for name, path in (("gsplat", "gut"), ("fastgs", "fastgs")):
+                line["reference_gpu"][name] = reference_gpu_leg(path, a.config, a.n_gaussians, vpg, a.steps)
+            for name, key in (("gsplat", "vs_reference_gsplat"), ("fastgs", "vs_reference_fastgs")):
+                v = line["reference_gpu"][name].get("value")
+                line[key] = (line["value"] / v) if v else None
         except Exception as e:
             line["reference_gpu"] = {"error": repr(e)}
         try:  # the EWA (fastgs) surface of this library on the same workload, op level (forward + backward per view)

@@ -138,7 +138,8 @@ int lfs_rasterize_to_pixels_from_world_3dgs_fwd(
  * written (zero-filled then accumulated, like the reference's at::zeros_like + atomics). */
 int lfs_rasterize_to_pixels_from_world_3dgs_bwd(
     const float* means, const float* quats, const float* scales, const float* colors, const float* opacities,
-    const float* backgrounds, const uint8_t* masks, uint32_t N, uint32_t C, uint32_t image_width,
+    const float* backgrounds, const uint8_t* masks, uint32_t N, uint32_t C, uint32_t channels,
+    uint32_t image_width,
     uint32_t image_height, uint32_t tile_size, const float* viewmats0, const float* viewmats1, const float* Ks,
     int camera_model, const lfs_ut_params* ut_params, int rs_type, const float* radial_coeffs,
     const float* tangential_coeffs, const float* thin_prism_coeffs, const int32_t* tile_offsets,

@@ -111,7 +111,7 @@ SIGNATURES = {
     ),
     "lfs_rasterize_to_pixels_from_world_3dgs_bwd": (
         C.c_int,
-        [_vp] * 7 + [_u32] * 5 + [_vp] * 3 + [C.c_int, C.POINTER(UTParams), C.c_int] + [_vp] * 3 + [_vp, _vp, _i64]
+        [_vp] * 7 + [_u32] * 6 + [_vp] * 3 + [C.c_int, C.POINTER(UTParams), C.c_int] + [_vp] * 3 + [_vp, _vp, _i64]
         + [_vp] * 4 + [ALLOC_FN, _vp] + [_vp] * 5 + [_vp],
     ),
     "lfs_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _f, _vp]),

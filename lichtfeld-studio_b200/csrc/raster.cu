@@ -205,9 +205,44 @@ __device__ __forceinline__ float poly2(const float dx, const float dy, const flo
     return fmaf(dx, fmaf(dx, cxx, fmaf(dy, cxy, cx)), fmaf(dy, fmaf(dy, cyy, cy), c0));
 }
 
-template <int MODE, bool EWA, int MINB = 1> // MODE 0: register-staged InstRec, 1: TMA-staged InstRec, 2: fused expansion
-                                             // (GaussRec gather); EWA: fastgs-surface records (2-D conic, D == 1),
-                                             // MODE 2 only; MINB: minimum resident CTAs per SM (register cap)
+// Packed fp32 pairs (sm_100a FFMA2 / FMUL2: two IEEE fp32 operations per instruction, each component rounded exactly like
+// the scalar fmaf / __fmul_rn): the N' and D polynomials of a pair share (dx, dy), so one FFMA2 chain evaluates both
+// with the same bits as two poly2() calls.
+__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(d)
+        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)),
+          "l"(*reinterpret_cast<const unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fmul2(const float2 a, const float2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;"
+        : "=l"(d)
+        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+// (N', D)(dx, dy) with coefficient pairs c = {(n0,d0), (n1x,d1x), (n1y,d1y), (n2xx,d2xx), (n2xy,d2xy), (n2yy,d2yy)}:
+// the same nesting as poly2, five FFMA2 instead of ten FFMA
+__device__ __forceinline__ float2 poly2x2(const float2 DX, const float2 DY, const float2 c0, const float2 cx,
+                                          const float2 cy, const float2 cxx, const float2 cxy, const float2 cyy) {
+    return ffma2(DX, ffma2(DX, cxx, ffma2(DY, cxy, cx)), ffma2(DY, ffma2(DY, cyy, cy), c0));
+}
+
+// staged record of the PK (FFMA2) forward: (N', D) coefficient pairs, colour first
+//   [0] = (n0,d0, n1x,d1x)  [1] = (n1y,d1y, n2xx,d2xx)  [2] = (n2xy,d2xy, n2yy,d2yy)  [3] = (r, g, b, opacity)
+__device__ __forceinline__ void store_rec_pk(float4* d, const float4 A, const float4 B, const float4 Cc, const float4 E) {
+    d[0] = make_float4(A.x, B.z, A.y, B.w);
+    d[1] = make_float4(A.z, Cc.x, A.w, Cc.y);
+    d[2] = make_float4(B.x, Cc.z, B.y, Cc.w);
+    d[3] = make_float4(E.y, E.z, E.w, E.x);
+}
+
+template <int MODE, bool EWA, int MINB = 1, bool PK = false> // MODE 0: register-staged InstRec, 1: TMA-staged InstRec,
+                                             // 2: fused expansion (GaussRec gather); EWA: fastgs-surface records (2-D
+                                             // conic, D == 1), MODE 2 only; MINB: minimum resident CTAs per SM (register
+                                             // cap); PK: FFMA2 evaluation of (N', D) (MODE 2, not EWA)
 __global__ void __launch_bounds__(kFwdThreads, MINB)
     k_blend_fwd(const RasterBuffers rb, const ViewCam* __restrict__ cams, const uint32_t width, const uint32_t height, const uint32_t tile_w,
                 const uint32_t tile_h, const bool write_ckpt, const float* __restrict__ backgrounds,
@@ -317,9 +352,13 @@ __global__ void __launch_bounds__(kFwdThreads, MINB)
                     expand_record_ewa(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), Xo, Yo, A, B, Cc);
                 } else {
                     expand_record(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), Xo, Yo, A, B, Cc);
-                    s_rec[0][4 * tid + 3] = __ldg(gp + 3);
+                    if (PK)
+                        store_rec_pk(&s_rec[0][4 * tid], A, B, Cc, __ldg(gp + 3));
+                    else
+                        s_rec[0][4 * tid + 3] = __ldg(gp + 3);
                 }
-                s_rec[0][4 * tid] = A, s_rec[0][4 * tid + 1] = B, s_rec[0][4 * tid + 2] = Cc;
+                if (!PK)
+                    s_rec[0][4 * tid] = A, s_rec[0][4 * tid + 1] = B, s_rec[0][4 * tid + 2] = Cc;
             }
             if ((int)tid < cnt - kBatch)
                 gid_next = (uint32_t)__ldg(rb.inst_gid + start + kBatch + tid);
@@ -406,6 +445,34 @@ __global__ void __launch_bounds__(kFwdThreads, MINB)
                     E = make_float4(B.z, B.w, Cc.x, Cc.y);
                 else
                     E = s[4 * t + 3];
+                if (PK) { // A, B, Cc hold the three pair-interleaved float4, E = (r, g, b, opacity)
+                    const float2 P0 = make_float2(A.x, A.y), P1 = make_float2(A.z, A.w), P2 = make_float2(B.x, B.y),
+                                 P3 = make_float2(B.z, B.w), P4 = make_float2(Cc.x, Cc.y), P5 = make_float2(Cc.z, Cc.w);
+                    const float2 Erg = make_float2(E.x, E.y);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float2 ND = poly2x2(make_float2(dx[k], dx[k]), make_float2(dy[k], dy[k]), P0, P1, P2, P3,
+                                                  P4, P5);
+                        const float vis = ex2_approx(ND.x * rcp_approx(ND.y));
+                        const float alpha = fminf(kAlphaMax, E.w * vis);
+                        if (((live >> k) & 1u) && alpha >= kAlphaMin) {
+                            const float next_T = T[k] * (1.0f - alpha);
+                            if (next_T <= kTMin) {
+                                live &= ~(1u << k);
+                            } else {
+                                const float w = alpha * T[k];
+                                const float2 rg = ffma2(make_float2(w, w), Erg, make_float2(r[k], g[k]));
+                                r[k] = rg.x, g[k] = rg.y;
+                                b[k] = fmaf(w, E.z, b[k]);
+                                T[k] = next_T;
+                                ncon[k] = li + 1;
+                            }
+                        }
+                    }
+                    if (live == 0)
+                        break;
+                    continue;
+                }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const float Nv = poly2(dx[k], dy[k], A.x, A.y, A.z, A.w, B.x, B.y);
@@ -453,9 +520,13 @@ __global__ void __launch_bounds__(kFwdThreads, MINB)
                     expand_record_ewa(pre[0], pre[1], pre[2], Xo, Yo, A, B, Cc);
                 } else {
                     expand_record(pre[0], pre[1], pre[2], Xo, Yo, A, B, Cc);
-                    d[3] = pre[3];
+                    if (PK)
+                        store_rec_pk(d, A, B, Cc, pre[3]);
+                    else
+                        d[3] = pre[3];
                 }
-                d[0] = A, d[1] = B, d[2] = Cc;
+                if (!PK)
+                    d[0] = A, d[1] = B, d[2] = Cc;
             }
         } else if (!USE_TMA) {
 #pragma unroll
@@ -535,6 +606,10 @@ int launch_blend_fwd(const RasterBuffers& rb, const ViewCam* cams_dev, uint32_t 
     if (raster_options().fuse_expand && raster_options().fwd_variant == 1)
         k_blend_fwd<2, false, 10><<<grid, kFwdThreads, 0, stream>>>(rb, cams_dev, width, height, tile_w, tile_h, write_ckpt,
                                                                    backgrounds, masks, renders, alphas, last_ids);
+    else if (raster_options().fuse_expand && raster_options().fwd_variant == 3)
+        k_blend_fwd<2, false, 1, true><<<grid, kFwdThreads, 0, stream>>>(rb, cams_dev, width, height, tile_w, tile_h,
+                                                                        write_ckpt, backgrounds, masks, renders, alphas,
+                                                                        last_ids);
     else if (raster_options().fuse_expand && raster_options().fwd_variant == 2)
         k_blend_fwd<2, false, 12><<<grid, kFwdThreads, 0, stream>>>(rb, cams_dev, width, height, tile_w, tile_h, write_ckpt,
                                                                    backgrounds, masks, renders, alphas, last_ids);
@@ -577,207 +652,20 @@ __device__ __forceinline__ void quat_to_rotmat_dev(const float4 q_wxyz, float R[
     R[6] = 2.f * (xz - wy), R[7] = 2.f * (yz + wx), R[8] = 1.f - 2.f * (x2 + y2);
 }
 
-// EWA = fastgs surface: records are 2-D conics (D == 1), outputs are the per-primitive helpers of the reference's
-// blend_backward_cu (kernels_backward.cuh:240-449) passed in the slots v_means -> grad_mean2d [N,2],
-// v_quats -> grad_conic [N,3] (a, b, c; b is the TRUE derivative, twice the reference's stored value),
-// v_colors -> grad_color [N,3], v_opacities -> grad_raw_opacity [N]; quats / scales / means / cams are unused.
-template <bool FUSED, int kBwdWarps, int kMinBlocks, bool EWA = false>
-__global__ void __launch_bounds__(kBwdWarps * 32, kMinBlocks)
-    k_blend_bwd(const RasterBuffers rb, const ViewCam* __restrict__ cams, const float4* __restrict__ v_pix,
-                const float* __restrict__ quats, const float* __restrict__ scales, const float* __restrict__ means,
-                const uint32_t N, const uint32_t width, const uint32_t height, const uint32_t tile_w,
-                const uint32_t tile_h, const uint32_t n_bucket_cap, const uint32_t* __restrict__ n_buckets_dev,
-                float* __restrict__ v_means, float* __restrict__ v_quats, float* __restrict__ v_scales,
-                float* __restrict__ v_colors, float* __restrict__ v_opacities) {
-    // ring of per-pixel records the lanes read directly (no 9-register rotation): two float4 per pixel,
-    //   ringA = (v_r, v_g, v_b, dx)   ringB = (dy, bits(n_rel), T0, u0)
-    // n_rel = how many instances of THIS bucket the pixel consumed (lane < n_rel <=> the forward evaluated the pair);
-    // T0 = transmittance at the bucket start; u0 = <colour accumulated from this bucket on, v_rgb> - v_alpha term.
-    __shared__ float4 ringA[kBwdWarps][64];
-    __shared__ float4 ringB[kBwdWarps][64];
-    __shared__ uint8_t s_pix[kBwdWarps][kTilePix];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t b = blockIdx.x * kBwdWarps + warp;
-    uint32_t nbk = *n_buckets_dev;
-    nbk = nbk < n_bucket_cap ? nbk : n_bucket_cap;
-    if (b >= nbk)
-        return;
-    const uint32_t n_tiles = tile_w * tile_h;
-    const uint32_t ft = rb.bucket_tile[b];
-    const uint32_t cam = ft / n_tiles, tile = ft - cam * n_tiles;
-    const uint32_t ty = tile / tile_w, tx = tile - ty * tile_w;
-    const int32_t tstart = rb.tile_off[ft], tend = rb.tile_off[ft + 1];
-    const uint32_t local_b = b - rb.bucket_off[ft];
-    if (local_b * kBucket >= rb.tile_max_contrib[ft])
-        return;
-    const uint32_t li = local_b * kBucket + lane; // tile-local instance index of this lane
-    const int32_t inst = tstart + (int32_t)li;
-    const bool valid = inst < tend;
-    const float Xo = (float)(tx * kTile + kTile / 2) - (EWA ? 0.f : cams[cam].cx);
-    const float Yo = (float)(ty * kTile + kTile / 2) - (EWA ? 0.f : cams[cam].cy);
-
-    float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A, Cc = A, E = A;
-    uint32_t g = 0;
-    if (valid) {
-        g = (uint32_t)__ldg(rb.inst_gid + inst);
-        if (EWA) {
-            const float4* gp = reinterpret_cast<const float4*>(rb.gauss + g);
-            expand_record_ewa(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), Xo, Yo, A, B, Cc);
-            E = make_float4(B.z, B.w, Cc.x, Cc.y);
-        } else if (FUSED) {
-            const float4* gp = reinterpret_cast<const float4*>(rb.gauss + g);
-            expand_record(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), Xo, Yo, A, B, Cc);
-            E = __ldg(gp + 3);
-        } else {
-            const float4* rp = reinterpret_cast<const float4*>(rb.inst + inst);
-            A = ld_nc4(rp), B = ld_nc4(rp + 1), Cc = ld_nc4(rp + 2), E = ld_nc4(rp + 3);
-        }
-    }
-
-    // state that still rotates through the lanes: transmittance before this lane's instance, and
-    // u = <sum_{j >= this instance} c_j alpha_j T_j, v_rgb> - v_alpha_term   (one scalar instead of 3 + 1)
-    float T = 0.f, u = 0.f;
-    // per-instance accumulators
-    float an0 = 0.f, an1 = 0.f, an2 = 0.f, an3 = 0.f, an4 = 0.f, an5 = 0.f;
-    float ad0 = 0.f, ad1 = 0.f, ad2 = 0.f, ad3 = 0.f, ad4 = 0.f, ad5 = 0.f;
-    float aop = 0.f, acr = 0.f, acg = 0.f, acb = 0.f;
-
-    const float4* ck = rb.ckpt + (size_t)b * kTilePix;
-
-    // compact list of the tile's pixels that reach this bucket (n_contrib > first instance of the bucket):
-    // late buckets are reached by few pixels, so the rotation below runs m + 31 instead of 256 + 31 steps
-    int m = 0;
-    {
-        const uint32_t lt = (1u << lane) - 1u;
-#pragma unroll
-        for (int rr = 0; rr < kTilePix / 32; ++rr) {
-            const int p = rr * 32 + lane;
-            const uint32_t px = tx * kTile + (p & 15), py = ty * kTile + (p >> 4);
-            bool kp = false;
-            if (px < width && py < height)
-                kp = (uint32_t)__ldg(rb.n_contrib + ((size_t)cam * height + py) * width + px) > local_b * kBucket;
-            const uint32_t mask = __ballot_sync(0xffffffffu, kp);
-            if (kp)
-                s_pix[warp][m + __popc(mask & lt)] = (uint8_t)p;
-            m += __popc(mask);
-        }
-        __syncwarp();
-    }
-
-    const int ilane = lane;
-    for (int i = 0; i < m + 31; ++i) {
-        if ((i & 31) == 0 && i < m) { // stage the next 32 pixels of the list into the ring half (i & 32)
-            __syncwarp();
-            float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a4;
-            if (i + lane < m) {
-                const int p = s_pix[warp][i + lane];
-                const uint32_t px = tx * kTile + (p & 15), py = ty * kTile + (p >> 4);
-                const size_t pix = ((size_t)cam * height + py) * width + px;
-                const int32_t nrel = __ldg(rb.n_contrib + pix) - (int32_t)(local_b * kBucket);
-                const float4 c4 = ld_nc4(ck + p);
-                const float4 f4 = __ldg(rb.pix_state + pix);
-                const float4 v4 = __ldg(v_pix + pix);
-                const float u0 = fmaf(f4.x - c4.x, v4.x, fmaf(f4.y - c4.y, v4.y, fmaf(f4.z - c4.z, v4.z, -v4.w)));
-                a4 = make_float4(v4.x, v4.y, v4.z, (float)(p & 15) - 7.5f);
-                b4 = make_float4((float)(p >> 4) - 7.5f, __int_as_float(nrel), c4.w, u0);
-            }
-            ringA[warp][(i + lane) & 63] = a4;
-            ringB[warp][(i + lane) & 63] = b4;
-            __syncwarp();
-        }
-        const int idx = i - ilane; // position in the compact list of the pixel currently at this lane
-        const float4 ea = ringA[warp][idx & 63], eb = ringB[warp][idx & 63];
-        T = __shfl_up_sync(0xffffffffu, T, 1);
-        u = __shfl_up_sync(0xffffffffu, u, 1);
-        if (lane == 0) {
-            T = eb.z;
-            u = eb.w;
-        }
-        const bool active = valid && (uint32_t)idx < (uint32_t)m && ilane < __float_as_int(eb.y);
-        if (!active)
-            continue;
-        const float dx = ea.w, dy = eb.x;
-        const float Nv = poly2(dx, dy, A.x, A.y, A.z, A.w, B.x, B.y);
-        float rD = 1.f, p2 = Nv;
-        if (EWA) {
-            if (Nv > 0.f) // sigma/2 < 0 is skipped (kernels_backward.cuh:391-392)
-                continue;
-        } else {
-            const float Dv = poly2(dx, dy, B.z, B.w, Cc.x, Cc.y, Cc.z, Cc.w);
-            rD = rcp_approx(Dv);
-            p2 = Nv * rD;
-        }
-        const float vis = ex2_approx(p2);
-        const float a_raw = E.x * vis;
-        const float alpha = fminf(kAlphaMax, a_raw);
-        if (alpha < kAlphaMin)
-            continue;
-        const float w = T * alpha;
-        acr = fmaf(w, ea.x, acr);
-        acg = fmaf(w, ea.y, acg);
-        acb = fmaf(w, ea.z, acb);
-        const float Ev = fmaf(E.y, ea.x, fmaf(E.z, ea.y, E.w * ea.z)); // <c_i, v_rgb>
-        u = fmaf(-w, Ev, u);                                           // now the sum over j > i
-        const float om = 1.0f - alpha;                                 // >= 0.001: plain rcp is safe
-        const float v_alpha = fmaf(T, Ev, -u * rcp_approx(om));
-        if (EWA) {
-            // the reference differentiates through the clamped alpha as if it were not clamped (:418-427)
-            aop = fmaf(alpha, v_alpha, aop);
-            const float vN = v_alpha * alpha * kLn2;
-            const float dxx = dx * dx, dxy = dx * dy, dyy = dy * dy;
-            an0 += vN;
-            an1 = fmaf(vN, dx, an1);
-            an2 = fmaf(vN, dy, an2);
-            an3 = fmaf(vN, dxx, an3);
-            an4 = fmaf(vN, dxy, an4);
-            an5 = fmaf(vN, dyy, an5);
-        } else if (a_raw <= kAlphaMax) {
-            aop = fmaf(vis, v_alpha, aop);
-            const float vN = v_alpha * a_raw * kLn2 * rD;
-            const float vD = -vN * p2;
-            const float dxx = dx * dx, dxy = dx * dy, dyy = dy * dy;
-            an0 += vN;
-            an1 = fmaf(vN, dx, an1);
-            an2 = fmaf(vN, dy, an2);
-            an3 = fmaf(vN, dxx, an3);
-            an4 = fmaf(vN, dxy, an4);
-            an5 = fmaf(vN, dyy, an5);
-            ad0 += vD;
-            ad1 = fmaf(vD, dx, ad1);
-            ad2 = fmaf(vD, dy, ad2);
-            ad3 = fmaf(vD, dxx, ad3);
-            ad4 = fmaf(vD, dxy, ad4);
-            ad5 = fmaf(vD, dyy, ad5);
-        }
-        T *= om;
-    }
-
-    if (!valid)
-        return;
-    if (EWA) {
-        // ---- polynomial-coefficient gradients -> (conic, mean2d); e = mean2d - tile centre
-        const float4* gp = reinterpret_cast<const float4*>(rb.gauss + g);
-        const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1), g2 = __ldg(gp + 2);
-        const float ex = g0.x - Xo, ey = g0.y - Yo, a = g0.z, b = g0.w, c = g1.x;
-        const float v_a = kEScale * (0.5f * ex * ex * an0 - ex * an1 + 0.5f * an3);
-        const float v_b = kEScale * (ex * ey * an0 - ey * an1 - ex * an2 + an4);
-        const float v_c = kEScale * (0.5f * ey * ey * an0 - ey * an2 + 0.5f * an5);
-        const float v_ex = kEScale * ((a * ex + b * ey) * an0 - a * an1 - b * an2);
-        const float v_ey = kEScale * ((c * ey + b * ex) * an0 - b * an1 - c * an2);
-        atomicAdd(v_means + 2 * (size_t)g, v_ex);
-        atomicAdd(v_means + 2 * (size_t)g + 1, v_ey);
-        atomicAdd(v_quats + 3 * (size_t)g, v_a);
-        atomicAdd(v_quats + 3 * (size_t)g + 1, v_b);
-        atomicAdd(v_quats + 3 * (size_t)g + 2, v_c);
-        // colour: gradient passes where the unclamped colour is >= 0 (color_grad_factor, :304-309)
-        atomicAdd(v_colors + 3 * (size_t)g, g1.z >= 0.f ? acr : 0.f);
-        atomicAdd(v_colors + 3 * (size_t)g + 1, g1.w >= 0.f ? acg : 0.f);
-        atomicAdd(v_colors + 3 * (size_t)g + 2, g2.x >= 0.f ? acb : 0.f);
-        atomicAdd(v_opacities + g, aop * (1.0f - g1.y)); // d alpha / d raw opacity = alpha (1 - opacity), :441
-        return;
-    }
+// per-instance chain rule of the from-world backward: gradients of the 12 tile-local polynomial coefficients ->
+// (vx, vy, w2, gro) -> (mean, quat, scale), then one red.global.add per output
+__device__ __forceinline__ void bwd_chain_rule(const RasterBuffers& rb, const ViewCam& cm_in, const uint32_t g, const uint32_t N,
+                                               const float Xo, const float Yo, const float an0, const float an1,
+                                               const float an2, const float an3, const float an4, const float an5,
+                                               const float ad0, const float ad1, const float ad2, const float ad3,
+                                               const float ad4, const float ad5, const float acr, const float acg,
+                                               const float acb, const float aop, const float* __restrict__ quats,
+                                               const float* __restrict__ scales, const float* __restrict__ means,
+                                               float* __restrict__ v_means, float* __restrict__ v_quats,
+                                               float* __restrict__ v_scales, float* __restrict__ v_colors,
+                                               float* __restrict__ v_opacities) {
     // ---- per-instance chain rule: polynomial coefficients -> (vx, vy, w2, gro) -> (mean, quat, scale)
-    const ViewCam& cm = cams[cam];
+    const ViewCam& cm = cm_in;
     const uint32_t gid = g % N;
     const float4* gp = reinterpret_cast<const float4*>(rb.gauss + g);
     const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1), g2 = __ldg(gp + 2);
@@ -869,6 +757,453 @@ __global__ void __launch_bounds__(kBwdWarps * 32, kMinBlocks)
     atomicAdd(v_opacities + g, aop);
 }
 
+// EWA = fastgs surface: records are 2-D conics (D == 1), outputs are the per-primitive helpers of the reference's
+// blend_backward_cu (kernels_backward.cuh:240-449) passed in the slots v_means -> grad_mean2d [N,2],
+// v_quats -> grad_conic [N,3] (a, b, c; b is the TRUE derivative, twice the reference's stored value),
+// v_colors -> grad_color [N,3], v_opacities -> grad_raw_opacity [N]; quats / scales / means / cams are unused.
+template <bool FUSED, int kBwdWarps, int kMinBlocks, bool EWA = false, bool PK = false>
+__global__ void __launch_bounds__(kBwdWarps * 32, kMinBlocks)
+    k_blend_bwd(const RasterBuffers rb, const ViewCam* __restrict__ cams, const float4* __restrict__ v_pix,
+                const float* __restrict__ quats, const float* __restrict__ scales, const float* __restrict__ means,
+                const uint32_t N, const uint32_t width, const uint32_t height, const uint32_t tile_w,
+                const uint32_t tile_h, const uint32_t n_bucket_cap, const uint32_t* __restrict__ n_buckets_dev,
+                float* __restrict__ v_means, float* __restrict__ v_quats, float* __restrict__ v_scales,
+                float* __restrict__ v_colors, float* __restrict__ v_opacities) {
+    // ring of per-pixel records the lanes read directly (no 9-register rotation): two float4 per pixel,
+    //   ringA = (v_r, v_g, v_b, dx)   ringB = (dy, bits(n_rel), T0, u0)
+    // n_rel = how many instances of THIS bucket the pixel consumed (lane < n_rel <=> the forward evaluated the pair);
+    // T0 = transmittance at the bucket start; u0 = <colour accumulated from this bucket on, v_rgb> - v_alpha term.
+    __shared__ float4 ringA[kBwdWarps][64];
+    __shared__ float4 ringB[kBwdWarps][64];
+    __shared__ uint8_t s_pix[kBwdWarps][kTilePix];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t b = blockIdx.x * kBwdWarps + warp;
+    uint32_t nbk = *n_buckets_dev;
+    nbk = nbk < n_bucket_cap ? nbk : n_bucket_cap;
+    if (b >= nbk)
+        return;
+    const uint32_t n_tiles = tile_w * tile_h;
+    const uint32_t ft = rb.bucket_tile[b];
+    const uint32_t cam = ft / n_tiles, tile = ft - cam * n_tiles;
+    const uint32_t ty = tile / tile_w, tx = tile - ty * tile_w;
+    const int32_t tstart = rb.tile_off[ft], tend = rb.tile_off[ft + 1];
+    const uint32_t local_b = b - rb.bucket_off[ft];
+    if (local_b * kBucket >= rb.tile_max_contrib[ft])
+        return;
+    const uint32_t li = local_b * kBucket + lane; // tile-local instance index of this lane
+    const int32_t inst = tstart + (int32_t)li;
+    const bool valid = inst < tend;
+    const float Xo = (float)(tx * kTile + kTile / 2) - (EWA ? 0.f : cams[cam].cx);
+    const float Yo = (float)(ty * kTile + kTile / 2) - (EWA ? 0.f : cams[cam].cy);
+
+    float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A, Cc = A, E = A;
+    uint32_t g = 0;
+    if (valid) {
+        g = (uint32_t)__ldg(rb.inst_gid + inst);
+        if (EWA) {
+            const float4* gp = reinterpret_cast<const float4*>(rb.gauss + g);
+            expand_record_ewa(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), Xo, Yo, A, B, Cc);
+            E = make_float4(B.z, B.w, Cc.x, Cc.y);
+        } else if (FUSED) {
+            const float4* gp = reinterpret_cast<const float4*>(rb.gauss + g);
+            expand_record(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), Xo, Yo, A, B, Cc);
+            E = __ldg(gp + 3);
+        } else {
+            const float4* rp = reinterpret_cast<const float4*>(rb.inst + inst);
+            A = ld_nc4(rp), B = ld_nc4(rp + 1), Cc = ld_nc4(rp + 2), E = ld_nc4(rp + 3);
+        }
+    }
+
+    // PK: (N', D) coefficient pairs and (dN', dD) accumulator pairs for the FFMA2 form of the loop body
+    const float2 P0 = make_float2(A.x, B.z), P1 = make_float2(A.y, B.w), P2 = make_float2(A.z, Cc.x),
+                 P3 = make_float2(A.w, Cc.y), P4 = make_float2(B.x, Cc.z), P5 = make_float2(B.y, Cc.w);
+    float2 G0 = make_float2(0.f, 0.f), G1 = G0, G2 = G0, G3 = G0, G4 = G0, G5 = G0, GC = G0; // GC = (acr, acg)
+
+    // state that still rotates through the lanes: transmittance before this lane's instance, and
+    // u = <sum_{j >= this instance} c_j alpha_j T_j, v_rgb> - v_alpha_term   (one scalar instead of 3 + 1)
+    float T = 0.f, u = 0.f;
+    // per-instance accumulators
+    float an0 = 0.f, an1 = 0.f, an2 = 0.f, an3 = 0.f, an4 = 0.f, an5 = 0.f;
+    float ad0 = 0.f, ad1 = 0.f, ad2 = 0.f, ad3 = 0.f, ad4 = 0.f, ad5 = 0.f;
+    float aop = 0.f, acr = 0.f, acg = 0.f, acb = 0.f;
+
+    const float4* ck = rb.ckpt + (size_t)b * kTilePix;
+
+    // compact list of the tile's pixels that reach this bucket (n_contrib > first instance of the bucket):
+    // late buckets are reached by few pixels, so the rotation below runs m + 31 instead of 256 + 31 steps
+    int m = 0;
+    {
+        const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+        for (int rr = 0; rr < kTilePix / 32; ++rr) {
+            const int p = rr * 32 + lane;
+            const uint32_t px = tx * kTile + (p & 15), py = ty * kTile + (p >> 4);
+            bool kp = false;
+            if (px < width && py < height)
+                kp = (uint32_t)__ldg(rb.n_contrib + ((size_t)cam * height + py) * width + px) > local_b * kBucket;
+            const uint32_t mask = __ballot_sync(0xffffffffu, kp);
+            if (kp)
+                s_pix[warp][m + __popc(mask & lt)] = (uint8_t)p;
+            m += __popc(mask);
+        }
+        __syncwarp();
+    }
+
+    const int ilane = lane;
+    for (int i = 0; i < m + 31; ++i) {
+        if ((i & 31) == 0 && i < m) { // stage the next 32 pixels of the list into the ring half (i & 32)
+            __syncwarp();
+            float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a4;
+            if (i + lane < m) {
+                const int p = s_pix[warp][i + lane];
+                const uint32_t px = tx * kTile + (p & 15), py = ty * kTile + (p >> 4);
+                const size_t pix = ((size_t)cam * height + py) * width + px;
+                const int32_t nrel = __ldg(rb.n_contrib + pix) - (int32_t)(local_b * kBucket);
+                const float4 c4 = ld_nc4(ck + p);
+                const float4 f4 = __ldg(rb.pix_state + pix);
+                const float4 v4 = __ldg(v_pix + pix);
+                const float u0 = fmaf(f4.x - c4.x, v4.x, fmaf(f4.y - c4.y, v4.y, fmaf(f4.z - c4.z, v4.z, -v4.w)));
+                a4 = make_float4(v4.x, v4.y, v4.z, (float)(p & 15) - 7.5f);
+                b4 = make_float4((float)(p >> 4) - 7.5f, __int_as_float(nrel), c4.w, u0);
+            }
+            ringA[warp][(i + lane) & 63] = a4;
+            ringB[warp][(i + lane) & 63] = b4;
+            __syncwarp();
+        }
+        const int idx = i - ilane; // position in the compact list of the pixel currently at this lane
+        const float4 ea = ringA[warp][idx & 63], eb = ringB[warp][idx & 63];
+        T = __shfl_up_sync(0xffffffffu, T, 1);
+        u = __shfl_up_sync(0xffffffffu, u, 1);
+        if (lane == 0) {
+            T = eb.z;
+            u = eb.w;
+        }
+        const bool active = valid && (uint32_t)idx < (uint32_t)m && ilane < __float_as_int(eb.y);
+        if (!active)
+            continue;
+        const float dx = ea.w, dy = eb.x;
+        float Nv, rD = 1.f, p2;
+        float2 DX, DY;
+        if (PK && !EWA) {
+            DX = make_float2(dx, dx), DY = make_float2(dy, dy);
+            const float2 ND = poly2x2(DX, DY, P0, P1, P2, P3, P4, P5);
+            Nv = ND.x;
+            rD = rcp_approx(ND.y);
+            p2 = Nv * rD;
+        } else {
+            Nv = poly2(dx, dy, A.x, A.y, A.z, A.w, B.x, B.y);
+            p2 = Nv;
+            if (EWA) {
+                if (Nv > 0.f) // sigma/2 < 0 is skipped (kernels_backward.cuh:391-392)
+                    continue;
+            } else {
+                const float Dv = poly2(dx, dy, B.z, B.w, Cc.x, Cc.y, Cc.z, Cc.w);
+                rD = rcp_approx(Dv);
+                p2 = Nv * rD;
+            }
+        }
+        const float vis = ex2_approx(p2);
+        const float a_raw = E.x * vis;
+        const float alpha = fminf(kAlphaMax, a_raw);
+        if (alpha < kAlphaMin)
+            continue;
+        const float w = T * alpha;
+        if (PK && !EWA) {
+            GC = ffma2(make_float2(w, w), make_float2(ea.x, ea.y), GC);
+        } else {
+            acr = fmaf(w, ea.x, acr);
+            acg = fmaf(w, ea.y, acg);
+        }
+        acb = fmaf(w, ea.z, acb);
+        const float Ev = fmaf(E.y, ea.x, fmaf(E.z, ea.y, E.w * ea.z)); // <c_i, v_rgb>
+        u = fmaf(-w, Ev, u);                                           // now the sum over j > i
+        const float om = 1.0f - alpha;                                 // >= 0.001: plain rcp is safe
+        const float v_alpha = fmaf(T, Ev, -u * rcp_approx(om));
+        if (EWA) {
+            // the reference differentiates through the clamped alpha as if it were not clamped (:418-427)
+            aop = fmaf(alpha, v_alpha, aop);
+            const float vN = v_alpha * alpha * kLn2;
+            const float dxx = dx * dx, dxy = dx * dy, dyy = dy * dy;
+            an0 += vN;
+            an1 = fmaf(vN, dx, an1);
+            an2 = fmaf(vN, dy, an2);
+            an3 = fmaf(vN, dxx, an3);
+            an4 = fmaf(vN, dxy, an4);
+            an5 = fmaf(vN, dyy, an5);
+        } else if (PK && a_raw <= kAlphaMax) {
+            aop = fmaf(vis, v_alpha, aop);
+            const float vN = v_alpha * a_raw * kLn2 * rD;
+            const float2 V = make_float2(vN, -vN * p2);
+            G0.x += V.x, G0.y += V.y;
+            G1 = ffma2(V, DX, G1);
+            G2 = ffma2(V, DY, G2);
+            G3 = ffma2(V, fmul2(DX, DX), G3);
+            G4 = ffma2(V, fmul2(DX, DY), G4);
+            G5 = ffma2(V, fmul2(DY, DY), G5);
+        } else if (a_raw <= kAlphaMax) {
+            aop = fmaf(vis, v_alpha, aop);
+            const float vN = v_alpha * a_raw * kLn2 * rD;
+            const float vD = -vN * p2;
+            const float dxx = dx * dx, dxy = dx * dy, dyy = dy * dy;
+            an0 += vN;
+            an1 = fmaf(vN, dx, an1);
+            an2 = fmaf(vN, dy, an2);
+            an3 = fmaf(vN, dxx, an3);
+            an4 = fmaf(vN, dxy, an4);
+            an5 = fmaf(vN, dyy, an5);
+            ad0 += vD;
+            ad1 = fmaf(vD, dx, ad1);
+            ad2 = fmaf(vD, dy, ad2);
+            ad3 = fmaf(vD, dxx, ad3);
+            ad4 = fmaf(vD, dxy, ad4);
+            ad5 = fmaf(vD, dyy, ad5);
+        }
+        T *= om;
+    }
+
+    if (PK && !EWA) {
+        an0 = G0.x, ad0 = G0.y, an1 = G1.x, ad1 = G1.y, an2 = G2.x, ad2 = G2.y;
+        an3 = G3.x, ad3 = G3.y, an4 = G4.x, ad4 = G4.y, an5 = G5.x, ad5 = G5.y;
+        acr = GC.x, acg = GC.y;
+    }
+    if (!valid)
+        return;
+    if (EWA) {
+        // ---- polynomial-coefficient gradients -> (conic, mean2d); e = mean2d - tile centre
+        const float4* gp = reinterpret_cast<const float4*>(rb.gauss + g);
+        const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1), g2 = __ldg(gp + 2);
+        const float ex = g0.x - Xo, ey = g0.y - Yo, a = g0.z, b = g0.w, c = g1.x;
+        const float v_a = kEScale * (0.5f * ex * ex * an0 - ex * an1 + 0.5f * an3);
+        const float v_b = kEScale * (ex * ey * an0 - ey * an1 - ex * an2 + an4);
+        const float v_c = kEScale * (0.5f * ey * ey * an0 - ey * an2 + 0.5f * an5);
+        const float v_ex = kEScale * ((a * ex + b * ey) * an0 - a * an1 - b * an2);
+        const float v_ey = kEScale * ((c * ey + b * ex) * an0 - b * an1 - c * an2);
+        atomicAdd(v_means + 2 * (size_t)g, v_ex);
+        atomicAdd(v_means + 2 * (size_t)g + 1, v_ey);
+        atomicAdd(v_quats + 3 * (size_t)g, v_a);
+        atomicAdd(v_quats + 3 * (size_t)g + 1, v_b);
+        atomicAdd(v_quats + 3 * (size_t)g + 2, v_c);
+        // colour: gradient passes where the unclamped colour is >= 0 (color_grad_factor, :304-309)
+        atomicAdd(v_colors + 3 * (size_t)g, g1.z >= 0.f ? acr : 0.f);
+        atomicAdd(v_colors + 3 * (size_t)g + 1, g1.w >= 0.f ? acg : 0.f);
+        atomicAdd(v_colors + 3 * (size_t)g + 2, g2.x >= 0.f ? acb : 0.f);
+        atomicAdd(v_opacities + g, aop * (1.0f - g1.y)); // d alpha / d raw opacity = alpha (1 - opacity), :441
+        return;
+    }
+    bwd_chain_rule(rb, cams[cam], g, N, Xo, Yo, an0, an1, an2, an3, an4, an5, ad0, ad1, ad2, ad3, ad4, ad5, acr, acg, acb, aop,
+                   quats, scales, means, v_means, v_quats, v_scales, v_colors, v_opacities);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// backward blend, software-pipelined (the default): same algorithm, same arithmetic (bit-identical alphas), but
+//   * the alpha of step i+1 (ring loads, FFMA2 polynomial chain, rcp, ex2) is issued BEFORE the transmittance / suffix
+//     chain of step i: the two dependency chains of a step (about 100 cycles each) overlap inside one warp instead of
+//     running back to back (measured before: 0.6 instructions per clock and scheduler at 4 warps each, 142 clocks per
+//     step; profiles/r02_bucket_stats_c3.json),
+//   * the loop is unrolled by two with alternating register sets, so the hand-over costs no moves,
+//   * (N', D) are evaluated and accumulated as FFMA2 pairs.
+// ------------------------------------------------------------------------------------------------------
+struct BwdEval { // everything the chain / gradient half of a step needs, produced one step ahead
+    float vr, vg, vb, dx, dy; // pixel data
+    float T0, u0;             // lane 0 only: state entering the bucket
+    float a_raw, vis, p2, rD; // opacity * vis (unclamped), vis, N'/D, 1/D
+    bool pass;                // the forward evaluated this pair and alpha >= 1/255
+};
+
+template <bool EWA, int kBwdWarps>
+__global__ void __launch_bounds__(kBwdWarps * 32)
+    k_blend_bwd_sp(const RasterBuffers rb, const ViewCam* __restrict__ cams, const float4* __restrict__ v_pix,
+                   const float* __restrict__ quats, const float* __restrict__ scales, const float* __restrict__ means,
+                   const uint32_t N, const uint32_t width, const uint32_t height, const uint32_t tile_w,
+                   const uint32_t tile_h, const uint32_t n_bucket_cap, const uint32_t* __restrict__ n_buckets_dev,
+                   float* __restrict__ v_means, float* __restrict__ v_quats, float* __restrict__ v_scales,
+                   float* __restrict__ v_colors, float* __restrict__ v_opacities) {
+    __shared__ float4 ringA[kBwdWarps][64]; // (v_r, v_g, v_b, dx)
+    __shared__ float4 ringB[kBwdWarps][64]; // (dy, bits(n_rel), T0, u0)
+    __shared__ uint8_t s_pix[kBwdWarps][kTilePix];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t b = blockIdx.x * kBwdWarps + warp;
+    uint32_t nbk = *n_buckets_dev;
+    nbk = nbk < n_bucket_cap ? nbk : n_bucket_cap;
+    if (b >= nbk)
+        return;
+    const uint32_t n_tiles = tile_w * tile_h;
+    const uint32_t ft = rb.bucket_tile[b];
+    const uint32_t cam = ft / n_tiles, tile = ft - cam * n_tiles;
+    const uint32_t ty = tile / tile_w, tx = tile - ty * tile_w;
+    const int32_t tstart = rb.tile_off[ft], tend = rb.tile_off[ft + 1];
+    const uint32_t local_b = b - rb.bucket_off[ft];
+    if (local_b * kBucket >= rb.tile_max_contrib[ft])
+        return;
+    const uint32_t li = local_b * kBucket + lane;
+    const int32_t inst = tstart + (int32_t)li;
+    const bool valid = inst < tend;
+    const float Xo = (float)(tx * kTile + kTile / 2) - (EWA ? 0.f : cams[cam].cx);
+    const float Yo = (float)(ty * kTile + kTile / 2) - (EWA ? 0.f : cams[cam].cy);
+
+    float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A, Cc = A, E = A;
+    uint32_t g = 0;
+    if (valid) {
+        g = (uint32_t)__ldg(rb.inst_gid + inst);
+        const float4* gp = reinterpret_cast<const float4*>(rb.gauss + g);
+        if (EWA) {
+            expand_record_ewa(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), Xo, Yo, A, B, Cc);
+            E = make_float4(B.z, B.w, Cc.x, Cc.y);
+        } else {
+            expand_record(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), Xo, Yo, A, B, Cc);
+            E = __ldg(gp + 3);
+        }
+    }
+    // (N', D) coefficient pairs; EWA: D == 1 (second components unused)
+    const float2 P0 = make_float2(A.x, EWA ? 1.f : B.z), P1 = make_float2(A.y, EWA ? 0.f : B.w),
+                 P2 = make_float2(A.z, EWA ? 0.f : Cc.x), P3 = make_float2(A.w, EWA ? 0.f : Cc.y),
+                 P4 = make_float2(B.x, EWA ? 0.f : Cc.z), P5 = make_float2(B.y, EWA ? 0.f : Cc.w);
+    float2 G0 = make_float2(0.f, 0.f), G1 = G0, G2 = G0, G3 = G0, G4 = G0, G5 = G0, GC = G0; // (dN', dD) and (r, g)
+    float acb = 0.f, aop = 0.f;
+    float T = 0.f, u = 0.f;
+
+    const float4* ck = rb.ckpt + (size_t)b * kTilePix;
+    int m = 0;
+    {
+        const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+        for (int rr = 0; rr < kTilePix / 32; ++rr) {
+            const int p = rr * 32 + lane;
+            const uint32_t px = tx * kTile + (p & 15), py = ty * kTile + (p >> 4);
+            bool kp = false;
+            if (px < width && py < height)
+                kp = (uint32_t)__ldg(rb.n_contrib + ((size_t)cam * height + py) * width + px) > local_b * kBucket;
+            const uint32_t mask = __ballot_sync(0xffffffffu, kp);
+            if (kp)
+                s_pix[warp][m + __popc(mask & lt)] = (uint8_t)p;
+            m += __popc(mask);
+        }
+        __syncwarp();
+    }
+    // stage list positions [i0, i0 + 32) into the ring
+    auto stage = [&](const int i0) {
+        __syncwarp(); // every lane is done reading the entries that are about to be replaced
+        float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a4;
+        if (i0 + lane < m) {
+            const int p = s_pix[warp][i0 + lane];
+            const uint32_t px = tx * kTile + (p & 15), py = ty * kTile + (p >> 4);
+            const size_t pix = ((size_t)cam * height + py) * width + px;
+            const int32_t nrel = __ldg(rb.n_contrib + pix) - (int32_t)(local_b * kBucket);
+            const float4 c4 = ld_nc4(ck + p);
+            const float4 f4 = __ldg(rb.pix_state + pix);
+            const float4 v4 = __ldg(v_pix + pix);
+            const float u0 = fmaf(f4.x - c4.x, v4.x, fmaf(f4.y - c4.y, v4.y, fmaf(f4.z - c4.z, v4.z, -v4.w)));
+            a4 = make_float4(v4.x, v4.y, v4.z, (float)(p & 15) - 7.5f);
+            b4 = make_float4((float)(p >> 4) - 7.5f, __int_as_float(nrel), c4.w, u0);
+        }
+        ringA[warp][(i0 + lane) & 63] = a4;
+        ringB[warp][(i0 + lane) & 63] = b4;
+        __syncwarp();
+    };
+    // the alpha half of step i for this lane (list position i - lane)
+    auto eval = [&](const int i, BwdEval& e) {
+        const int idx = i - lane;
+        const float4 ea = ringA[warp][idx & 63], eb = ringB[warp][idx & 63];
+        e.vr = ea.x, e.vg = ea.y, e.vb = ea.z, e.dx = ea.w, e.dy = eb.x, e.T0 = eb.z, e.u0 = eb.w;
+        const bool act = valid && (uint32_t)idx < (uint32_t)m && lane < __float_as_int(eb.y);
+        const float2 ND = poly2x2(make_float2(e.dx, e.dx), make_float2(e.dy, e.dy), P0, P1, P2, P3, P4, P5);
+        bool ok = act;
+        if (EWA) {
+            e.rD = 1.f;
+            e.p2 = ND.x;
+            ok = ok && ND.x <= 0.f; // sigma/2 < 0 is skipped (kernels_backward.cuh:391-392)
+        } else {
+            e.rD = rcp_approx(ND.y);
+            e.p2 = ND.x * e.rD;
+        }
+        e.vis = ex2_approx(e.p2);
+        e.a_raw = E.x * e.vis;
+        e.pass = ok && fminf(kAlphaMax, e.a_raw) >= kAlphaMin;
+    };
+    // the chain + gradient half.  Branch-free: a pair that does not contribute runs with alpha = 0 and zero gradient
+    // weights (selects, not multiplications: its vis / p2 may be garbage), so the whole step is ONE basic block and the
+    // scheduler can interleave this half with the alpha half of the next step.
+    auto chain = [&](const BwdEval& e) {
+        T = __shfl_up_sync(0xffffffffu, T, 1);
+        u = __shfl_up_sync(0xffffffffu, u, 1);
+        if (lane == 0) {
+            T = e.T0;
+            u = e.u0;
+        }
+        const float alpha = e.pass ? fminf(kAlphaMax, e.a_raw) : 0.f;
+        const float w = T * alpha;
+        GC = ffma2(make_float2(w, w), make_float2(e.vr, e.vg), GC);
+        acb = fmaf(w, e.vb, acb);
+        const float Ev = fmaf(E.y, e.vr, fmaf(E.z, e.vg, E.w * e.vb)); // <c_i, v_rgb>
+        u = fmaf(-w, Ev, u);                                           // now the sum over j > i
+        const float om = 1.0f - alpha;                                 // >= 0.001: plain rcp is safe
+        const float v_alpha = fmaf(T, Ev, -u * rcp_approx(om));
+        T *= om;
+        // EWA: the reference differentiates through the clamped alpha as if it were not clamped (:418-427);
+        // from-world: no geometry / opacity gradient through a clamped alpha (...Bwd.cu:318)
+        const bool grad = EWA ? e.pass : (e.pass && e.a_raw <= kAlphaMax);
+        const float vo = (EWA ? alpha : e.vis) * v_alpha;
+        aop += grad ? vo : 0.f;
+        const float vN = EWA ? v_alpha * alpha * kLn2 : v_alpha * e.a_raw * kLn2 * e.rD;
+        const float2 V = grad ? make_float2(vN, -vN * e.p2) : make_float2(0.f, 0.f);
+        const float2 DX = make_float2(e.dx, e.dx), DY = make_float2(e.dy, e.dy);
+        G0.x += V.x, G0.y += V.y;
+        G1 = ffma2(V, DX, G1);
+        G2 = ffma2(V, DY, G2);
+        G3 = ffma2(V, fmul2(DX, DX), G3);
+        G4 = ffma2(V, fmul2(DX, DY), G4);
+        G5 = ffma2(V, fmul2(DY, DY), G5);
+    };
+
+    const int total = m + 31;
+    BwdEval ea_, eb_;
+    stage(0);
+    eval(0, ea_);
+    for (int i = 0; i < total; i += 2) {
+        // ---- step i: prefetch i+1 into eb_, then chain on ea_
+        if (((i + 1) & 31) == 0 && i + 1 < m)
+            stage(i + 1);
+        eval(i + 1, eb_);
+        chain(ea_);
+        if (i + 1 >= total)
+            break;
+        // ---- step i+1: prefetch i+2 into ea_, then chain on eb_
+        if (((i + 2) & 31) == 0 && i + 2 < m)
+            stage(i + 2);
+        eval(i + 2, ea_);
+        chain(eb_);
+    }
+
+    if (!valid)
+        return;
+    const float an0 = G0.x, an1 = G1.x, an2 = G2.x, an3 = G3.x, an4 = G4.x, an5 = G5.x;
+    const float ad0 = G0.y, ad1 = G1.y, ad2 = G2.y, ad3 = G3.y, ad4 = G4.y, ad5 = G5.y;
+    const float acr = GC.x, acg = GC.y;
+    if (EWA) {
+        // ---- polynomial-coefficient gradients -> (conic, mean2d); e = mean2d - tile centre
+        const float4* gp = reinterpret_cast<const float4*>(rb.gauss + g);
+        const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1), g2 = __ldg(gp + 2);
+        const float ex = g0.x - Xo, ey = g0.y - Yo, a = g0.z, b_ = g0.w, c = g1.x;
+        const float v_a = kEScale * (0.5f * ex * ex * an0 - ex * an1 + 0.5f * an3);
+        const float v_b = kEScale * (ex * ey * an0 - ey * an1 - ex * an2 + an4);
+        const float v_c = kEScale * (0.5f * ey * ey * an0 - ey * an2 + 0.5f * an5);
+        const float v_ex = kEScale * ((a * ex + b_ * ey) * an0 - a * an1 - b_ * an2);
+        const float v_ey = kEScale * ((c * ey + b_ * ex) * an0 - b_ * an1 - c * an2);
+        atomicAdd(v_means + 2 * (size_t)g, v_ex);
+        atomicAdd(v_means + 2 * (size_t)g + 1, v_ey);
+        atomicAdd(v_quats + 3 * (size_t)g, v_a);
+        atomicAdd(v_quats + 3 * (size_t)g + 1, v_b);
+        atomicAdd(v_quats + 3 * (size_t)g + 2, v_c);
+        atomicAdd(v_colors + 3 * (size_t)g, g1.z >= 0.f ? acr : 0.f);
+        atomicAdd(v_colors + 3 * (size_t)g + 1, g1.w >= 0.f ? acg : 0.f);
+        atomicAdd(v_colors + 3 * (size_t)g + 2, g2.x >= 0.f ? acb : 0.f);
+        atomicAdd(v_opacities + g, aop * (1.0f - g1.y));
+        return;
+    }
+    bwd_chain_rule(rb, cams[cam], g, N, Xo, Yo, an0, an1, an2, an3, an4, an5, ad0, ad1, ad2, ad3, ad4, ad5, acr, acg, acb, aop,
+                   quats, scales, means, v_means, v_quats, v_scales, v_colors, v_opacities);
+}
+
 int launch_blend_bwd(const RasterBuffers& rb, const ViewCam* cams_dev, const float4* v_pix, const float* quats,
                      const float* scales, const float* means, uint32_t C, uint32_t N, uint32_t width, uint32_t height,
                      uint32_t tile_w, uint32_t tile_h, uint32_t n_bucket_cap, const uint32_t* n_buckets_dev,
@@ -892,6 +1227,14 @@ int launch_blend_bwd(const RasterBuffers& rb, const ViewCam* cams_dev, const flo
         LFS_BWD_LAUNCH(true, 1, 32);
     } else if (variant == 4) {
         LFS_BWD_LAUNCH(true, 2, 1);
+    } else if (variant == 6) { // software-pipelined + FFMA2
+        k_blend_bwd_sp<false, 4><<<div_up(n_bucket_cap, 4), 4 * 32, 0, stream>>>(
+            rb, cams_dev, v_pix, quats, scales, means, N, width, height, tile_w, tile_h, n_bucket_cap, n_buckets_dev,
+            v_means, v_quats, v_scales, v_colors, v_opacities);
+    } else if (variant == 5) { // FFMA2 body
+        k_blend_bwd<true, 4, 1, false, true><<<div_up(n_bucket_cap, 4), 4 * 32, 0, stream>>>(
+            rb, cams_dev, v_pix, quats, scales, means, N, width, height, tile_w, tile_h, n_bucket_cap, n_buckets_dev,
+            v_means, v_quats, v_scales, v_colors, v_opacities);
     } else {
         LFS_BWD_LAUNCH(true, 4, 1);
     }

@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(256)
     k_prep_gaussians(const float* __restrict__ means, const float* __restrict__ quats,
                      const float* __restrict__ scales, const float* __restrict__ colors,
                      const float* __restrict__ opacities, const ViewCam* __restrict__ cams, const uint32_t N,
-                     const uint32_t total, GaussRec* __restrict__ out) {
+                     const uint32_t total, const uint32_t channels, const uint32_t ch0, GaussRec* __restrict__ out) {
     const uint32_t idx = blockIdx.x * 256 + threadIdx.x;
     if (idx >= total)
         return;
@@ -51,8 +51,43 @@ __global__ void __launch_bounds__(256)
     o[0] = make_float4(vx.x, vx.y, vx.z, vy.x);
     o[1] = make_float4(vy.y, vy.z, w2.x, w2.y);
     o[2] = make_float4(w2.z, gro.x, gro.y, gro.z);
-    o[3] = make_float4(__ldg(opacities + idx), __ldg(colors + 3 * (size_t)idx), __ldg(colors + 3 * (size_t)idx + 1),
-                       __ldg(colors + 3 * (size_t)idx + 2));
+    // colour channels [ch0, ch0 + 3) of the `channels` of this pair (zero padded): channel counts other than 3 run as
+    // ceil(channels / 3) passes of the same 3-channel blend, which is exact because the blend is linear in the colours
+    const float* cp = colors + (size_t)idx * channels + ch0;
+    o[3] = make_float4(__ldg(opacities + idx), __ldg(cp), ch0 + 1 < channels ? __ldg(cp + 1) : 0.f,
+                       ch0 + 2 < channels ? __ldg(cp + 2) : 0.f);
+}
+
+// one channel group of the blend state -> renders [C,H,W,channels] (+ T * background)
+__global__ void __launch_bounds__(256)
+    k_export_group(const float4* __restrict__ pix_state, const float* __restrict__ backgrounds, const uint32_t hw,
+                   const uint32_t total, const uint32_t channels, const uint32_t ch0, float* __restrict__ renders) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= total)
+        return;
+    const float4 st = pix_state[i];
+    const float v[3] = {st.x, st.y, st.z};
+    const uint32_t cam = i / hw;
+#pragma unroll
+    for (uint32_t k = 0; k < 3; ++k)
+        if (ch0 + k < channels)
+            renders[(size_t)i * channels + ch0 + k] =
+                backgrounds ? fmaf(st.w, backgrounds[(size_t)cam * channels + ch0 + k], v[k]) : v[k];
+}
+
+// v_colors of one channel group [C*N,3] -> v_colors [C,N,channels]; clears the group buffer for the next pass
+__global__ void __launch_bounds__(256)
+    k_scatter_vcolors(float* __restrict__ group, const uint32_t total, const uint32_t channels, const uint32_t ch0,
+                      float* __restrict__ v_colors) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= total)
+        return;
+#pragma unroll
+    for (uint32_t k = 0; k < 3; ++k) {
+        if (ch0 + k < channels)
+            v_colors[(size_t)i * channels + ch0 + k] = group[3 * (size_t)i + k];
+        group[3 * (size_t)i + k] = 0.f;
+    }
 }
 
 __global__ void k_copy_offsets(const int32_t* __restrict__ src, uint32_t n, int32_t last, int32_t* __restrict__ dst) {
@@ -67,15 +102,16 @@ __global__ void k_copy_offsets(const int32_t* __restrict__ src, uint32_t n, int3
 __global__ void __launch_bounds__(256)
     k_pack_vpix(const float* __restrict__ v_colors, const float* __restrict__ v_alphas,
                 const float4* __restrict__ pix_state, const float* __restrict__ backgrounds, const uint32_t hw,
-                const uint32_t total, float4* __restrict__ v_pix) {
+                const uint32_t total, const uint32_t channels, const uint32_t ch0, float4* __restrict__ v_pix) {
     const uint32_t i = blockIdx.x * 256 + threadIdx.x;
     if (i >= total)
         return;
-    const float r = v_colors[3 * (size_t)i], g = v_colors[3 * (size_t)i + 1], b = v_colors[3 * (size_t)i + 2];
-    float va = v_alphas[i];
+    const float* vp = v_colors + (size_t)i * channels + ch0;
+    const float r = vp[0], g = ch0 + 1 < channels ? vp[1] : 0.f, b = ch0 + 2 < channels ? vp[2] : 0.f;
+    float va = ch0 == 0 ? v_alphas[i] : 0.f; // the alpha gradient belongs to the first channel group only
     if (backgrounds) {
-        const uint32_t cam = i / hw;
-        va -= backgrounds[3 * cam] * r + backgrounds[3 * cam + 1] * g + backgrounds[3 * cam + 2] * b;
+        const float* bp = backgrounds + (size_t)(i / hw) * channels + ch0;
+        va -= bp[0] * r + (ch0 + 1 < channels ? bp[1] * g : 0.f) + (ch0 + 2 < channels ? bp[2] * b : 0.f);
     }
     v_pix[i] = make_float4(r, g, b, pix_state[i].w * va);
 }
@@ -94,18 +130,19 @@ struct RasterScratch {
     float4* pix_state;
     int32_t* n_contrib;
     float4* v_pix;
+    float* v_colors_group; // [C*N,3] gradient of one channel group (channels != 3)
     void* scan_scratch;
     size_t bytes;
 };
 
 static RasterScratch carve_scratch(void* blob, uint32_t C, uint32_t N, uint32_t n_tiles_total, uint64_t n_isects,
-                                   uint64_t n_pix, bool bwd) {
+                                   uint64_t n_pix, bool bwd, uint32_t channels = 3) {
     Carver c(blob);
     RasterScratch s;
     s.cams = c.take<ViewCam>(C);
     s.gauss = c.take<GaussRec>((size_t)C * N);
     s.tile_off = c.take<int32_t>(n_tiles_total + 1);
-    s.inst = c.take<InstRec>(n_isects ? n_isects : 1);
+    s.inst = raster_options().fuse_expand ? nullptr : c.take<InstRec>(n_isects ? n_isects : 1); // unused when fused
     s.bucket_off = c.take<uint32_t>(n_tiles_total + 1);
     s.counts_tmp = c.take<uint32_t>(n_tiles_total + 1);
     s.n_buckets = c.take<uint32_t>(4);
@@ -118,10 +155,12 @@ static RasterScratch carve_scratch(void* blob, uint32_t C, uint32_t N, uint32_t 
         s.bucket_tile = c.take<uint32_t>(n_bucket_cap);
         s.ckpt = c.take<float4>(n_bucket_cap * kTilePix);
         s.v_pix = c.take<float4>(n_pix);
+        s.v_colors_group = channels != 3 ? c.take<float>(3 * (size_t)C * N) : nullptr;
     } else {
         s.bucket_tile = nullptr;
         s.ckpt = nullptr;
         s.v_pix = nullptr;
+        s.v_colors_group = nullptr;
     }
     s.bytes = c.total();
     return s;
@@ -141,13 +180,13 @@ static int raster_front(const RasterScratch& s, RasterBuffers& rb, const float* 
                         const float* scales, const float* colors, const float* opacities, uint32_t N, uint32_t C,
                         uint32_t width, uint32_t height, const float* viewmats, const float* Ks,
                         const int32_t* tile_offsets, const int32_t* flatten_ids, int64_t n_isects, bool bwd,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, uint32_t channels = 3, uint32_t ch0 = 0) {
     const uint32_t tile_w = (width + kTile - 1) / kTile, tile_h = (height + kTile - 1) / kTile;
     const uint32_t n_tiles = tile_w * tile_h, n_tiles_total = C * n_tiles;
     k_make_cams<<<div_up(C, 32), 32, 0, stream>>>(viewmats, Ks, C, (int)width, (int)height, s.cams);
     LFS_LAUNCH_OK("k_make_cams");
     k_prep_gaussians<<<div_up((uint64_t)C * N, 256), 256, 0, stream>>>(means, quats, scales, colors, opacities, s.cams, N,
-                                                                       C * N, s.gauss);
+                                                                       C * N, channels, ch0, s.gauss);
     LFS_LAUNCH_OK("k_prep_gaussians");
     k_copy_offsets<<<div_up(n_tiles_total + 1, 256), 256, 0, stream>>>(tile_offsets, n_tiles_total, (int32_t)n_isects,
                                                                        s.tile_off);
@@ -195,7 +234,7 @@ extern "C" int lfs_rasterize_to_pixels_from_world_3dgs_fwd(
                       alphas && last_ids && alloc,
                   "rasterize_fwd: null required pointer");
     LFS_CHECK_ARG(n_isects == 0 || flatten_ids, "rasterize_fwd: flatten_ids is null");
-    LFS_UNSUPPORTED(channels != 3, "rasterize_fwd: channels=%u not implemented (3 only)", channels);
+    LFS_CHECK_ARG(channels >= 1 && channels <= 513, "rasterize_fwd: channels=%u out of range", channels);
     int rc = check_common(tile_size, camera_model, rs_type, viewmats1, radial_coeffs, tangential_coeffs,
                           thin_prism_coeffs, "rasterize_fwd");
     if (rc)
@@ -214,17 +253,34 @@ extern "C" int lfs_rasterize_to_pixels_from_world_3dgs_fwd(
     }
     RasterScratch s = carve_scratch(blob, C, N, n_tiles_total, (uint64_t)n_isects, n_pix, false);
     RasterBuffers rb{};
-    rc = raster_front(s, rb, means, quats, scales, colors, opacities, N, C, image_width, image_height, viewmats0, Ks,
-                      tile_offsets, flatten_ids, n_isects, false, stream);
-    if (rc)
-        return rc;
-    return launch_blend_fwd(rb, s.cams, C, image_width, image_height, tile_w, tile_h, false, backgrounds, masks, renders, alphas,
-                            last_ids, stream);
+    if (channels == 3) {
+        rc = raster_front(s, rb, means, quats, scales, colors, opacities, N, C, image_width, image_height, viewmats0, Ks,
+                          tile_offsets, flatten_ids, n_isects, false, stream);
+        if (rc)
+            return rc;
+        return launch_blend_fwd(rb, s.cams, C, image_width, image_height, tile_w, tile_h, false, backgrounds, masks, renders,
+                                alphas, last_ids, stream);
+    }
+    // any other channel count (gsplat/Rasterization.cpp:106-128 instantiates 1..513): groups of three channels
+    for (uint32_t ch0 = 0; ch0 < channels; ch0 += 3) {
+        rc = raster_front(s, rb, means, quats, scales, colors, opacities, N, C, image_width, image_height, viewmats0, Ks,
+                          tile_offsets, flatten_ids, n_isects, false, stream, channels, ch0);
+        if (rc)
+            return rc;
+        rc = launch_blend_fwd(rb, s.cams, C, image_width, image_height, tile_w, tile_h, false, nullptr, masks, nullptr,
+                              ch0 == 0 ? alphas : nullptr, ch0 == 0 ? last_ids : nullptr, stream);
+        if (rc)
+            return rc;
+        k_export_group<<<div_up(n_pix, 256), 256, 0, stream>>>(s.pix_state, backgrounds, image_width * image_height,
+                                                               (uint32_t)n_pix, channels, ch0, renders);
+        LFS_LAUNCH_OK("k_export_group");
+    }
+    return LFS_OK;
 }
 
 extern "C" int lfs_rasterize_to_pixels_from_world_3dgs_bwd(
     const float* means, const float* quats, const float* scales, const float* colors, const float* opacities,
-    const float* backgrounds, const uint8_t* masks, uint32_t N, uint32_t C, uint32_t image_width,
+    const float* backgrounds, const uint8_t* masks, uint32_t N, uint32_t C, uint32_t channels, uint32_t image_width,
     uint32_t image_height, uint32_t tile_size, const float* viewmats0, const float* viewmats1, const float* Ks,
     int camera_model, const lfs_ut_params* ut_params, int rs_type, const float* radial_coeffs,
     const float* tangential_coeffs, const float* thin_prism_coeffs, const int32_t* tile_offsets,
@@ -247,7 +303,8 @@ extern "C" int lfs_rasterize_to_pixels_from_world_3dgs_bwd(
     LFS_CUDA_OK(cudaMemsetAsync(v_means, 0, sizeof(float) * 3 * (size_t)N, stream));
     LFS_CUDA_OK(cudaMemsetAsync(v_quats, 0, sizeof(float) * 4 * (size_t)N, stream));
     LFS_CUDA_OK(cudaMemsetAsync(v_scales, 0, sizeof(float) * 3 * (size_t)N, stream));
-    LFS_CUDA_OK(cudaMemsetAsync(v_colors, 0, sizeof(float) * 3 * (size_t)C * N, stream));
+    LFS_CHECK_ARG(channels >= 1 && channels <= 513, "rasterize_bwd: channels=%u out of range", channels);
+    LFS_CUDA_OK(cudaMemsetAsync(v_colors, 0, sizeof(float) * channels * (size_t)C * N, stream));
     LFS_CUDA_OK(cudaMemsetAsync(v_opacities, 0, sizeof(float) * (size_t)C * N, stream));
     if (C == 0 || N == 0 || n_isects <= 0 || image_width == 0 || image_height == 0)
         return LFS_OK; // reference: kernel launch skipped when n_isects == 0 (…Bwd.cu:434-437)
@@ -255,26 +312,42 @@ extern "C" int lfs_rasterize_to_pixels_from_world_3dgs_bwd(
     const uint32_t tile_w = (image_width + kTile - 1) / kTile, tile_h = (image_height + kTile - 1) / kTile;
     const uint32_t n_tiles_total = C * tile_w * tile_h;
     const uint64_t n_pix = (uint64_t)C * image_width * image_height;
-    RasterScratch sz = carve_scratch(nullptr, C, N, n_tiles_total, (uint64_t)n_isects, n_pix, true);
+    RasterScratch sz = carve_scratch(nullptr, C, N, n_tiles_total, (uint64_t)n_isects, n_pix, true, channels);
     void* blob = alloc(alloc_ctx, LFS_TAG_SCRATCH, sz.bytes);
     if (!blob) {
         set_error("rasterize_bwd: scratch allocation of %zu bytes failed", sz.bytes);
         return LFS_ERR_ALLOC;
     }
-    RasterScratch s = carve_scratch(blob, C, N, n_tiles_total, (uint64_t)n_isects, n_pix, true);
+    RasterScratch s = carve_scratch(blob, C, N, n_tiles_total, (uint64_t)n_isects, n_pix, true, channels);
     RasterBuffers rb{};
-    rc = raster_front(s, rb, means, quats, scales, colors, opacities, N, C, image_width, image_height, viewmats0, Ks,
-                      tile_offsets, flatten_ids, n_isects, true, stream);
-    if (rc)
-        return rc;
-    rc = launch_blend_fwd(rb, s.cams, C, image_width, image_height, tile_w, tile_h, true, nullptr, masks, nullptr, nullptr,
-                          nullptr, stream);
-    if (rc)
-        return rc;
-    k_pack_vpix<<<div_up(n_pix, 256), 256, 0, stream>>>(v_render_colors, v_render_alphas, s.pix_state, backgrounds,
-                                                        image_width * image_height, (uint32_t)n_pix, s.v_pix);
-    LFS_LAUNCH_OK("k_pack_vpix");
     const uint32_t n_bucket_cap = (uint32_t)((uint64_t)n_isects / kBucket + n_tiles_total + 1);
-    return launch_blend_bwd(rb, s.cams, s.v_pix, quats, scales, means, C, N, image_width, image_height, tile_w, tile_h,
-                            n_bucket_cap, s.n_buckets, v_means, v_quats, v_scales, v_colors, v_opacities, stream);
+    if (channels != 3)
+        LFS_CUDA_OK(cudaMemsetAsync(s.v_colors_group, 0, sizeof(float) * 3 * (size_t)C * N, stream));
+    // groups of three channels; geometry / opacity gradients are linear in (colour, upstream colour gradient) and add up
+    // over the groups, the alpha gradient enters with the first group only
+    for (uint32_t ch0 = 0; ch0 < channels; ch0 += 3) {
+        rc = raster_front(s, rb, means, quats, scales, colors, opacities, N, C, image_width, image_height, viewmats0, Ks,
+                          tile_offsets, flatten_ids, n_isects, true, stream, channels, ch0);
+        if (rc)
+            return rc;
+        rc = launch_blend_fwd(rb, s.cams, C, image_width, image_height, tile_w, tile_h, true, nullptr, masks, nullptr,
+                              nullptr, nullptr, stream);
+        if (rc)
+            return rc;
+        k_pack_vpix<<<div_up(n_pix, 256), 256, 0, stream>>>(v_render_colors, v_render_alphas, s.pix_state, backgrounds,
+                                                            image_width * image_height, (uint32_t)n_pix, channels, ch0,
+                                                            s.v_pix);
+        LFS_LAUNCH_OK("k_pack_vpix");
+        rc = launch_blend_bwd(rb, s.cams, s.v_pix, quats, scales, means, C, N, image_width, image_height, tile_w, tile_h,
+                              n_bucket_cap, s.n_buckets, v_means, v_quats, v_scales,
+                              channels == 3 ? v_colors : s.v_colors_group, v_opacities, stream);
+        if (rc)
+            return rc;
+        if (channels != 3) {
+            k_scatter_vcolors<<<div_up((uint64_t)C * N, 256), 256, 0, stream>>>(s.v_colors_group, C * N, channels, ch0,
+                                                                                v_colors);
+            LFS_LAUNCH_OK("k_scatter_vcolors");
+        }
+    }
+    return LFS_OK;
 }

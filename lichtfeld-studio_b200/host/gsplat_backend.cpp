@@ -266,8 +266,7 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor, at::Tensor, at::Tensor> rasterize
     CHECK_INPUT(last_ids);
     CHECK_INPUT(v_render_colors);
     CHECK_INPUT(v_render_alphas);
-    TORCH_CHECK(colors.size(-1) == 3, "lfs_b200: rasterize bwd supports 3 channels");
-    const uint32_t C = tile_offsets.size(0), N = means.size(0);
+    const uint32_t C = tile_offsets.size(0), N = means.size(0), channels = colors.size(-1);
     at::Tensor v_means = at::empty_like(means), v_quats = at::empty_like(quats), v_scales = at::empty_like(scales);
     at::Tensor v_colors = at::empty_like(colors), v_opacities = at::empty_like(opacities);
     const bool has_bg = backgrounds.has_value() && backgrounds.value().numel() > 0;
@@ -275,7 +274,7 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor, at::Tensor, at::Tensor> rasterize
     Alloc al{means.device(), {}, {}};
     lfs_ok(lfs_rasterize_to_pixels_from_world_3dgs_bwd(
                fp(means), fp(quats), fp(scales), fp(colors), fp(opacities), has_bg ? fp(backgrounds.value()) : nullptr,
-               maskp(masks), N, C, image_width, image_height, tile_size, fp(viewmats0), fpo(viewmats1), fp(Ks),
+               maskp(masks), N, C, channels, image_width, image_height, tile_size, fp(viewmats0), fpo(viewmats1), fp(Ks),
                (int)camera_model, &ut, (int)rs_type, fpo(radial_coeffs), fpo(tangential_coeffs), fpo(thin_prism_coeffs),
                tile_offsets.data_ptr<int32_t>(), flatten_ids.data_ptr<int32_t>(), flatten_ids.numel(), fp(render_alphas),
                last_ids.data_ptr<int32_t>(), fp(v_render_colors), fp(v_render_alphas), &Alloc::fn, &al,

@@ -241,8 +241,8 @@ def rasterize_to_pixels_from_world_3dgs_bwd(means, quats, scales, colors, opacit
     ut = ut_params or UTParams.default()
     al = _Alloc(dev)
     check(lib.lfs_rasterize_to_pixels_from_world_3dgs_bwd(
-        _p(means), _p(quats), _p(scales), _p(colors), _p(opacities), _p(backgrounds), _p(m8), N, Cc, image_width,
-        image_height, tile_size, _p(viewmats0), _p(viewmats1), _p(Ks), camera_model, C.byref(ut), rs_type,
+        _p(means), _p(quats), _p(scales), _p(colors), _p(opacities), _p(backgrounds), _p(m8), N, Cc, colors.shape[-1],
+        image_width, image_height, tile_size, _p(viewmats0), _p(viewmats1), _p(Ks), camera_model, C.byref(ut), rs_type,
         _p(radial_coeffs), _p(tangential_coeffs), _p(thin_prism_coeffs), _p(tile_offsets), _p(flatten_ids),
         flatten_ids.numel(), _p(render_alphas), _p(last_ids), _p(v_render_colors), _p(v_render_alphas), al.cb, None,
         _p(v_means), _p(v_quats), _p(v_scales), _p(v_colors), _p(v_opacities), _stream()))

@@ -48,11 +48,18 @@
 namespace {
     using namespace fast_gs::rasterization;
 
+    struct AbsurdRequest { // thrown out of a resize callback (through the reference's forward) instead of allocating
+        size_t bytes;
+    };
     struct Blob { // plays the torch byte tensor of fastgs/utils/torch_utils.h:10-17 (resize_ keeps or regrows storage)
         char* ptr = nullptr;
         size_t cap = 0, req = 0;
         char* resize(size_t n) {
             req = n;
+            if (n > (64ull << 30))
+                throw AbsurdRequest{n};
+            if (getenv("REF_FASTGS_TRACE"))
+                fprintf(stderr, "[trace] blob request %zu bytes (capacity %zu, ptr %p)\n", n, cap, (void*)ptr);
             if (n > cap) {
                 if (ptr)
                     CK(cudaFree(ptr));
@@ -255,9 +262,86 @@ int main(int argc, char** argv) {
         fflush(stdout);
     };
 
+    // after the reference asked for an absurd blob: which intermediate result is the first wrong one?
+    auto diagnose = [&](int v, size_t bytes) {
+        CK(cudaDeviceSynchronize());
+        cudaError_t le = cudaGetLastError();
+        const int n_tiles = ((W + 15) / 16) * ((H + 15) / 16);
+        char* p = b_prim.ptr;
+        PerPrimitiveBuffers pb = PerPrimitiveBuffers::from_blob(p, (size_t)N);
+        unsigned n_vis = 0, n_inst = 0;
+        CK(cudaMemcpy(&n_vis, pb.n_visible_primitives, 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&n_inst, pb.n_instances, 4, cudaMemcpyDeviceToHost));
+        auto inversions_u32 = [&](const unsigned* d, size_t n) {
+            std::vector<unsigned> h(n);
+            CK(cudaMemcpy(h.data(), d, n * 4, cudaMemcpyDeviceToHost));
+            long long inv = 0;
+            for (size_t i = 1; i < n; ++i) inv += h[i] < h[i - 1];
+            return inv;
+        };
+        long long dk0 = -1, dk1 = -1, off_bad = -1, sum_touched = -1;
+        if (n_vis > 0 && n_vis <= (unsigned)N) {
+            dk0 = inversions_u32(pb.depth_keys.d_buffers[0], n_vis);
+            dk1 = inversions_u32(pb.depth_keys.d_buffers[1], n_vis);
+            std::vector<unsigned> off(n_vis), touched(N), idx0(n_vis), idx1(n_vis);
+            CK(cudaMemcpy(off.data(), pb.offset, (size_t)n_vis * 4, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(touched.data(), pb.n_touched_tiles, (size_t)N * 4, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(idx0.data(), pb.primitive_indices.d_buffers[0], (size_t)n_vis * 4, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(idx1.data(), pb.primitive_indices.d_buffers[1], (size_t)n_vis * 4, cudaMemcpyDeviceToHost));
+            // which index buffer is consistent with the offsets?  offset[i+1] - offset[i] == n_touched[idx[i]]
+            for (int which = 0; which < 2; ++which) {
+                const std::vector<unsigned>& idx = which ? idx1 : idx0;
+                long long bad = 0, sum = 0;
+                for (unsigned i = 0; i < n_vis; ++i) {
+                    const unsigned g = idx[i];
+                    const unsigned t = g < (unsigned)N ? touched[g] : 0xffffffffu;
+                    sum += t;
+                    const unsigned next = i + 1 < n_vis ? off[i + 1] : n_inst;
+                    bad += (next - off[i]) != t;
+                }
+                if (which == 0 || bad < off_bad) off_bad = bad, sum_touched = sum;
+            }
+        }
+        long long k0 = -1, k1 = -1, over0 = -1, over1 = -1;
+        if (b_inst.ptr && n_inst > 0 && n_inst < (1u << 30)) {
+            char* q = b_inst.ptr;
+            PerInstanceBuffers ib = PerInstanceBuffers::from_blob(q, (size_t)n_inst);
+            for (int which = 0; which < 2; ++which) {
+                std::vector<unsigned short> k(n_inst);
+                CK(cudaMemcpy(k.data(), ib.keys.d_buffers[which], (size_t)n_inst * 2, cudaMemcpyDeviceToHost));
+                long long inv = 0, over = 0;
+                for (unsigned i = 0; i < n_inst; ++i) {
+                    if (i && k[i] < k[i - 1]) ++inv;
+                    over += k[i] >= n_tiles;
+                }
+                (which ? k1 : k0) = inv, (which ? over1 : over0) = over;
+            }
+        }
+        long long bad_rng = -1;
+        if (b_tile.ptr) {
+            char* q = b_tile.ptr;
+            PerTileBuffers tb = PerTileBuffers::from_blob(q, (size_t)n_tiles);
+            std::vector<unsigned> rng(2 * (size_t)n_tiles);
+            CK(cudaMemcpy(rng.data(), tb.instance_ranges, rng.size() * 4, cudaMemcpyDeviceToHost));
+            bad_rng = 0;
+            for (int t = 0; t < n_tiles; ++t) bad_rng += rng[2 * t + 1] < rng[2 * t] || rng[2 * t + 1] > n_inst;
+        }
+        printf("{\"event\":\"absurd_request\",\"view\":%d,\"bytes\":%zu,\"last_error\":\"%s\",\"n_visible\":%u,\"n_instances\":%u,"
+               "\"depth_key_inversions\":[%lld,%lld],\"offsets_inconsistent_with_touched\":%lld,\"sum_touched\":%lld,"
+               "\"tile_key_inversions\":[%lld,%lld],\"tile_keys_out_of_range\":[%lld,%lld],\"bad_tile_ranges\":%lld}\n",
+               v, bytes, cudaGetErrorString(le), n_vis, n_inst, dk0, dk1, off_bad, sum_touched, k0, k1, over0, over1, bad_rng);
+        fflush(stdout);
+    };
+
     if (check) {
         for (int v = 0; v < nv; ++v) {
-            forward(v);
+            try {
+                forward(v);
+            } catch (const AbsurdRequest& a) {
+                diagnose(v, a.bytes);
+                ++bad_views;
+                continue;
+            }
             check_view(v);
         }
         if (bad_views) {

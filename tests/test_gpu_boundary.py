@@ -1,0 +1,178 @@
+"""-m gpu: the drop-in boundary EXECUTED.
+
+oracle/ref_train_harness.cpp holds the reference's own callers compiled unchanged -- FastGSRasterize
+(fast_rasterizer_autograd.cpp), SphericalHarmonicsFunction / fully_fused_projection_with_ut / GUTRasterizationFunction
+(rasterizer_autograd.cpp), FusedAdam (fused_adam.cpp), fused_ssim (ssim.cu) -- and is linked twice:
+    ref_fastgs_torch   on the reference's own fastgs + gsplat CUDA objects
+    b200_fastgs_torch  on lichtfeld-studio_b200/libgsplat_backend_b200.so (this project's host layer)
+Every test runs the same call through both modules and compares: all 10 gsplat:: ops, forward_wrapper /
+backward_wrapper, adam_step_wrapper go through the host layer on the GPU (so libgsplat_backend_b200.so shows up in the
+driver's native_so_loaded), with the reference's callers above it bit-for-bit the same object code.
+Metric as in test_gpu_baseline_configs.py (maxnorm + element-wise pass fraction)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import gpu_diag as D  # noqa: E402
+import ref_libs as R  # noqa: E402
+from lichtfeld_studio_b200 import scene  # noqa: E402
+from test_gpu_baseline_configs import gate, strict  # noqa: E402
+
+T = D.T
+LRS = [0.00016, 0.0025, 0.0025 / 20, 0.005, 0.001, 0.05]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda_and_refs():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    R.require_all()
+
+
+@pytest.fixture(scope="module")
+def mods():
+    return R.fastgs_torch_module("ref"), R.fastgs_torch_module("b200")
+
+
+def _scene(n=20000, w=400, h=304, deg=3, views=2, seed=17):
+    sc = scene.make_scene(n, views, w, h, deg, seed=seed, sigma_px=4.0)
+    P = [T(sc.means), T(sc.sh0), T(sc.shN), T(sc.scaling), T(sc.rotation), T(sc.opacity.reshape(-1, 1))]
+    cams = []
+    for v in range(views):
+        vm = sc.viewmats[v].astype(np.float64)
+        cams.append(dict(w2c=T(sc.viewmats[v]), campos=T(-vm[:3, :3].T @ vm[:3, 3]), viewmat=T(sc.viewmats[v:v + 1]),
+                         K=T(sc.Ks[v:v + 1]), k=[float(sc.Ks[v, 0, 0]), float(sc.Ks[v, 1, 1]), float(sc.Ks[v, 0, 2]),
+                                                  float(sc.Ks[v, 1, 2])],
+                         gt=T(scene.make_target(v, w, h)).permute(2, 0, 1).div(255.0).contiguous()))
+    return sc, P, cams
+
+
+GRADS = ("means", "sh0", "shN", "scaling", "rotation", "opacity")
+
+
+def test_fastgs_callers_on_both_backends(mods):
+    ref, b200 = mods
+    sc, P, cams = _scene()
+    bg = T(np.array([0.1, 0.2, 0.3]))
+    rep = {}
+    hr, hb = ref.Harness(*P, LRS), b200.Harness(*P, LRS)
+    c = cams[0]
+    nb = (sc.sh_degree + 1) ** 2
+    a = hr.view_grads(c["w2c"], c["campos"], c["k"], c["gt"], bg, 0.2, nb, sc.width, sc.height)
+    b = hb.view_grads(c["w2c"], c["campos"], c["k"], c["gt"], bg, 0.2, nb, sc.width, sc.height)
+    gate(rep, "image", b[0], a[0], 1e-4, 0.999)
+    gate(rep, "alpha", b[1], a[1], 1e-4, 0.999)
+    assert abs(float(a[2]) - float(b[2])) <= 1e-5 * abs(float(a[2])), (float(a[2]), float(b[2]))
+    for name, x, y in zip(GRADS, b[3:], a[3:]):
+        gate(rep, "grad_" + name, x, y, 1e-3, 0.99)
+    assert torch.equal(hr.densification_info[0], hb.densification_info[0])  # visibility counts
+    gate(rep, "densification_norm", hb.densification_info[1], hr.densification_info[1], 1e-3, 0.99)
+    print("fastgs callers:", rep)
+
+
+def test_fastgs_training_steps_on_both_backends(mods):
+    """Three optimiser steps (two views each, crossing iteration 1000 -> 1001 where FusedAdam starts stepping shN) of the
+    reference's loop on both backends: the parameters must stay together."""
+    ref, b200 = mods
+    sc, P, cams = _scene()
+    bg = T(np.zeros(3))
+    hr, hb = ref.Harness(*P, LRS), b200.Harness(*P, LRS)
+    nb = (sc.sh_degree + 1) ** 2
+    args = ([c["w2c"] for c in cams], [c["campos"] for c in cams], [c["k"] for c in cams], [c["gt"] for c in cams], bg, 0.2,
+            nb, sc.width, sc.height, True)
+    for it in (999, 1000, 1001):
+        lr_, lb_ = hr.train_step(it, *args), hb.train_step(it, *args)
+        assert abs(lr_ - lb_) <= 1e-4 * abs(lr_), (it, lr_, lb_)
+    rep = {}
+    for name, x, y, p0 in zip(GRADS, hb.params(), hr.params(), P):
+        # Adam's first steps move every parameter by ~lr * sign(g): compare the UPDATES
+        gate(rep, "update_" + name, x - p0, y - p0, 2e-2, 0.98)
+    print("fastgs training steps:", rep)
+
+
+def test_gut_callers_on_both_backends(mods):
+    ref, b200 = mods
+    sc, P, cams = _scene(n=12000, w=320, h=240)
+    bg = T(np.array([0.1, 0.2, 0.3]))
+    rep = {}
+    hr, hb = ref.GutHarness(*P, LRS), b200.GutHarness(*P, LRS)
+    c = cams[0]
+    a = hr.view_grads(c["viewmat"], c["K"], c["gt"], bg, 0.2, sc.sh_degree, sc.width, sc.height, 0)
+    b = hb.view_grads(c["viewmat"], c["K"], c["gt"], bg, 0.2, sc.sh_degree, sc.width, sc.height, 0)
+    assert hr.last_n_isects > 50_000 and abs(hr.last_n_isects - hb.last_n_isects) <= 2 + hr.last_n_isects // 2000
+    # whole pipeline on each side's own projection: a radius that rounds the other way adds / removes a tile instance
+    # (+-1 px is the reference's own tolerance), hence 5e-4 here; the per-stage gates on identical inputs are 1e-4
+    gate(rep, "image", b[0], a[0], 5e-4, 0.999)
+    gate(rep, "alpha", b[1], a[1], 5e-4, 0.999)
+    assert abs(float(a[3]) - float(b[3])) <= 1e-4 * abs(float(a[3]))
+    for name, x, y in zip(GRADS, b[4:], a[4:]):
+        gate(rep, "grad_" + name, x, y, 2e-3, 0.98)
+    print("3DGUT callers:", rep)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_gut_depth_render_modes_on_both_backends(mods, mode):
+    """RGB_D (4 channels) and D (1 channel): rasterizer.cpp:272-300, gsplat/Rasterization.cpp:106-128."""
+    ref, b200 = mods
+    sc, P, cams = _scene(n=6000, w=240, h=160)
+    bg = T(np.array([0.1, 0.2, 0.3]))
+    rep = {}
+    hr, hb = ref.GutHarness(*P, LRS), b200.GutHarness(*P, LRS)
+    c = cams[0]
+    a = hr.view_grads(c["viewmat"], c["K"], c["gt"], bg, 0.2, sc.sh_degree, sc.width, sc.height, mode)
+    b = hb.view_grads(c["viewmat"], c["K"], c["gt"], bg, 0.2, sc.sh_degree, sc.width, sc.height, mode)
+    if mode == 1:
+        gate(rep, "image", b[0], a[0], 5e-4, 0.999)
+    gate(rep, "depth", b[2], a[2], 5e-4, 0.999)
+    for name, x, y in zip(GRADS, b[4:], a[4:]):
+        if x is None or y is None:
+            assert x is None and y is None, name
+            continue
+        gate(rep, "grad_" + name, x, y, 2e-3, 0.98)
+    print(f"3DGUT mode {mode}:", rep)
+
+
+def test_densification_ops_on_both_backends(mods):
+    """relocation / add_noise / quats_to_rotmats (gsplat/RelocationCUDA.cu:12,113, QuatToRotmatCUDA.cu:14)."""
+    ref, b200 = mods
+    rng = np.random.RandomState(5)
+    n, n_max = 50_000, 51
+    q = T(rng.normal(size=(n, 4)))
+    gate({}, "quats_to_rotmats", b200.quats_to_rotmats(q), ref.quats_to_rotmats(q), 1e-6, 0.9999)
+    op = T(rng.uniform(0.01, 0.99, size=n))
+    sc = T(np.exp(rng.normal(-3, 1, size=(n, 3))))
+    ratios = torch.as_tensor(rng.randint(1, n_max, size=n), dtype=torch.int32, device="cuda")
+    import math
+    binoms = np.zeros((n_max, n_max), np.float32)
+    for i in range(n_max):
+        for k in range(i + 1):
+            binoms[i, k] = math.comb(i, k)
+    bt = T(binoms)
+    ro, rs = ref.relocation(op, sc, ratios, bt, n_max)
+    bo, bs = b200.relocation(op, sc, ratios, bt, n_max)
+    gate({}, "relocation_opacity", bo, ro, 1e-5, 0.999)
+    gate({}, "relocation_scales", bs, rs, 1e-4, 0.999)
+    raw_op, raw_sc, raw_q = T(rng.normal(size=n)), T(rng.normal(-3, 1, size=(n, 3))), T(rng.normal(size=(n, 4)))
+    noise = T(rng.normal(size=(n, 3)))
+    m_ref = T(rng.normal(size=(n, 3)))
+    m_b = m_ref.clone()
+    ref.add_noise(raw_op, raw_sc, raw_q, noise, m_ref, 1e-3)
+    b200.add_noise(raw_op, raw_sc, raw_q, noise, m_b, 1e-3)
+    gate({}, "add_noise_means", m_b, m_ref, 1e-6, 0.999)
+
+
+def test_intersect_ops_on_both_backends(mods):
+    ref, b200 = mods
+    rng = np.random.RandomState(3)
+    Cc, N, W, H = 2, 20000, 640, 480
+    tw, th = (W + 15) // 16, (H + 15) // 16
+    m2d = T((rng.uniform(-0.1, 1.1, size=(Cc, N, 2)) * np.array([W, H])))
+    radii = torch.as_tensor(rng.randint(0, 30, size=(Cc, N, 2)), dtype=torch.int32, device="cuda")
+    dep = T(rng.uniform(0.1, 20.0, size=(Cc, N)))
+    a = ref.intersect_tile(m2d, radii, dep, Cc, 16, tw, th, True)
+    b = b200.intersect_tile(m2d, radii, dep, Cc, 16, tw, th, True)
+    for x, y in zip(a, b):
+        assert x.shape == y.shape and torch.equal(x, y)
+    assert torch.equal(ref.intersect_offset(a[1], Cc, tw, th), b200.intersect_offset(b[1], Cc, tw, th))

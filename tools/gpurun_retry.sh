@@ -5,6 +5,6 @@ for i in $(seq 1 40); do
   /usr/local/graft/bin/gpurun --timeout $T "$@"
   rc=$?
   if [ $rc -ne 3 ]; then exit $rc; fi
-  sleep 120
+  sleep 45
 done
 exit 3

@@ -16,7 +16,7 @@ for var in static shared nofast sm100; do
 done
 # through the reference's own forward_wrapper inside a torch process
 for cfg in C2 C3; do
-  timeout 600 python tools/ref_fastgs_train.py --module ref --config $cfg --check > $O/torch_ref_${cfg}_check.json 2> $O/torch_ref_${cfg}_check.err
+  timeout 600 python tools/ref_train.py --module ref --config $cfg --check > $O/torch_ref_${cfg}_check.json 2> $O/torch_ref_${cfg}_check.err
   echo "exit $?" >> $O/torch_ref_${cfg}_check.json
 done
 # sanitizer passes on the smallest failing size (C2), standalone static build
@@ -30,8 +30,8 @@ for var in static; do
   timeout 600 oracle/_ref/fastgs_standalone_$var /tmp/c3.bin --check --train --views 8 --steps 3 --warmup 1 > $O/standalone_${var}_c3_train.jsonl 2> $O/standalone_${var}_c3_train.err
   echo "exit $?" >> $O/standalone_${var}_c3_train.jsonl
 done
-timeout 900 python tools/ref_fastgs_train.py --module ref --config C3 --views 8 --steps 3 --warmup 1 > $O/torch_ref_C3_train.json 2> $O/torch_ref_C3_train.err
+timeout 900 python tools/ref_train.py --module ref --config C3 --views 8 --steps 3 --warmup 1 > $O/torch_ref_C3_train.json 2> $O/torch_ref_C3_train.err
 echo "exit $?" >> $O/torch_ref_C3_train.json
-timeout 900 python tools/ref_fastgs_train.py --module b200 --config C3 --views 8 --steps 3 --warmup 1 > $O/torch_b200_C3_train.json 2> $O/torch_b200_C3_train.err
+timeout 900 python tools/ref_train.py --module b200 --config C3 --views 8 --steps 3 --warmup 1 > $O/torch_b200_C3_train.json 2> $O/torch_b200_C3_train.err
 echo "exit $?" >> $O/torch_b200_C3_train.json
 tail -n 3 $O/*.jsonl $O/*.json | cut -c1-600

@@ -1,10 +1,12 @@
-"""Runs the reference's OWN fastgs training step (oracle/ref_train_harness.cpp: FastGSRasterize autograd Function,
-fused_ssim, FusedAdam -- all compiled unchanged from /root/reference) on a seeded BASELINE config, through
+"""Runs the reference's OWN training step (oracle/ref_train_harness.cpp: the FastGSRasterize / GUTRasterizationFunction /
+SphericalHarmonicsFunction autograd Functions, fused_ssim, FusedAdam -- all compiled unchanged from /root/reference) on a
+seeded BASELINE config, through
 
-    --module ref    oracle/_ref/ref_fastgs_torch*.so   the reference's fastgs CUDA backend        (the denominator)
+    --module ref    oracle/_ref/ref_fastgs_torch*.so   the reference's own CUDA backends          (the denominator)
     --module b200   oracle/_ref/b200_fastgs_torch*.so  this project's host layer as the backend   (boundary executed)
+    --path fastgs   the default EWA rasterizer (fast_rasterize)      --path gut   the 3DGUT rasterizer (--gut)
 
-    python tools/ref_fastgs_train.py --module ref --config C3 --views 8 --steps 3 --warmup 1 [--check]
+    python tools/ref_train.py --module ref --path fastgs --config C3 --views 8 --steps 3 --warmup 1 [--check]
 
 Prints one JSON line: views/s (CUDA events on the current stream, steps bracketed by synchronize), counts and a
 plausibility check of the first forward (finite image, n_buckets consistent).  TEST / BENCH INFRASTRUCTURE ONLY."""
@@ -47,9 +49,42 @@ def scene_tensors(sc, dev):
     return P, cams
 
 
+def run_gut(a, mod, sc, P, out, dev, V, W, H, deg):
+    """the reference's 3DGUT step: GutHarness = rasterize() of rasterizer.cpp on its own autograd Functions"""
+    T = lambda x: torch.as_tensor(np.ascontiguousarray(x, np.float32)).to(dev)  # noqa: E731
+    h = mod.GutHarness(*P, LRS)
+    gts = [torch.as_tensor(S.make_target(v, W, H)).to(dev).permute(2, 0, 1).float().div_(255.0).contiguous()
+           for v in range(V)]
+    vms = [T(sc.viewmats[v:v + 1]) for v in range(V)]
+    Ks = [T(sc.Ks[v:v + 1]) for v in range(V)]
+    bg = torch.zeros(3, device=dev)
+    it = 1001
+    for i in range(a.warmup):
+        h.train_step(it + i, vms, Ks, gts, bg, a.lambda_dssim, deg, W, H, False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    loss = 0.0
+    for i in range(a.steps):
+        loss = h.train_step(it + a.warmup + i, vms, Ks, gts, bg, a.lambda_dssim, deg, W, H, i == a.steps - 1)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.steps
+    out.update({"value": V / ms * 1e3, "unit": "views/s", "ms_per_step": ms, "steps": a.steps, "warmup": a.warmup,
+                "loss_last_step": loss, "instances_last_view": int(h.last_n_isects),
+                "impl": ("reference gsplat (3DGUT) CUDA kernels + the reference's rasterizer_autograd.cpp / fused_ssim / "
+                         "FusedAdam, all unmodified (kernels built against oracle/glm_shim)" if a.module == "ref" else
+                         "the reference's rasterizer_autograd.cpp / fused_ssim / FusedAdam (unmodified) on this project's "
+                         "host layer"),
+                "note": "targets resident in HBM; L1 + fused SSIM loss; one FusedAdam::step per step"})
+    print(json.dumps(out))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--module", default="ref", choices=["ref", "b200"])
+    ap.add_argument("--path", default="fastgs", choices=["fastgs", "gut"])
     ap.add_argument("--config", default="C3")
     ap.add_argument("--n-gaussians", type=int, default=0)
     ap.add_argument("--views", type=int, default=0)
@@ -66,8 +101,10 @@ def main():
     mod = load_module(a.module)
     P, cams = scene_tensors(sc, dev)
     nb = (deg + 1) ** 2
-    out = {"module": a.module, "config": a.config, "gaussians": n, "views_per_step": V, "width": W, "height": H,
-           "cudart": torch.version.cuda}
+    out = {"module": a.module, "path": a.path, "config": a.config, "gaussians": n, "views_per_step": V, "width": W,
+           "height": H, "cudart": torch.version.cuda}
+    if a.path == "gut":
+        return run_gut(a, mod, sc, P, out, dev, V, W, H, deg)
 
     # 1. the reference's forward_wrapper, called directly, torch-owned blobs, nothing zero-filled, nothing swallowed
     w2c, cp, k = cams[0]
