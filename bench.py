@@ -51,6 +51,8 @@ def parse():
                          "local Adam (nccl); auto = p2p when symmetric memory can be set up")
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / reference_gpu legs")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    ap.add_argument("--no-balance", action="store_true", help="N > 1: plain round-robin view sharding instead of the "
+                                                              "instance-count balanced one")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = --views-per-gpu views on every GPU; strong = the config's total view count "
                          "(8 for C3, 32 for C4) split over the GPUs")
@@ -237,6 +239,19 @@ def main():
     for v in my_views:
         tr.forward(sc.viewmats[v], sc.Ks[v], deg)
         n_inst_per_view.append(tr.stats()[0])
+    view_costs = None
+    if world > 1 and not a.no_balance:
+        # cost-balanced sharding: the tile-instance count of a camera (known from its last visit in a real run, from the
+        # calibration pass here) predicts its render time; every rank gets the same number of views
+        mine = torch.zeros(V, dtype=torch.float64, device=device)
+        for v, c in zip(my_views, n_inst_per_view):
+            mine[v] = float(c)
+        dist.all_reduce(mine, op=dist.ReduceOp.SUM)
+        view_costs = mine.cpu().tolist()
+        from lichtfeld_studio_b200 import dp as _dp
+        my_views = _dp.shard_views(V, world, rank, view_costs)
+        tr.ensure_capacity([sc.viewmats[v] for v in my_views], [sc.Ks[v] for v in my_views], deg)
+        n_inst_per_view = [view_costs[v] for v in my_views]
 
     dp_mode = "single"
     if world > 1:
@@ -278,7 +293,7 @@ def main():
         tr.adam_step(n_views=V)
 
     def step_e2e():
-        tr.train_step(sc.viewmats, sc.Ks, targets_host, bg, deg, world, rank, read_loss=True)
+        tr.train_step(sc.viewmats, sc.Ks, targets_host, bg, deg, world, rank, read_loss=True, view_costs=view_costs)
         torch.cuda.current_stream().synchronize()  # the step's result (loss) is read on the host
 
     def timed(fn, steps, warmup):
@@ -350,7 +365,8 @@ def main():
         "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload, "gaussians": n, "views_per_step": V, "width": W, "height": H, "sh_degree": deg,
-                   "parallelism": f"view-sharded dp{world}: {dp_mode}",
+                   "parallelism": f"view-sharded dp{world}" + ("" if view_costs is None else " (views assigned by instance "
+                                  "count, equal counts per rank)") + f": {dp_mode}",
                    "instances_per_view": I, "l2": "per-step working set (params+grads+Adam state+records) >= 1 GB, "
                                                   "larger than the 126 MB L2: no flush needed"},
         "clocks": clk,

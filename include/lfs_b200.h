@@ -333,6 +333,28 @@ int lfs_trainer_poll_capacity(void* trainer, uint64_t* max_instances_seen /* or 
  * of the full buffer through *full_bytes (may be NULL). */
 int lfs_trainer_debug_copy(void* trainer, int which, void* dst, uint64_t dst_bytes, uint64_t* full_bytes, void* stream);
 
+/* ---- densification-side state surgery on the planar arenas -----------------------------------------
+ * The reference's strategies edit its six parameter tensors and the Adam moments with index_select + cat per tensor
+ * (src/training/strategies/default_strategy.cpp:49-230 duplicate / split / prune, mcmc.cpp:112-347 relocate / add,
+ * strategy_utils.cpp:57-131).  On the planar layout every such edit is one ROW GATHER:
+ *   output Gaussian i <- every plane of source Gaussian index[i]   (index[i] < 0: leave the destination slot as it is)
+ * applied to the parameter arena and, when given, to both Adam moment arenas in the same launch; zero_state[i] != 0
+ * zeroes the moments of slot i (a new Gaussian starts with fresh optimiser state, default_strategy.cpp:62-75).
+ * Source and destination may be the same arenas only for in-place relocation (every written slot is read by nobody).
+ * plane_elems = padded plane length (N_pad) of the respective arena.  All pointers are device pointers. */
+int lfs_arena_gather(const float* src_params, const float* src_m, const float* src_v, float* dst_params, float* dst_m,
+                     float* dst_v, const int32_t* index, const uint8_t* zero_state, uint32_t n_out, uint32_t n_src,
+                     uint32_t planes, uint64_t src_plane_elems, uint64_t dst_plane_elems, void* stream);
+/* AoS rows [n, n_planes] <-> slots index[n] (NULL: 0..n-1) of planes [first_plane, first_plane + n_planes): how a strategy
+ * reads the activated inputs of a split and writes the new means / scales / opacities (default_strategy.cpp:107-128). */
+int lfs_arena_set_rows(float* arena, uint64_t plane_elems, uint32_t first_plane, uint32_t n_planes, const int32_t* index,
+                       const float* rows, uint32_t n, uint32_t n_slots, void* stream);
+int lfs_arena_get_rows(const float* arena, uint64_t plane_elems, uint32_t first_plane, uint32_t n_planes,
+                       const int32_t* index, float* rows, uint32_t n, uint32_t n_slots, void* stream);
+/* Multi-GPU: lfs_adam_step_multi_p2p keeps the Adam moments of an element on its owner only.  Before a surgery every
+ * rank zeroes what it does not own; an all-reduce(sum) of the result is the complete moment arena on every rank. */
+int lfs_adam_p2p_zero_unowned(float* arena, int64_t n_floats, int world, int rank, void* stream);
+
 /* Per-stage device timing of the view step with CUDA events on the launching stream (bench.py roofline).
  * Stages: 0 preprocess_fwd | 1 depth sort + scan + emit + tile sort + offsets | 2 bucket offsets + expand |
  *         3 blend_fwd | 4 (loss: caller side, always 0) | 5 blend_bwd | 6 preprocess_bwd.

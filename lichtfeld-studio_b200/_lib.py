@@ -143,6 +143,10 @@ SIGNATURES = {
     "lfs_adam_p2p_owner": (C.c_int, [C.c_int64, C.c_int]),
     "lfs_adam_p2p_owned_chunks": (C.c_int, [C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64),
                                             C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "lfs_arena_gather": (C.c_int, [_vp] * 8 + [_u32, _u32, _u32, C.c_uint64, C.c_uint64, _vp]),
+    "lfs_arena_set_rows": (C.c_int, [_vp, C.c_uint64, _u32, _u32, _vp, _vp, _u32, _u32, _vp]),
+    "lfs_arena_get_rows": (C.c_int, [_vp, C.c_uint64, _u32, _u32, _vp, _vp, _u32, _u32, _vp]),
+    "lfs_adam_p2p_zero_unowned": (C.c_int, [_vp, _i64, C.c_int, C.c_int, _vp]),
     "lfs_trainer_poll_capacity": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "lfs_trainer_debug_copy": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64, C.POINTER(C.c_uint64), _vp]),
 }

@@ -159,4 +159,23 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return y;
 }
 
+// Packed fp32 pairs (sm_100a FFMA2 / FMUL2: two IEEE fp32 operations per instruction, each component rounded exactly like
+// the scalar fmaf / __fmul_rn): used wherever two accumulations share a multiplier
+// (the N' / D polynomials of a pair, the SSIM convolutions).
+__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(d)
+        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)),
+          "l"(*reinterpret_cast<const unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fmul2(const float2 a, const float2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;"
+        : "=l"(d)
+        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+
 } // namespace lfs

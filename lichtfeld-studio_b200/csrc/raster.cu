@@ -205,24 +205,6 @@ __device__ __forceinline__ float poly2(const float dx, const float dy, const flo
     return fmaf(dx, fmaf(dx, cxx, fmaf(dy, cxy, cx)), fmaf(dy, fmaf(dy, cyy, cy), c0));
 }
 
-// Packed fp32 pairs (sm_100a FFMA2 / FMUL2: two IEEE fp32 operations per instruction, each component rounded exactly like
-// the scalar fmaf / __fmul_rn): the N' and D polynomials of a pair share (dx, dy), so one FFMA2 chain evaluates both
-// with the same bits as two poly2() calls.
-__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c) {
-    unsigned long long d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;"
-        : "=l"(d)
-        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)),
-          "l"(*reinterpret_cast<const unsigned long long*>(&c)));
-    return *reinterpret_cast<float2*>(&d);
-}
-__device__ __forceinline__ float2 fmul2(const float2 a, const float2 b) {
-    unsigned long long d;
-    asm("mul.rn.f32x2 %0, %1, %2;"
-        : "=l"(d)
-        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
-    return *reinterpret_cast<float2*>(&d);
-}
 // (N', D)(dx, dy) with coefficient pairs c = {(n0,d0), (n1x,d1x), (n1y,d1y), (n2xx,d2xx), (n2xy,d2xy), (n2yy,d2yy)}:
 // the same nesting as poly2, five FFMA2 instead of ten FFMA
 __device__ __forceinline__ float2 poly2x2(const float2 DX, const float2 DY, const float2 c0, const float2 cx,
@@ -455,19 +437,19 @@ __global__ void __launch_bounds__(kFwdThreads, MINB)
                                                   P4, P5);
                         const float vis = ex2_approx(ND.x * rcp_approx(ND.y));
                         const float alpha = fminf(kAlphaMax, E.w * vis);
-                        if (((live >> k) & 1u) && alpha >= kAlphaMin) {
-                            const float next_T = T[k] * (1.0f - alpha);
-                            if (next_T <= kTMin) {
-                                live &= ~(1u << k);
-                            } else {
-                                const float w = alpha * T[k];
-                                const float2 rg = ffma2(make_float2(w, w), Erg, make_float2(r[k], g[k]));
-                                r[k] = rg.x, g[k] = rg.y;
-                                b[k] = fmaf(w, E.z, b[k]);
-                                T[k] = next_T;
-                                ncon[k] = li + 1;
-                            }
-                        }
+                        // branch-free (selects): the four pixels of a thread form one basic block the scheduler can
+                        // interleave; a pair that does not contribute blends with weight 0
+                        const bool hit = ((live >> k) & 1u) && alpha >= kAlphaMin;
+                        const float next_T = T[k] * (1.0f - alpha);
+                        const bool stop = hit && next_T <= kTMin; // gsplat stops at T <= 1e-4 (...Fwd.cu:244-248)
+                        const bool acc = hit && !stop;
+                        const float w = acc ? alpha * T[k] : 0.f;
+                        const float2 rg = ffma2(make_float2(w, w), Erg, make_float2(r[k], g[k]));
+                        r[k] = rg.x, g[k] = rg.y;
+                        b[k] = fmaf(w, E.z, b[k]);
+                        T[k] = acc ? next_T : T[k];
+                        ncon[k] = acc ? li + 1 : ncon[k];
+                        live &= ~((stop ? 1u : 0u) << k);
                     }
                     if (live == 0)
                         break;

@@ -633,25 +633,27 @@ __global__ void __launch_bounds__(256)
     for (int c = 0; c < 3; ++c) {
         for (int t = threadIdx.x; t < kSsimS * kTile; t += 256) { // horizontal 11x1
             const int ly = t >> 4, lx = (t & 15) + kSsimHalo;
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            float2 a01 = make_float2(0.f, 0.f), a23 = a01; // FFMA2 pairs: (E[X], E[Y]) and (E[X^2 + Y^2], E[XY])
 #pragma unroll
             for (int d = -kSsimHalo; d <= kSsimHalo; ++d) {
-                const float w = c_ssim_g[d + kSsimHalo];
+                const float2 w2 = make_float2(c_ssim_g[d + kSsimHalo], c_ssim_g[d + kSsimHalo]);
                 const float2 v = sXY[c][ly][lx + d];
-                a0 = fmaf(w, v.x, a0), a1 = fmaf(w, v.y, a1), a2 = fmaf(w, fmaf(v.x, v.x, v.y * v.y), a2);
-                a3 = fmaf(w, v.x * v.y, a3);
+                a01 = ffma2(w2, v, a01);
+                a23 = ffma2(w2, make_float2(fmaf(v.x, v.x, v.y * v.y), v.x * v.y), a23);
             }
-            xc[ly][t & 15] = make_float4(a0, a1, a2, a3);
+            xc[ly][t & 15] = make_float4(a01.x, a01.y, a23.x, a23.y);
         }
         __syncthreads();
         {
-            float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f; // vertical 1x11
+            float2 o01 = make_float2(0.f, 0.f), o23 = o01; // vertical 1x11
 #pragma unroll
             for (int d = 0; d < 2 * kSsimHalo + 1; ++d) {
-                const float w = c_ssim_g[d];
+                const float2 w2 = make_float2(c_ssim_g[d], c_ssim_g[d]);
                 const float4 r = xc[ty + d][tx];
-                o0 = fmaf(w, r.x, o0), o1 = fmaf(w, r.y, o1), o2 = fmaf(w, r.z, o2), o3 = fmaf(w, r.w, o3);
+                o01 = ffma2(w2, make_float2(r.x, r.y), o01);
+                o23 = ffma2(w2, make_float2(r.z, r.w), o23);
             }
+            const float o0 = o01.x, o1 = o01.y, o2 = o23.x, o3 = o23.y;
             if (px < W && py < H) {
                 const float mu1 = o0, mu2 = o1, s12 = o3 - mu1 * mu2;
                 const float C1 = 0.0001f, C2 = 0.0009f;
@@ -727,24 +729,29 @@ __global__ void __launch_bounds__(256)
     for (int c = 0; c < 3; ++c) {
         for (int t = threadIdx.x; t < kSsimS * kTile; t += 256) {
             const int ly = t >> 4, lx = (t & 15) + kSsimHalo;
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+            float2 a01 = make_float2(0.f, 0.f);
+            float a2 = 0.f;
 #pragma unroll
             for (int d = -kSsimHalo; d <= kSsimHalo; ++d) {
                 const float w = c_ssim_g[d + kSsimHalo];
                 const float4 v = sD[c][ly][lx + d];
-                a0 = fmaf(w, v.x, a0), a1 = fmaf(w, v.y, a1), a2 = fmaf(w, v.z, a2);
+                a01 = ffma2(make_float2(w, w), make_float2(v.x, v.y), a01);
+                a2 = fmaf(w, v.z, a2);
             }
-            xc[ly][t & 15] = make_float4(a0, a1, a2, 0.f);
+            xc[ly][t & 15] = make_float4(a01.x, a01.y, a2, 0.f);
         }
         __syncthreads();
         if (inside) {
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+            float2 s01 = make_float2(0.f, 0.f);
+            float s2 = 0.f;
 #pragma unroll
             for (int d = 0; d < 2 * kSsimHalo + 1; ++d) {
                 const float w = c_ssim_g[d];
                 const float4 r = xc[ty + d][tx];
-                s0 = fmaf(w, r.x, s0), s1 = fmaf(w, r.y, s1), s2 = fmaf(w, r.z, s2);
+                s01 = ffma2(make_float2(w, w), make_float2(r.x, r.y), s01);
+                s2 = fmaf(w, r.z, s2);
             }
+            const float s0 = s01.x, s1 = s01.y;
             const float bgc = c == 0 ? bg_r : (c == 1 ? bg_g : bg_b);
             const float raw = fmaf(st.w, bgc, chan(st, c));
             const float X = fminf(fmaxf(raw, 0.f), 1.f), Y = Yt[c];

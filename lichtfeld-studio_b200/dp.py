@@ -12,11 +12,26 @@ from typing import List, Sequence
 import numpy as np
 
 
-def shard_views(n_views: int, world_size: int, rank: int) -> List[int]:
-    """Views handled by `rank`: rank, rank + world_size, ...  (view v -> rank v mod world_size)."""
+def shard_views(n_views: int, world_size: int, rank: int, costs: Sequence[float] | None = None) -> List[int]:
+    """Views handled by `rank`.  Without costs: rank, rank + world_size, ...  (view v -> rank v mod world_size).
+    With per-view cost estimates (e.g. the tile-instance counts of the cameras from the previous epoch -- the blend
+    kernels, 60 % of a view, scale with them): longest-processing-time-first assignment with equal view counts per rank,
+    so that the slowest rank of a step, which every other rank waits for at the exchange barrier, is as fast as possible.
+    Deterministic: every rank computes the same partition from the same costs."""
     if not (0 <= rank < world_size):
         raise ValueError(f"rank {rank} outside world of {world_size}")
-    return list(range(rank, n_views, world_size))
+    if costs is None:
+        return list(range(rank, n_views, world_size))
+    if len(costs) != n_views:
+        raise ValueError(f"{len(costs)} costs for {n_views} views")
+    quota = [(n_views + world_size - 1 - r) // world_size for r in range(world_size)]  # same counts as round-robin
+    load = [0.0] * world_size
+    mine: List[List[int]] = [[] for _ in range(world_size)]
+    for v in sorted(range(n_views), key=lambda i: (-float(costs[i]), i)):
+        r = min((r for r in range(world_size) if len(mine[r]) < quota[r]), key=lambda r: (load[r], r))
+        mine[r].append(v)
+        load[r] += float(costs[v])
+    return sorted(mine[rank])
 
 
 def plane_table(K: int) -> dict:

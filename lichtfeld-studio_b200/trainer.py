@@ -128,11 +128,12 @@ class SplatTrainer:
         self._h_grads = symm_mem.rendezvous(new_g, group)
         self.params, self.grads = new_p, new_g
         # NVSwitch multicast (NVLS) addresses of the same buffers, 0 when the fabric has none.  The in-switch variant
-        # (multimem.ld_reduce / multimem.st) is opt-in with LFS_P2P_MULTICAST=1: it is validated on 2 and 4 GPUs
-        # (tools/check_p2p.py); the plain peer load/store kernel is the one validated on 2, 4 and 8
+        # (multimem.ld_reduce / multimem.st: the reduction happens inside the switch, 1/W of the inbound traffic) is used
+        # whenever the fabric offers it; LFS_P2P_MULTICAST=0 falls back to plain peer loads / stores (tools/check_p2p.py
+        # validates both against ncclAllReduce + Adam)
         self._mc_grads = int(getattr(self._h_grads, "multicast_ptr", 0) or 0)
         self._mc_params = int(getattr(self._h_params, "multicast_ptr", 0) or 0)
-        if os.environ.get("LFS_P2P_MULTICAST", "0") != "1" or not (self._mc_grads and self._mc_params):
+        if os.environ.get("LFS_P2P_MULTICAST", "1") == "0" or not (self._mc_grads and self._mc_params):
             self._mc_grads = self._mc_params = 0
         self.p2p = True
 
@@ -174,6 +175,106 @@ class SplatTrainer:
 
     def export_grads(self) -> dict:
         return self._unpack(self.grads)
+
+    # ---- densification-side state surgery -----------------------------------------------------
+    def gather_moments(self) -> None:
+        """Multi-GPU (p2p): the fused step keeps the Adam moments of an element on its owner only.  Before the arenas
+        are restructured every rank zeroes what it does not own and the moments are summed over the ranks, so that all
+        ranks hold the complete state and apply the same surgery.  Ownership is positional (lfs_adam_p2p_owner), so
+        afterwards every rank simply goes on updating the chunks it owns.  Collective; once per densification step."""
+        if not self.p2p:
+            return
+        for arena in (self.exp_avg, self.exp_avg_sq):
+            check(self.lib.lfs_adam_p2p_zero_unowned(arena.data_ptr(), arena.numel(), self._p2p_world, self._p2p_rank,
+                                                     self._stream()))
+            dp.allreduce_sum_(arena)
+
+    def restructure(self, index: torch.Tensor, zero_state: Optional[torch.Tensor] = None) -> None:
+        """One row gather over every plane of the parameter arena and both Adam moment arenas (lfs_arena_gather):
+        Gaussian i of the new model = Gaussian index[i] of the old one; zero_state[i] starts it with fresh moments.
+        Every strategy edit of the reference (duplicate / split / remove, default_strategy.cpp:49-230) is this call.
+        The per-view scratch is re-created for the new count; gradients are dropped (the reference's zero_grad)."""
+        if self.p2p:
+            raise _lib.LfsError(_lib.LFS_ERR_UNSUPPORTED, "restructure: call gather_moments(), disable p2p, restructure, "
+                                "enable_p2p() again (the symmetric arenas have a fixed size)")
+        index = index.to(device=self.device, dtype=torch.int32).contiguous()
+        n_new = int(index.numel())
+        zs = None if zero_state is None else zero_state.to(device=self.device, dtype=torch.uint8).contiguous()
+        np_new = (n_new + 3) // 4 * 4
+        planes = 11 + 3 * self.K
+        mk = lambda: torch.zeros(planes * np_new, dtype=torch.float32, device=self.device)  # noqa: E731
+        new_p, new_m, new_v = mk(), mk(), mk()
+        check(self.lib.lfs_arena_gather(self.params.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                                        new_p.data_ptr(), new_m.data_ptr(), new_v.data_ptr(), index.data_ptr(),
+                                        None if zs is None else zs.data_ptr(), n_new, self.N, planes, self.Np, np_new,
+                                        self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()
+        self.params, self.exp_avg, self.exp_avg_sq, self.grads = new_p, new_m, new_v, mk()
+        cap_per_gauss = self.instance_capacity / max(self.N, 1)
+        self.N, self.Np = n_new, np_new
+        self.desc.n_gaussians = n_new
+        self.desc.instance_capacity = int(cap_per_gauss * n_new) + (1 << 16)
+        self._create_handle()
+        planes_per_group = [3, 3, 3 * (self.K - 1), 3, 4, 1]
+        self.seg_begin = [0]
+        for p in planes_per_group:
+            self.seg_begin.append(self.seg_begin[-1] + p * self.Np)
+
+    def _rows(self, group: str, index: Optional[torch.Tensor] = None) -> torch.Tensor:
+        first, cnt = dp.plane_table(self.K)[group]
+        n = self.N if index is None else int(index.numel())
+        out = torch.empty((n, cnt), dtype=torch.float32, device=self.device)
+        check(self.lib.lfs_arena_get_rows(self.params.data_ptr(), self.Np, first, cnt,
+                                          None if index is None else index.data_ptr(), out.data_ptr(), n, self.N,
+                                          self._stream()))
+        return out
+
+    def _set_rows(self, group: str, index: torch.Tensor, rows: torch.Tensor) -> None:
+        first, cnt = dp.plane_table(self.K)[group]
+        rows = rows.to(torch.float32).contiguous()
+        check(self.lib.lfs_arena_set_rows(self.params.data_ptr(), self.Np, first, cnt, index.data_ptr(), rows.data_ptr(),
+                                          int(index.numel()), self.N, self._stream()))
+
+    def remove(self, is_prune: torch.Tensor) -> None:
+        """DefaultStrategy::remove (default_strategy.cpp:188-218)."""
+        keep = torch.nonzero(~is_prune.to(self.device).bool()).squeeze(-1)
+        self.restructure(keep)
+
+    def duplicate(self, is_duplicated: torch.Tensor) -> None:
+        """DefaultStrategy::duplicate (default_strategy.cpp:49-84): selected Gaussians are appended, fresh moments."""
+        sel = torch.nonzero(is_duplicated.to(self.device).bool()).squeeze(-1)
+        n0 = self.N
+        index = torch.cat([torch.arange(n0, device=self.device), sel])
+        zero = torch.zeros(index.numel(), dtype=torch.uint8, device=self.device)
+        zero[n0:] = 1
+        self.restructure(index, zero)
+
+    def split(self, is_split: torch.Tensor, revised_opacity: bool = False, generator=None) -> None:
+        """DefaultStrategy::split (default_strategy.cpp:86-160): a selected Gaussian is replaced by two samples of
+        itself (means + R S eps, scales / 1.6, optionally revised opacity), appended after the unselected ones."""
+        from . import ops
+        is_split = is_split.to(self.device).bool()
+        sel = torch.nonzero(is_split).squeeze(-1).to(torch.int32)
+        rest = torch.nonzero(~is_split).squeeze(-1)
+        ns = int(sel.numel())
+        scales = torch.exp(self._rows("scaling", sel))
+        quats = torch.nn.functional.normalize(self._rows("rotation", sel), dim=-1)
+        means = self._rows("means", sel)
+        op_raw = self._rows("opacity", sel)
+        rot = ops.quats_to_rotmats(quats.contiguous())
+        eps = torch.randn((2, ns, 3), device=self.device, generator=generator)
+        samples = torch.einsum("nij,nj,bnj->bni", rot, scales, eps)
+        index = torch.cat([rest, sel.long(), sel.long()])
+        zero = torch.zeros(index.numel(), dtype=torch.uint8, device=self.device)
+        zero[rest.numel():] = 1
+        self.restructure(index, zero)
+        new = torch.arange(rest.numel(), rest.numel() + 2 * ns, device=self.device, dtype=torch.int32)
+        self._set_rows("means", new, (means.unsqueeze(0) + samples).reshape(-1, 3))
+        self._set_rows("scaling", new, torch.log(scales / 1.6).repeat(2, 1))
+        if revised_opacity:
+            new_op = 1.0 - torch.sqrt(1.0 - torch.sigmoid(op_raw))
+            self._set_rows("opacity", new, torch.logit(new_op).repeat(2, 1))
+        torch.cuda.current_stream(self.device).synchronize()
 
     # ---- one view ----------------------------------------------------------------------------------------
     def forward(self, viewmat: np.ndarray, K: np.ndarray, active_sh_degree: Optional[int] = None,
@@ -302,12 +403,14 @@ class SplatTrainer:
     # ---- full step: B views -> one Adam update --------------------------------------------------------------
     def train_step(self, viewmats: np.ndarray, Ks: np.ndarray, targets_pinned: Sequence[torch.Tensor],
                    bg=(0.0, 0.0, 0.0), active_sh_degree: Optional[int] = None, world_size: int = 1, rank: int = 0,
-                   read_loss: bool = True, lambda_dssim: Optional[float] = 0.2):
+                   read_loss: bool = True, lambda_dssim: Optional[float] = 0.2,
+                   view_costs: Optional[Sequence[float]] = None):
         """targets_pinned: pinned host uint8 [H,W,3] tensors, one per view of the GLOBAL batch; this rank renders
-        views rank, rank + world_size, ...  Host->device copies run on a side stream, double buffered."""
+        views rank, rank + world_size, ... (or the cost-balanced partition of dp.shard_views when view_costs is given).
+        Host->device copies run on a side stream, double buffered."""
         main = torch.cuda.current_stream(self.device)
         self.loss_dev.zero_()
-        my_views = dp.shard_views(len(targets_pinned), world_size, rank)
+        my_views = dp.shard_views(len(targets_pinned), world_size, rank, view_costs)
         for i, v in enumerate(my_views):
             slot = i & 1
             with torch.cuda.stream(self.copy_stream):

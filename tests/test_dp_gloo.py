@@ -106,3 +106,22 @@ def test_two_rank_gloo_matches_single_process():
     np.testing.assert_array_equal(res[0][2], res[1][2])  # hence identical parameters, no broadcast needed
     np.testing.assert_allclose(res[0][1], grads_all, rtol=1e-12, atol=1e-15)
     np.testing.assert_allclose(res[0][2], want_p, rtol=1e-12, atol=1e-15)
+
+
+def test_cost_balanced_view_sharding():
+    """shard_views(costs=...): a partition (every view exactly once), equal view counts per rank like round-robin, and
+    a smaller maximum rank load than round-robin on skewed costs; identical on every rank by construction."""
+    import lichtfeld_studio_b200  # noqa: F401
+    from lichtfeld_studio_b200 import dp
+    rng = np.random.RandomState(0)
+    for world, n in ((2, 7), (4, 32), (8, 64)):
+        costs = rng.lognormal(0.0, 0.6, size=n)
+        parts = [dp.shard_views(n, world, r, costs) for r in range(world)]
+        assert sorted(sum(parts, [])) == list(range(n))
+        assert [len(p) for p in parts] == [len(dp.shard_views(n, world, r)) for r in range(world)]
+        load = max(costs[p].sum() for p in parts)
+        rr = max(costs[dp.shard_views(n, world, r)].sum() for r in range(world))
+        assert load <= rr + 1e-12
+        assert load <= 1.15 * costs.sum() / world
+    with pytest.raises(ValueError):
+        dp.shard_views(4, 2, 0, [1.0, 2.0])
