@@ -579,13 +579,311 @@ __global__ void __launch_bounds__(kFwdThreads, MINB)
         rb.tile_max_contrib[ft] = max(s_warp_tot[0], s_warp_tot[1]);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// forward blend, TMA gather (the default).  Same algorithm and arithmetic as k_blend_fwd<2, ., ., PK> (active-pixel
+// compaction, in-kernel expansion, FFMA2 evaluation, branch-free pixel update), but the per-tile Gaussian records of
+// the NEXT batch are staged into shared memory by the TMA engine: every thread issues one 64-byte cp.async.bulk of
+// "its" GaussRec (gathered through inst_gid) that completes on an mbarrier, blends the current batch while the copies
+// are in flight, then expands the raw records from shared memory.  No record ever passes through registers on its way
+// in (the register-staged version held 16 registers of prefetched record per thread).
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <bool EWA>
+__global__ void __launch_bounds__(kFwdThreads)
+    k_blend_fwd_tg(const RasterBuffers rb, const ViewCam* __restrict__ cams, const uint32_t width, const uint32_t height,
+                   const uint32_t tile_w, const uint32_t tile_h, const bool write_ckpt,
+                   const float* __restrict__ backgrounds, const uint8_t* __restrict__ masks, float* __restrict__ renders,
+                   float* __restrict__ alphas, int32_t* __restrict__ last_ids) {
+    __shared__ __align__(128) float4 s_raw[kBatch * 4]; // GaussRec of the next batch, written by the TMA engine
+    __shared__ __align__(16) float4 s_rec[2][kBatch * 4]; // expanded tile-local records (store_rec_pk layout)
+    __shared__ __align__(16) float4 s_state[kTilePix];    // (r, g, b, T) per pixel
+    __shared__ uint32_t s_ncon[kTilePix];
+    __shared__ uint8_t s_list[2][kTilePix];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_warp_tot[kFwdThreads / 32];
+    __shared__ uint32_t s_nact[2];
+
+    const uint32_t tile = blockIdx.x, cam = blockIdx.y;
+    const uint32_t n_tiles = tile_w * tile_h;
+    const uint32_t ft = cam * n_tiles + tile;
+    const uint32_t ty = tile / tile_w, tx = tile - ty * tile_w;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+
+    const int32_t start = rb.tile_off[ft];
+    int32_t end = rb.tile_off[ft + 1];
+    const int32_t cnt_raw = end > start ? end - start : 0;
+    if (masks && !masks[ft])
+        end = start;
+    const int32_t cnt = end > start ? end - start : 0;
+    const uint32_t boff = rb.bucket_off ? rb.bucket_off[ft] : 0u;
+    if (write_ckpt) { // bucket -> tile map for the backward (unmasked count: bucket_off is mask-agnostic)
+        const uint32_t nb = (uint32_t)(cnt_raw + kBucket - 1) / kBucket;
+        for (uint32_t k = tid; k < nb; k += kFwdThreads)
+            rb.bucket_tile[boff + k] = ft;
+    }
+    float4* ckpt_tile = write_ckpt ? rb.ckpt + (size_t)boff * kTilePix : nullptr;
+    if (tid == 0) {
+        mbar_init(&s_bar, kFwdThreads);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+
+    // ---- initial state + initial active list (pixels inside the image, row-major order)
+    uint32_t keep = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t p = tid * 4 + k;
+        s_state[p] = make_float4(0.f, 0.f, 0.f, 1.f);
+        s_ncon[p] = 0;
+        const uint32_t px = tx * kTile + (p & 15u), py = ty * kTile + (p >> 4);
+        keep |= (px < width && py < height ? 1u : 0u) << k;
+    }
+    int cur = 0;
+    auto compact = [&](const uint32_t keep_mask, const uint8_t ids[4], const int dst) {
+        const uint32_t c = __popc(keep_mask);
+        uint32_t x = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= (uint32_t)o)
+                x += y;
+        }
+        if (lane == 31)
+            s_warp_tot[warp] = x;
+        __syncthreads();
+        uint32_t base = x - c;
+        if (warp == 1)
+            base += s_warp_tot[0];
+        if (tid == kFwdThreads - 1)
+            s_nact[dst] = base + c;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if ((keep_mask >> k) & 1u)
+                s_list[dst][base++] = ids[k];
+        __syncthreads();
+    };
+    {
+        const uint8_t ids[4] = {(uint8_t)(tid * 4), (uint8_t)(tid * 4 + 1), (uint8_t)(tid * 4 + 2), (uint8_t)(tid * 4 + 3)};
+        compact(keep, ids, cur); // also orders the mbarrier init before its first use
+    }
+
+    const float Xo = (float)(tx * kTile + kTile / 2) - (EWA ? 0.f : cams[cam].cx);
+    const float Yo = (float)(ty * kTile + kTile / 2) - (EWA ? 0.f : cams[cam].cy);
+    const int nbatch = (cnt + kBatch - 1) / kBatch;
+    int n_issued = 0, n_waited = 0; // uniform over the CTA: completed phases of s_bar
+
+    // every thread arrives once per batch; those that own a record of the batch add 64 bytes to the transaction count
+    // and launch the copy (gathered address: rb.gauss + gid)
+    auto issue = [&](const int kb_next, const uint32_t gid) {
+        const int nrec = min(kBatch, cnt - kb_next * kBatch);
+        if ((int)tid < nrec) {
+            mbar_expect_tx(&s_bar, (uint32_t)sizeof(GaussRec));
+            tma_load_1d(&s_raw[4 * tid], rb.gauss + gid, (uint32_t)sizeof(GaussRec), &s_bar);
+        } else {
+            mbar_arrive(&s_bar);
+        }
+        ++n_issued;
+    };
+    auto wait_expand = [&](const int kb_next, const int dst) {
+        mbar_wait(&s_bar, (uint32_t)(n_waited & 1));
+        ++n_waited;
+        const int nrec = min(kBatch, cnt - kb_next * kBatch);
+        if ((int)tid < nrec) {
+            const float4 g0 = s_raw[4 * tid], g1 = s_raw[4 * tid + 1], g2 = s_raw[4 * tid + 2], g3 = s_raw[4 * tid + 3];
+            float4 A, B, Cc;
+            float4* d = &s_rec[dst][4 * tid];
+            if (EWA) {
+                expand_record_ewa(g0, g1, g2, Xo, Yo, A, B, Cc);
+                d[0] = A, d[1] = B, d[2] = Cc;
+            } else {
+                expand_record(g0, g1, g2, Xo, Yo, A, B, Cc);
+                store_rec_pk(d, A, B, Cc, g3);
+            }
+        }
+    };
+    auto load_gid = [&](const int kb_) -> uint32_t {
+        const int j = kb_ * kBatch + (int)tid;
+        return j < cnt ? (uint32_t)__ldg(rb.inst_gid + start + j) : 0u;
+    };
+
+    uint32_t gid_next = 0; // Gaussian id of this thread's record in the batch issued next
+    if (nbatch > 0) {
+        issue(0, load_gid(0));
+        gid_next = load_gid(1);
+        wait_expand(0, 0);
+        __syncthreads(); // s_rec[0] complete; every thread is done reading s_raw
+        if (nbatch > 1) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(1, gid_next);
+            gid_next = load_gid(2);
+        }
+    }
+
+    for (int kb = 0; kb < nbatch; ++kb) {
+        const int buf = kb & 1;
+        const uint32_t n_act = s_nact[cur];
+        if (n_act == 0)
+            break;
+        uint8_t pid[4];
+        float r[4], g[4], b[4], T[4], dx[4], dy[4];
+        uint32_t ncon[4];
+        uint32_t live = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t j = tid * 4 + k;
+            pid[k] = 0;
+            if (j < n_act) {
+                pid[k] = s_list[cur][j];
+                const float4 st = s_state[pid[k]];
+                r[k] = st.x, g[k] = st.y, b[k] = st.z, T[k] = st.w;
+                ncon[k] = s_ncon[pid[k]];
+                dx[k] = (float)(pid[k] & 15u) - 7.5f;
+                dy[k] = (float)(pid[k] >> 4) - 7.5f;
+                live |= 1u << k;
+            } else {
+                r[k] = g[k] = b[k] = 0.f, T[k] = 1.f, ncon[k] = 0, dx[k] = dy[k] = 0.f;
+            }
+        }
+        const uint32_t mine = live;
+
+        if (live) {
+            const float4* s = &s_rec[buf][0];
+            const int nrec = min(kBatch, cnt - kb * kBatch);
+            const uint32_t first_li = (uint32_t)(kb * kBatch);
+            for (int t = 0; t < nrec; ++t) {
+                const uint32_t li = first_li + t;
+                if (write_ckpt && (li & (kBucket - 1)) == 0) {
+                    float4* c = ckpt_tile + (size_t)(li >> 5) * kTilePix;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if ((live >> k) & 1u)
+                            c[pid[k]] = make_float4(r[k], g[k], b[k], T[k]);
+                }
+                const float4 R0 = s[4 * t], R1 = s[4 * t + 1], R2 = s[4 * t + 2];
+                if (EWA) { // R0 = (n0, n1x, n1y, n2xx), R1 = (n2xy, n2yy, opacity, max(r,0)), R2 = (max(g,0), max(b,0), -, -)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float Nv = poly2(dx[k], dy[k], R0.x, R0.y, R0.z, R0.w, R1.x, R1.y);
+                        const float alpha = fminf(kAlphaMax, R1.z * ex2_approx(Nv));
+                        // sigma/2 < 0 is skipped (kernels_forward.cuh:423-424); fastgs stops at T < 1e-4 (strict)
+                        const bool hit = ((live >> k) & 1u) && alpha >= kAlphaMin && Nv <= 0.f;
+                        const float next_T = T[k] * (1.0f - alpha);
+                        const bool stop = hit && next_T < kTMin;
+                        const bool acc = hit && !stop;
+                        const float w = acc ? alpha * T[k] : 0.f;
+                        r[k] = fmaf(w, R1.w, r[k]);
+                        g[k] = fmaf(w, R2.x, g[k]);
+                        b[k] = fmaf(w, R2.y, b[k]);
+                        T[k] = acc ? next_T : T[k];
+                        ncon[k] = acc ? li + 1 : ncon[k];
+                        live &= ~((stop ? 1u : 0u) << k);
+                    }
+                } else {
+                    const float4 E = s[4 * t + 3]; // (r, g, b, opacity)
+                    const float2 P0 = make_float2(R0.x, R0.y), P1 = make_float2(R0.z, R0.w), P2 = make_float2(R1.x, R1.y),
+                                 P3 = make_float2(R1.z, R1.w), P4 = make_float2(R2.x, R2.y), P5 = make_float2(R2.z, R2.w);
+                    const float2 Erg = make_float2(E.x, E.y);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float2 ND = poly2x2(make_float2(dx[k], dx[k]), make_float2(dy[k], dy[k]), P0, P1, P2, P3, P4,
+                                                  P5);
+                        const float vis = ex2_approx(ND.x * rcp_approx(ND.y));
+                        const float alpha = fminf(kAlphaMax, E.w * vis);
+                        const bool hit = ((live >> k) & 1u) && alpha >= kAlphaMin;
+                        const float next_T = T[k] * (1.0f - alpha);
+                        const bool stop = hit && next_T <= kTMin; // gsplat stops at T <= 1e-4 (...Fwd.cu:244-248)
+                        const bool acc = hit && !stop;
+                        const float w = acc ? alpha * T[k] : 0.f;
+                        const float2 rg = ffma2(make_float2(w, w), Erg, make_float2(r[k], g[k]));
+                        r[k] = rg.x, g[k] = rg.y;
+                        b[k] = fmaf(w, E.z, b[k]);
+                        T[k] = acc ? next_T : T[k];
+                        ncon[k] = acc ? li + 1 : ncon[k];
+                        live &= ~((stop ? 1u : 0u) << k);
+                    }
+                }
+                if (live == 0)
+                    break;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if ((mine >> k) & 1u) {
+                s_state[pid[k]] = make_float4(r[k], g[k], b[k], T[k]);
+                s_ncon[pid[k]] = ncon[k];
+            }
+        if (kb + 1 < nbatch) // the copies of batch kb + 1 have been in flight during the blend above
+            wait_expand(kb + 1, buf ^ 1);
+        // rebuild the active list only when some pixel finished in this batch; the barrier also means that every thread is
+        // done with s_raw and with s_rec[buf]
+        const int changed = __syncthreads_or((int)(live != mine));
+        if (changed) {
+            compact(live, pid, cur ^ 1);
+            cur ^= 1;
+        }
+        if (kb + 2 < nbatch && s_nact[cur] != 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(kb + 2, gid_next);
+            gid_next = load_gid(kb + 3);
+        }
+    }
+    // a batch may still be in flight into this CTA's shared memory (early exit, or no active pixel at all): drain it
+    while (n_waited < n_issued) {
+        mbar_wait(&s_bar, (uint32_t)(n_waited & 1));
+        ++n_waited;
+    }
+    __syncthreads();
+
+    // ---- outputs: thread t writes its 4 row-adjacent pixels (64 B contiguous per thread)
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t p = tid * 4 + k;
+        const uint32_t px = tx * kTile + (p & 15u), py = ty * kTile + (p >> 4);
+        if (!(px < width && py < height))
+            continue;
+        const float4 st = s_state[p];
+        const uint32_t nc = s_ncon[p];
+        m = max(m, nc);
+        const size_t pix = ((size_t)cam * height + py) * width + px;
+        rb.pix_state[pix] = st;
+        rb.n_contrib[pix] = (int32_t)nc;
+        if (renders) {
+            float br = 0.f, bgc = 0.f, bb = 0.f;
+            if (backgrounds) {
+                br = backgrounds[cam * 3], bgc = backgrounds[cam * 3 + 1], bb = backgrounds[cam * 3 + 2];
+            }
+            renders[pix * 3] = fmaf(st.w, br, st.x);
+            renders[pix * 3 + 1] = fmaf(st.w, bgc, st.y);
+            renders[pix * 3 + 2] = fmaf(st.w, bb, st.z);
+        }
+        if (alphas)
+            alphas[pix] = 1.0f - st.w;
+        if (last_ids)
+            last_ids[pix] = nc > 0 ? start + (int32_t)nc - 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0)
+        s_warp_tot[warp] = m;
+    __syncthreads();
+    if (tid == 0)
+        rb.tile_max_contrib[ft] = max(s_warp_tot[0], s_warp_tot[1]);
+}
+
 int launch_blend_fwd(const RasterBuffers& rb, const ViewCam* cams_dev, uint32_t C, uint32_t width, uint32_t height,
                      uint32_t tile_w, uint32_t tile_h, bool write_ckpt, const float* backgrounds, const uint8_t* masks,
                      float* renders, float* alphas, int32_t* last_ids, cudaStream_t stream) {
     if (C == 0 || tile_w == 0 || tile_h == 0)
         return LFS_OK;
     dim3 grid(tile_w * tile_h, C);
-    if (raster_options().fuse_expand && raster_options().fwd_variant == 1)
+    if (raster_options().fuse_expand && raster_options().fwd_variant == 4)
+        k_blend_fwd_tg<false><<<grid, kFwdThreads, 0, stream>>>(rb, cams_dev, width, height, tile_w, tile_h, write_ckpt,
+                                                               backgrounds, masks, renders, alphas, last_ids);
+    else if (raster_options().fuse_expand && raster_options().fwd_variant == 1)
         k_blend_fwd<2, false, 10><<<grid, kFwdThreads, 0, stream>>>(rb, cams_dev, width, height, tile_w, tile_h, write_ckpt,
                                                                    backgrounds, masks, renders, alphas, last_ids);
     else if (raster_options().fuse_expand && raster_options().fwd_variant == 3)
