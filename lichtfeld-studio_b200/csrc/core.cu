@@ -1,6 +1,7 @@
 // lfs_b200 -- error plumbing and library-level entry points.
 #include "common.cuh"
 #include "raster.cuh"
+#include "sort_scan.cuh"
 
 #include <atomic>
 #include <cstdarg>
@@ -59,6 +60,10 @@ extern "C" int lfs_set_option(const char* name, int value) {
     }
     if (name && std::string(name) == "exact_cull") {
         lfs::raster_options().exact_cull = value;
+        return LFS_OK;
+    }
+    if (name && std::string(name) == "sort_variant") {
+        lfs::set_sort_variant(value);
         return LFS_OK;
     }
     if (name && std::string(name) == "blend_fused") {

@@ -303,6 +303,221 @@ __global__ void __launch_bounds__(kRsThreads)
     }
 }
 
+// ------------------------------------------------------------------------------------------- onesweep
+// Single-sweep LSD passes (Adinets & Merrill, "Onesweep", 2022) with 8-bit digits: ONE histogram kernel reads the keys
+// once and counts the digits of every pass (the global digit histogram does not depend on the element order), then each
+// pass is ONE kernel: a tile of 4096 pairs is ranked in shared memory, publishes its digit counts, obtains its global
+// offsets by DECOUPLED LOOK-BACK over the preceding tiles' published counts, and scatters.  Compared with the
+// hist / scan-rows / scan-totals / scatter chain above this removes one full read of the keys and three small launches
+// per pass.  Tiles take their index from an atomic ticket, so a tile only ever waits for tiles whose CTAs are already
+// running (forward progress without relying on the block scheduler's order); the wait is bounded and a timeout raises
+// a device-side error flag instead of hanging.
+constexpr int kOsBits = 8, kOsDig = 1 << kOsBits, kOsMaxPass = 4;
+constexpr uint32_t kOsFlagAgg = 1u << 30, kOsFlagInc = 2u << 30, kOsValMask = (1u << 30) - 1u;
+
+struct OsPlan {
+    int n_pass;
+    int shift[kOsMaxPass];
+    int bits[kOsMaxPass];
+};
+static inline OsPlan make_os_plan(int begin, int total_bits) {
+    OsPlan p;
+    p.n_pass = (total_bits + kOsBits - 1) / kOsBits;
+    int done = 0;
+    for (int i = 0; i < p.n_pass; ++i) { // balanced digits: 13 bits -> 7 + 6
+        const int b = (total_bits - done + (p.n_pass - i) - 1) / (p.n_pass - i);
+        p.bits[i] = b, p.shift[i] = begin + done;
+        done += b;
+    }
+    return p;
+}
+
+// ghist [n_pass][256] digit counts of the whole input (zeroed by the caller)
+__global__ void __launch_bounds__(kRsThreads)
+    k_os_hist(const uint32_t* __restrict__ keys, uint32_t n_cap, const uint32_t* __restrict__ n_dev, const OsPlan plan,
+              uint32_t* __restrict__ ghist) {
+    __shared__ uint32_t sh[kOsMaxPass * kOsDig];
+    const uint32_t n = resolve_n(n_cap, n_dev);
+    for (int d = threadIdx.x; d < plan.n_pass * kOsDig; d += kRsThreads)
+        sh[d] = 0;
+    __syncthreads();
+    const uint32_t n4 = n >> 2;
+    const bool al = (reinterpret_cast<uintptr_t>(keys) & 15u) == 0;
+    auto count = [&](const uint32_t k) {
+#pragma unroll
+        for (int p = 0; p < kOsMaxPass; ++p)
+            if (p < plan.n_pass)
+                atomicAdd(&sh[p * kOsDig + ((k >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u))], 1u);
+    };
+    if (al) {
+        const uint4* k4 = reinterpret_cast<const uint4*>(keys);
+        for (uint32_t i = blockIdx.x * kRsThreads + threadIdx.x; i < n4; i += gridDim.x * kRsThreads) {
+            const uint4 v = __ldg(k4 + i);
+            count(v.x), count(v.y), count(v.z), count(v.w);
+        }
+        for (uint32_t i = (n4 << 2) + blockIdx.x * kRsThreads + threadIdx.x; i < n; i += gridDim.x * kRsThreads)
+            count(__ldg(keys + i));
+    } else {
+        for (uint32_t i = blockIdx.x * kRsThreads + threadIdx.x; i < n; i += gridDim.x * kRsThreads)
+            count(__ldg(keys + i));
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < plan.n_pass * kOsDig; d += kRsThreads)
+        if (sh[d])
+            atomicAdd(&ghist[d], sh[d]);
+}
+
+// One pass.  status [n_tiles][256]: (flag << 30) | count, zeroed by the caller; ticket: tile counter of this pass (zeroed);
+// err: set to 1 on a look-back timeout.
+__global__ void __launch_bounds__(kRsThreads)
+    k_os_pass(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
+              uint32_t* __restrict__ vals_out, uint32_t n_cap, const uint32_t* __restrict__ n_dev, const int shift,
+              const int bits, const uint32_t* __restrict__ ghist /* [256] of this pass */, uint32_t* __restrict__ status,
+              uint32_t* __restrict__ ticket, uint32_t* __restrict__ err) {
+    constexpr int kWarps = kRsThreads / 32;
+    __shared__ uint32_t whist[kWarps * kOsDig]; // warp-private digit counts -> exclusive prefix over the warps
+    __shared__ uint32_t sbase[kOsDig];          // global position of this tile's run of digit d
+    __shared__ uint32_t dstart[kOsDig];         // tile-local start of digit d
+    __shared__ uint32_t skey[kRsTile], sval[kRsTile];
+    __shared__ uint32_t s_scan[33];
+    __shared__ uint32_t s_tile;
+    const uint32_t n = resolve_n(n_cap, n_dev);
+    if (threadIdx.x == 0)
+        s_tile = atomicAdd(ticket, 1u);
+    for (int d = threadIdx.x; d < kWarps * kOsDig; d += kRsThreads)
+        whist[d] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t blk_base = tile * kRsTile;
+    if (blk_base >= n)
+        return;
+    const uint32_t dmask = (1u << bits) - 1u;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t wbase = blk_base + warp * (kRsItems * 32);
+    uint32_t* wh = whist + warp * kOsDig;
+    uint32_t key[kRsItems], val[kRsItems], lrank[kRsItems];
+#pragma unroll
+    for (int r = 0; r < kRsItems; ++r) {
+        const uint32_t i = wbase + r * 32 + lane;
+        const bool valid = i < n;
+        key[r] = valid ? __ldg(keys_in + i) : 0u;
+        val[r] = valid ? __ldg(vals_in + i) : 0u;
+        const uint32_t d = valid ? ((key[r] >> shift) & dmask) : (uint32_t)kOsDig;
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t rank = __popc(peers & lt_mask);
+        const int leader = __ffs(peers) - 1;
+        uint32_t before = 0;
+        if (valid && rank == 0) // same-address atomics of one warp retire in program order -> ranks stay stable
+            before = atomicAdd(&wh[d], (uint32_t)__popc(peers));
+        before = __shfl_sync(0xffffffffu, before, leader);
+        lrank[r] = before + rank;
+    }
+    __syncthreads();
+    // one thread per digit: counts of this tile, publish, look back, global base
+    {
+        const int d = threadIdx.x; // kRsThreads == kOsDig
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            const uint32_t t = whist[w * kOsDig + d];
+            whist[w * kOsDig + d] = run;
+            run += t;
+        }
+        dstart[d] = run; // count; scanned below
+        volatile uint32_t* st = status + (size_t)tile * kOsDig + d;
+        if (tile == 0) {
+            *st = kOsFlagInc | run;
+        } else {
+            *st = kOsFlagAgg | run;
+        }
+        __threadfence();
+        uint32_t excl = 0;
+        if (tile > 0) {
+            int t = (int)tile - 1;
+            uint32_t spins = 0;
+            while (true) {
+                const uint32_t v = *(volatile uint32_t*)(status + (size_t)t * kOsDig + d);
+                const uint32_t flag = v & ~kOsValMask;
+                if (flag == 0) {
+                    if (++spins > (1u << 26)) { // ~ seconds: a predecessor never published -> report, do not hang
+                        *err = 1u;
+                        break;
+                    }
+                    continue;
+                }
+                excl += v & kOsValMask;
+                if (flag == kOsFlagInc || t == 0)
+                    break;
+                --t;
+            }
+            __threadfence();
+            *st = kOsFlagInc | ((excl + run) & kOsValMask);
+        }
+        // exclusive scan of the global digit histogram (256 values, every tile redundantly: cheaper than a launch)
+        uint32_t total;
+        const uint32_t gh = __ldg(ghist + d);
+        const uint32_t gincl = block_inclusive_scan(gh, s_scan, &total);
+        sbase[d] = gincl - gh + excl;
+        // tile-local starts
+        const uint32_t lincl = block_inclusive_scan(run, s_scan, &total);
+        dstart[d] = lincl - run;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kRsItems; ++r) {
+        const uint32_t i = wbase + r * 32 + lane;
+        if (i < n) {
+            const uint32_t d = (key[r] >> shift) & dmask;
+            const uint32_t lp = dstart[d] + wh[d] + lrank[r];
+            skey[lp] = key[r];
+            sval[lp] = val[r];
+        }
+    }
+    __syncthreads();
+    const uint32_t n_here = n - blk_base < (uint32_t)kRsTile ? n - blk_base : (uint32_t)kRsTile;
+    for (uint32_t t = threadIdx.x; t < n_here; t += kRsThreads) {
+        const uint32_t k = skey[t];
+        const uint32_t d = (k >> shift) & dmask;
+        const uint32_t pos = sbase[d] + (t - dstart[d]);
+        keys_out[pos] = k;
+        vals_out[pos] = sval[t];
+    }
+}
+
+static int g_sort_variant = 0;
+void set_sort_variant(int v) { g_sort_variant = v; }
+
+static int radix_sort_pairs_onesweep(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t n_cap,
+                                     const uint32_t* n_dev, int begin_bit, int n_bits, void* scratch, int* result_in_b,
+                                     cudaStream_t stream) {
+    static_assert(kRsThreads == kOsDig, "one thread per digit");
+    const OsPlan plan = make_os_plan(begin_bit, n_bits);
+    const uint32_t ntiles = div_up(n_cap, kRsTile);
+    // scratch layout: ghist [4][256] | ticket [4] | err [1] | pad | status [n_pass][ntiles][256]
+    uint32_t* ghist = static_cast<uint32_t*>(scratch);
+    uint32_t* ticket = ghist + kOsMaxPass * kOsDig;
+    uint32_t* err = ticket + kOsMaxPass;
+    uint32_t* status = ghist + kOsMaxPass * kOsDig + 64;
+    const size_t zero_bytes = sizeof(uint32_t) * (kOsMaxPass * kOsDig + 64 + (size_t)plan.n_pass * ntiles * kOsDig);
+    LFS_CUDA_OK(cudaMemsetAsync(scratch, 0, zero_bytes, stream));
+    const unsigned hgrid = ntiles < (unsigned)(num_sms() * 8) ? ntiles : (unsigned)(num_sms() * 8);
+    k_os_hist<<<hgrid, kRsThreads, 0, stream>>>(keys_a, n_cap, n_dev, plan, ghist);
+    LFS_LAUNCH_OK("k_os_hist");
+    uint32_t *kin = keys_a, *vin = vals_a, *kout = keys_b, *vout = vals_b;
+    for (int p = 0; p < plan.n_pass; ++p) {
+        k_os_pass<<<ntiles, kRsThreads, 0, stream>>>(kin, vin, kout, vout, n_cap, n_dev, plan.shift[p], plan.bits[p],
+                                                     ghist + p * kOsDig, status + (size_t)p * ntiles * kOsDig, ticket + p, err);
+        LFS_LAUNCH_OK("k_os_pass");
+        uint32_t* t = kin;
+        kin = kout, kout = t;
+        t = vin;
+        vin = vout, vout = t;
+    }
+    *result_in_b = (plan.n_pass & 1);
+    return LFS_OK;
+}
+
 static size_t rs_scatter_smem(int ndig) {
     return sizeof(uint32_t) * ((size_t)(kRsThreads / 32 + 2) * ndig + 2 * (size_t)kRsTile);
 }
@@ -313,6 +528,9 @@ int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint3
     *result_in_b = 0;
     if (n_cap == 0 || n_bits <= 0)
         return LFS_OK;
+    if (g_sort_variant == 1 && n_bits <= kOsBits * kOsMaxPass && n_cap < (1u << 30))
+        return radix_sort_pairs_onesweep(keys_a, vals_a, keys_b, vals_b, n_cap, n_dev, begin_bit, n_bits, scratch,
+                                         result_in_b, stream);
     // per-device attribute; cheap enough to set on every call (one process may drive several devices)
     LFS_CUDA_OK(cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)rs_scatter_smem(1 << kRsMaxBits)));
