@@ -68,13 +68,13 @@ struct Carver {
 struct f3 {
     float x, y, z;
 };
-__device__ __forceinline__ f3 mk3(float x, float y, float z) { return f3{x, y, z}; }
-__device__ __forceinline__ f3 operator+(f3 a, f3 b) { return f3{a.x + b.x, a.y + b.y, a.z + b.z}; }
-__device__ __forceinline__ f3 operator-(f3 a, f3 b) { return f3{a.x - b.x, a.y - b.y, a.z - b.z}; }
-__device__ __forceinline__ f3 operator*(f3 a, float s) { return f3{a.x * s, a.y * s, a.z * s}; }
-__device__ __forceinline__ f3 operator*(float s, f3 a) { return f3{a.x * s, a.y * s, a.z * s}; }
-__device__ __forceinline__ float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-__device__ __forceinline__ f3 cross(f3 a, f3 b) {
+__host__ __device__ __forceinline__ f3 mk3(float x, float y, float z) { return f3{x, y, z}; }
+__host__ __device__ __forceinline__ f3 operator+(f3 a, f3 b) { return f3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+__host__ __device__ __forceinline__ f3 operator-(f3 a, f3 b) { return f3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+__host__ __device__ __forceinline__ f3 operator*(f3 a, float s) { return f3{a.x * s, a.y * s, a.z * s}; }
+__host__ __device__ __forceinline__ f3 operator*(float s, f3 a) { return f3{a.x * s, a.y * s, a.z * s}; }
+__host__ __device__ __forceinline__ float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__host__ __device__ __forceinline__ f3 cross(f3 a, f3 b) {
     return f3{a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y};
 }
 
@@ -122,7 +122,7 @@ __host__ __device__ __forceinline__ quat4 quat_from_rowmajor_rot(const float* m 
     }
     return q;
 }
-__device__ __forceinline__ f3 quat_rotate(quat4 q, f3 v) {
+__host__ __device__ __forceinline__ f3 quat_rotate(quat4 q, f3 v) {
     const f3 u = mk3(q.x, q.y, q.z);
     const f3 uv = cross(u, v);
     const f3 uuv = cross(u, uv);

@@ -38,8 +38,11 @@ __global__ void __launch_bounds__(kProjThreads)
                     const float* __restrict__ opacities, const float* __restrict__ viewmats,
                     const float* __restrict__ Ks, const uint32_t width, const uint32_t height, const float eps2d,
                     const float near_plane, const float far_plane, const float radius_clip,
-                    const lfs_ut_params ut, int32_t* __restrict__ radii, float* __restrict__ means2d,
-                    float* __restrict__ depths, float* __restrict__ conics, float* __restrict__ compensations) {
+                    const lfs_ut_params ut, const int camera_model, const int rs_type,
+                    const float* __restrict__ viewmats1, const float* __restrict__ radial,
+                    const float* __restrict__ tangential, const float* __restrict__ prism,
+                    int32_t* __restrict__ radii, float* __restrict__ means2d, float* __restrict__ depths,
+                    float* __restrict__ conics, float* __restrict__ compensations) {
     __shared__ __align__(16) float s_mean[kProjThreads * 3];
     __shared__ __align__(16) float s_scale[kProjThreads * 3];
     // grid: x over Gaussian blocks, y over cameras
@@ -60,8 +63,18 @@ __global__ void __launch_bounds__(kProjThreads)
     const float4 q = ldg4(quats + 4 * (size_t)gid);
     const float op = opacities ? __ldg(opacities + gid) : 0.f;
 
-    const UTOut o = ut_project_pinhole(cam, mean, q, scale, opacities != nullptr, op, eps2d, near_plane, far_plane,
-                                       radius_clip, ut);
+    // perfect pinhole + global shutter keeps the specialised routine; everything else goes through the camera model
+    const bool general = camera_model != LFS_PINHOLE || rs_type != kRsGlobal || viewmats1 || radial || tangential || prism;
+    UTOut o;
+    if (general) {
+        const int n_rad = camera_model == LFS_FISHEYE ? 4 : 6;
+        const CamModel cmod = make_cam_model(viewmats + 16 * cid, viewmats1 ? viewmats1 + 16 * cid : nullptr, Ks + 9 * cid,
+                                             width, height, camera_model, rs_type, radial ? radial + n_rad * cid : nullptr,
+                                             tangential ? tangential + 2 * cid : nullptr, prism ? prism + 4 * cid : nullptr);
+        o = ut_project_general(cmod, mean, q, scale, opacities != nullptr, op, eps2d, near_plane, far_plane, radius_clip, ut);
+    } else {
+        o = ut_project_pinhole(cam, mean, q, scale, opacities != nullptr, op, eps2d, near_plane, far_plane, radius_clip, ut);
+    }
     int2 r = make_int2(0, 0);
     if (o.ok) {
         r = make_int2((int32_t)o.rx, (int32_t)o.ry);
@@ -91,18 +104,20 @@ extern "C" int lfs_projection_ut_3dgs_fused(const float* means, const float* qua
     LFS_CHECK_ARG(means && quats && scales && viewmats0 && Ks && radii && means2d && depths && conics,
                   "projection_ut: null required pointer");
     LFS_CHECK_ARG(ut_params != nullptr, "projection_ut: ut_params is null");
-    LFS_UNSUPPORTED(camera_model != LFS_PINHOLE, "projection_ut: only the PINHOLE camera model is implemented");
-    LFS_UNSUPPORTED(rs_type != LFS_GLOBAL || viewmats1 != nullptr,
-                    "projection_ut: rolling shutter is not implemented (GLOBAL shutter only)");
-    LFS_UNSUPPORTED(radial_coeffs || tangential_coeffs || thin_prism_coeffs,
-                    "projection_ut: lens distortion is not implemented");
+    // the reference's UT projection has no ORTHO branch either (ProjectionUT3DGSFused.cu:84-140 asserts)
+    LFS_UNSUPPORTED(camera_model != LFS_PINHOLE && camera_model != LFS_FISHEYE,
+                    "projection_ut: camera model %d is not supported by the unscented-transform projection", camera_model);
+    LFS_CHECK_ARG(rs_type >= 0 && rs_type <= LFS_GLOBAL, "projection_ut: bad shutter type %d", rs_type);
+    LFS_CHECK_ARG(camera_model != LFS_FISHEYE || (!tangential_coeffs && !thin_prism_coeffs),
+                  "projection_ut: the fisheye model takes radial coefficients only");
     if (N == 0 || C == 0)
         return LFS_OK;
     LFS_CHECK_ARG(C <= 65535, "projection_ut: C too large");
     dim3 grid(div_up(N, kProjThreads), C);
     k_projection_ut<<<grid, kProjThreads, 0, (cudaStream_t)stream>>>(
         C, N, means, quats, scales, opacities, viewmats0, Ks, image_width, image_height, eps2d, near_plane, far_plane,
-        radius_clip, *ut_params, radii, means2d, depths, conics, compensations);
+        radius_clip, *ut_params, camera_model, rs_type, viewmats1, radial_coeffs, tangential_coeffs, thin_prism_coeffs, radii,
+        means2d, depths, conics, compensations);
     LFS_LAUNCH_OK("k_projection_ut");
     return LFS_OK;
 }

@@ -910,8 +910,12 @@ int launch_blend_fwd_ewa(const RasterBuffers& rb, uint32_t width, uint32_t heigh
                          bool write_ckpt, cudaStream_t stream) {
     if (tile_w == 0 || tile_h == 0)
         return LFS_OK;
-    k_blend_fwd<2, true><<<dim3(tile_w * tile_h, 1), kFwdThreads, 0, stream>>>(
-        rb, nullptr, width, height, tile_w, tile_h, write_ckpt, nullptr, nullptr, nullptr, nullptr, nullptr);
+    if (raster_options().fwd_variant == 4)
+        k_blend_fwd_tg<true><<<dim3(tile_w * tile_h, 1), kFwdThreads, 0, stream>>>(
+            rb, nullptr, width, height, tile_w, tile_h, write_ckpt, nullptr, nullptr, nullptr, nullptr, nullptr);
+    else
+        k_blend_fwd<2, true><<<dim3(tile_w * tile_h, 1), kFwdThreads, 0, stream>>>(
+            rb, nullptr, width, height, tile_w, tile_h, write_ckpt, nullptr, nullptr, nullptr, nullptr, nullptr);
     LFS_LAUNCH_OK("k_blend_fwd<ewa>");
     return LFS_OK;
 }
@@ -1528,9 +1532,14 @@ int launch_blend_bwd_ewa(const RasterBuffers& rb, const float4* v_pix, uint32_t 
                          float* v_mean2d, float* v_conic, float* v_color, float* v_raw_opacity, cudaStream_t stream) {
     if (n_bucket_cap == 0)
         return LFS_OK;
-    k_blend_bwd<true, 4, 1, true><<<div_up(n_bucket_cap, 4), 4 * 32, 0, stream>>>(
-        rb, nullptr, v_pix, nullptr, nullptr, nullptr, N, width, height, tile_w, tile_h, n_bucket_cap, n_buckets_dev,
-        v_mean2d, v_conic, nullptr, v_color, v_raw_opacity);
+    if (raster_options().bwd_variant == 6)
+        k_blend_bwd_sp<true, 4><<<div_up(n_bucket_cap, 4), 4 * 32, 0, stream>>>(
+            rb, nullptr, v_pix, nullptr, nullptr, nullptr, N, width, height, tile_w, tile_h, n_bucket_cap, n_buckets_dev,
+            v_mean2d, v_conic, nullptr, v_color, v_raw_opacity);
+    else
+        k_blend_bwd<true, 4, 1, true><<<div_up(n_bucket_cap, 4), 4 * 32, 0, stream>>>(
+            rb, nullptr, v_pix, nullptr, nullptr, nullptr, N, width, height, tile_w, tile_h, n_bucket_cap, n_buckets_dev,
+            v_mean2d, v_conic, nullptr, v_color, v_raw_opacity);
     LFS_LAUNCH_OK("k_blend_bwd<ewa>");
     return LFS_OK;
 }

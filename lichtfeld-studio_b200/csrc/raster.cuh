@@ -103,4 +103,21 @@ int launch_blend_bwd_ewa(const RasterBuffers& rb, const float4* v_pix, uint32_t 
                          uint32_t tile_w, uint32_t tile_h, uint32_t n_bucket_cap, const uint32_t* n_buckets_dev,
                          float* v_mean2d, float* v_conic, float* v_color, float* v_raw_opacity, cudaStream_t stream);
 
+// ---- arbitrary per-pixel rays (raster_rays.cu): OpenCV distortion, fisheye, rolling shutter --------------------------
+// `scratch` (rays_scratch_bytes) holds one RayRec per pixel and one GenRec per (camera, Gaussian)
+size_t rays_scratch_bytes(uint32_t C, uint32_t N, uint64_t n_pix);
+int launch_rays_prepare(void* scratch, const float* means, const float* quats, const float* scales, const float* colors,
+                        const float* opacities, uint32_t N, uint32_t C, uint32_t channels, uint32_t ch0, uint32_t width,
+                        uint32_t height, const float* viewmats0, const float* viewmats1, const float* Ks, int camera_model,
+                        int rs_type, const float* radial, const float* tangential, const float* prism, bool make_rays,
+                        cudaStream_t stream);
+int launch_blend_fwd_rays(const RasterBuffers& rb, void* scratch, uint32_t C, uint32_t N, uint32_t width, uint32_t height,
+                          uint32_t tile_w, uint32_t tile_h, bool write_ckpt, const float* backgrounds, const uint8_t* masks,
+                          float* renders, float* alphas, int32_t* last_ids, cudaStream_t stream);
+int launch_blend_bwd_rays(const RasterBuffers& rb, void* scratch, const float4* v_pix, const float* quats,
+                          const float* scales, const float* means, uint32_t C, uint32_t N, uint32_t width, uint32_t height,
+                          uint32_t tile_w, uint32_t tile_h, uint32_t n_bucket_cap, const uint32_t* n_buckets_dev,
+                          float* v_means, float* v_quats, float* v_scales, float* v_colors, float* v_opacities,
+                          cudaStream_t stream);
+
 } // namespace lfs

@@ -131,12 +131,13 @@ struct RasterScratch {
     int32_t* n_contrib;
     float4* v_pix;
     float* v_colors_group; // [C*N,3] gradient of one channel group (channels != 3)
+    void* rays;            // RayRec per pixel + GenRec per (camera, Gaussian): cameras with non-affine rays only
     void* scan_scratch;
     size_t bytes;
 };
 
 static RasterScratch carve_scratch(void* blob, uint32_t C, uint32_t N, uint32_t n_tiles_total, uint64_t n_isects,
-                                   uint64_t n_pix, bool bwd, uint32_t channels = 3) {
+                                   uint64_t n_pix, bool bwd, uint32_t channels = 3, bool general = false) {
     Carver c(blob);
     RasterScratch s;
     s.cams = c.take<ViewCam>(C);
@@ -150,6 +151,7 @@ static RasterScratch carve_scratch(void* blob, uint32_t C, uint32_t N, uint32_t 
     s.pix_state = c.take<float4>(n_pix);
     s.n_contrib = c.take<int32_t>(n_pix);
     s.scan_scratch = c.take<char>(scan_scratch_bytes(n_tiles_total + 1));
+    s.rays = general ? c.take<char>(rays_scratch_bytes(C, N, n_pix)) : nullptr;
     const uint64_t n_bucket_cap = n_isects / kBucket + n_tiles_total + 1;
     if (bwd) {
         s.bucket_tile = c.take<uint32_t>(n_bucket_cap);
@@ -167,11 +169,18 @@ static RasterScratch carve_scratch(void* blob, uint32_t C, uint32_t N, uint32_t 
 }
 
 static int check_common(uint32_t tile_size, int camera_model, int rs_type, const float* viewmats1,
-                        const float* radial, const float* tangential, const float* thin_prism, const char* who) {
+                        const float* radial, const float* tangential, const float* thin_prism, const char* who,
+                        bool* general) {
     LFS_UNSUPPORTED(tile_size != (uint32_t)kTile, "%s: tile_size %u not implemented (16 only)", who, tile_size);
-    LFS_UNSUPPORTED(camera_model != LFS_PINHOLE, "%s: only the PINHOLE camera model is implemented", who);
-    LFS_UNSUPPORTED(rs_type != LFS_GLOBAL || viewmats1 != nullptr, "%s: rolling shutter is not implemented", who);
-    LFS_UNSUPPORTED(radial || tangential || thin_prism, "%s: lens distortion is not implemented", who);
+    // the reference's kernels have no ORTHO branch either (RasterizeToPixelsFromWorld3DGSFwd.cu:88-130 asserts)
+    LFS_UNSUPPORTED(camera_model != LFS_PINHOLE && camera_model != LFS_FISHEYE, "%s: camera model %d is not supported", who,
+                    camera_model);
+    LFS_CHECK_ARG(rs_type >= 0 && rs_type <= LFS_GLOBAL, "%s: bad shutter type %d", who, rs_type);
+    LFS_CHECK_ARG(camera_model != LFS_FISHEYE || (!tangential && !thin_prism),
+                  "%s: the fisheye model takes radial coefficients only", who);
+    // perfect pinhole + global shutter: rays are affine in the pixel -> tile-local rational-quadratic kernels; anything
+    // else blends along per-pixel rays (raster_rays.cu)
+    *general = camera_model != LFS_PINHOLE || rs_type != LFS_GLOBAL || viewmats1 || radial || tangential || thin_prism;
     return LFS_OK;
 }
 
@@ -180,14 +189,16 @@ static int raster_front(const RasterScratch& s, RasterBuffers& rb, const float* 
                         const float* scales, const float* colors, const float* opacities, uint32_t N, uint32_t C,
                         uint32_t width, uint32_t height, const float* viewmats, const float* Ks,
                         const int32_t* tile_offsets, const int32_t* flatten_ids, int64_t n_isects, bool bwd,
-                        cudaStream_t stream, uint32_t channels = 3, uint32_t ch0 = 0) {
+                        cudaStream_t stream, uint32_t channels = 3, uint32_t ch0 = 0, bool general = false) {
     const uint32_t tile_w = (width + kTile - 1) / kTile, tile_h = (height + kTile - 1) / kTile;
     const uint32_t n_tiles = tile_w * tile_h, n_tiles_total = C * n_tiles;
     k_make_cams<<<div_up(C, 32), 32, 0, stream>>>(viewmats, Ks, C, (int)width, (int)height, s.cams);
     LFS_LAUNCH_OK("k_make_cams");
-    k_prep_gaussians<<<div_up((uint64_t)C * N, 256), 256, 0, stream>>>(means, quats, scales, colors, opacities, s.cams, N,
-                                                                       C * N, channels, ch0, s.gauss);
-    LFS_LAUNCH_OK("k_prep_gaussians");
+    if (!general) {
+        k_prep_gaussians<<<div_up((uint64_t)C * N, 256), 256, 0, stream>>>(means, quats, scales, colors, opacities, s.cams, N,
+                                                                           C * N, channels, ch0, s.gauss);
+        LFS_LAUNCH_OK("k_prep_gaussians");
+    }
     k_copy_offsets<<<div_up(n_tiles_total + 1, 256), 256, 0, stream>>>(tile_offsets, n_tiles_total, (int32_t)n_isects,
                                                                        s.tile_off);
     LFS_LAUNCH_OK("k_copy_offsets");
@@ -202,7 +213,7 @@ static int raster_front(const RasterScratch& s, RasterBuffers& rb, const float* 
     rb.pix_state = s.pix_state;
     rb.n_contrib = s.n_contrib;
     int rc = LFS_OK;
-    if (!raster_options().fuse_expand) {
+    if (!general && !raster_options().fuse_expand) {
         rc = launch_expand_instances(rb, s.cams, n_tiles, tile_w, (uint32_t)n_isects, nullptr, nullptr, C, N, stream);
         if (rc)
             return rc;
@@ -235,8 +246,9 @@ extern "C" int lfs_rasterize_to_pixels_from_world_3dgs_fwd(
                   "rasterize_fwd: null required pointer");
     LFS_CHECK_ARG(n_isects == 0 || flatten_ids, "rasterize_fwd: flatten_ids is null");
     LFS_CHECK_ARG(channels >= 1 && channels <= 513, "rasterize_fwd: channels=%u out of range", channels);
+    bool general = false;
     int rc = check_common(tile_size, camera_model, rs_type, viewmats1, radial_coeffs, tangential_coeffs,
-                          thin_prism_coeffs, "rasterize_fwd");
+                          thin_prism_coeffs, "rasterize_fwd", &general);
     if (rc)
         return rc;
     if (C == 0 || image_width == 0 || image_height == 0)
@@ -245,14 +257,39 @@ extern "C" int lfs_rasterize_to_pixels_from_world_3dgs_fwd(
     const uint32_t tile_w = (image_width + kTile - 1) / kTile, tile_h = (image_height + kTile - 1) / kTile;
     const uint32_t n_tiles_total = C * tile_w * tile_h;
     const uint64_t n_pix = (uint64_t)C * image_width * image_height;
-    RasterScratch sz = carve_scratch(nullptr, C, N, n_tiles_total, (uint64_t)n_isects, n_pix, false);
+    RasterScratch sz = carve_scratch(nullptr, C, N, n_tiles_total, (uint64_t)n_isects, n_pix, false, 3, general);
     void* blob = alloc(alloc_ctx, LFS_TAG_SCRATCH, sz.bytes);
     if (!blob) {
         set_error("rasterize_fwd: scratch allocation of %zu bytes failed", sz.bytes);
         return LFS_ERR_ALLOC;
     }
-    RasterScratch s = carve_scratch(blob, C, N, n_tiles_total, (uint64_t)n_isects, n_pix, false);
+    RasterScratch s = carve_scratch(blob, C, N, n_tiles_total, (uint64_t)n_isects, n_pix, false, 3, general);
     RasterBuffers rb{};
+    if (general) { // per-pixel rays; channel groups of three as below
+        for (uint32_t ch0 = 0; ch0 < channels; ch0 += 3) {
+            rc = raster_front(s, rb, means, quats, scales, colors, opacities, N, C, image_width, image_height, viewmats0, Ks,
+                              tile_offsets, flatten_ids, n_isects, false, stream, channels, ch0, true);
+            if (rc)
+                return rc;
+            rc = launch_rays_prepare(s.rays, means, quats, scales, colors, opacities, N, C, channels, ch0, image_width,
+                                     image_height, viewmats0, viewmats1, Ks, camera_model, rs_type, radial_coeffs,
+                                     tangential_coeffs, thin_prism_coeffs, ch0 == 0, stream);
+            if (rc)
+                return rc;
+            const bool direct = channels == 3;
+            rc = launch_blend_fwd_rays(rb, s.rays, C, N, image_width, image_height, tile_w, tile_h, false,
+                                       direct ? backgrounds : nullptr, masks, direct ? renders : nullptr,
+                                       ch0 == 0 ? alphas : nullptr, ch0 == 0 ? last_ids : nullptr, stream);
+            if (rc)
+                return rc;
+            if (!direct) {
+                k_export_group<<<div_up(n_pix, 256), 256, 0, stream>>>(s.pix_state, backgrounds, image_width * image_height,
+                                                                       (uint32_t)n_pix, channels, ch0, renders);
+                LFS_LAUNCH_OK("k_export_group");
+            }
+        }
+        return LFS_OK;
+    }
     if (channels == 3) {
         rc = raster_front(s, rb, means, quats, scales, colors, opacities, N, C, image_width, image_height, viewmats0, Ks,
                           tile_offsets, flatten_ids, n_isects, false, stream);
@@ -296,8 +333,9 @@ extern "C" int lfs_rasterize_to_pixels_from_world_3dgs_bwd(
                       render_alphas && last_ids && v_render_colors && v_render_alphas && alloc && v_means && v_quats &&
                       v_scales && v_colors && v_opacities,
                   "rasterize_bwd: null required pointer");
+    bool general = false;
     int rc = check_common(tile_size, camera_model, rs_type, viewmats1, radial_coeffs, tangential_coeffs,
-                          thin_prism_coeffs, "rasterize_bwd");
+                          thin_prism_coeffs, "rasterize_bwd", &general);
     if (rc)
         return rc;
     LFS_CUDA_OK(cudaMemsetAsync(v_means, 0, sizeof(float) * 3 * (size_t)N, stream));
@@ -312,13 +350,13 @@ extern "C" int lfs_rasterize_to_pixels_from_world_3dgs_bwd(
     const uint32_t tile_w = (image_width + kTile - 1) / kTile, tile_h = (image_height + kTile - 1) / kTile;
     const uint32_t n_tiles_total = C * tile_w * tile_h;
     const uint64_t n_pix = (uint64_t)C * image_width * image_height;
-    RasterScratch sz = carve_scratch(nullptr, C, N, n_tiles_total, (uint64_t)n_isects, n_pix, true, channels);
+    RasterScratch sz = carve_scratch(nullptr, C, N, n_tiles_total, (uint64_t)n_isects, n_pix, true, channels, general);
     void* blob = alloc(alloc_ctx, LFS_TAG_SCRATCH, sz.bytes);
     if (!blob) {
         set_error("rasterize_bwd: scratch allocation of %zu bytes failed", sz.bytes);
         return LFS_ERR_ALLOC;
     }
-    RasterScratch s = carve_scratch(blob, C, N, n_tiles_total, (uint64_t)n_isects, n_pix, true, channels);
+    RasterScratch s = carve_scratch(blob, C, N, n_tiles_total, (uint64_t)n_isects, n_pix, true, channels, general);
     RasterBuffers rb{};
     const uint32_t n_bucket_cap = (uint32_t)((uint64_t)n_isects / kBucket + n_tiles_total + 1);
     if (channels != 3)
@@ -327,20 +365,35 @@ extern "C" int lfs_rasterize_to_pixels_from_world_3dgs_bwd(
     // over the groups, the alpha gradient enters with the first group only
     for (uint32_t ch0 = 0; ch0 < channels; ch0 += 3) {
         rc = raster_front(s, rb, means, quats, scales, colors, opacities, N, C, image_width, image_height, viewmats0, Ks,
-                          tile_offsets, flatten_ids, n_isects, true, stream, channels, ch0);
+                          tile_offsets, flatten_ids, n_isects, true, stream, channels, ch0, general);
         if (rc)
             return rc;
-        rc = launch_blend_fwd(rb, s.cams, C, image_width, image_height, tile_w, tile_h, true, nullptr, masks, nullptr,
-                              nullptr, nullptr, stream);
+        if (general) {
+            rc = launch_rays_prepare(s.rays, means, quats, scales, colors, opacities, N, C, channels, ch0, image_width,
+                                     image_height, viewmats0, viewmats1, Ks, camera_model, rs_type, radial_coeffs,
+                                     tangential_coeffs, thin_prism_coeffs, ch0 == 0, stream);
+            if (rc)
+                return rc;
+            rc = launch_blend_fwd_rays(rb, s.rays, C, N, image_width, image_height, tile_w, tile_h, true, nullptr, masks,
+                                       nullptr, nullptr, nullptr, stream);
+        } else {
+            rc = launch_blend_fwd(rb, s.cams, C, image_width, image_height, tile_w, tile_h, true, nullptr, masks, nullptr,
+                                  nullptr, nullptr, stream);
+        }
         if (rc)
             return rc;
         k_pack_vpix<<<div_up(n_pix, 256), 256, 0, stream>>>(v_render_colors, v_render_alphas, s.pix_state, backgrounds,
                                                             image_width * image_height, (uint32_t)n_pix, channels, ch0,
                                                             s.v_pix);
         LFS_LAUNCH_OK("k_pack_vpix");
-        rc = launch_blend_bwd(rb, s.cams, s.v_pix, quats, scales, means, C, N, image_width, image_height, tile_w, tile_h,
-                              n_bucket_cap, s.n_buckets, v_means, v_quats, v_scales,
-                              channels == 3 ? v_colors : s.v_colors_group, v_opacities, stream);
+        if (general)
+            rc = launch_blend_bwd_rays(rb, s.rays, s.v_pix, quats, scales, means, C, N, image_width, image_height, tile_w,
+                                       tile_h, n_bucket_cap, s.n_buckets, v_means, v_quats, v_scales,
+                                       channels == 3 ? v_colors : s.v_colors_group, v_opacities, stream);
+        else
+            rc = launch_blend_bwd(rb, s.cams, s.v_pix, quats, scales, means, C, N, image_width, image_height, tile_w, tile_h,
+                                  n_bucket_cap, s.n_buckets, v_means, v_quats, v_scales,
+                                  channels == 3 ? v_colors : s.v_colors_group, v_opacities, stream);
         if (rc)
             return rc;
         if (channels != 3) {

@@ -253,6 +253,39 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("adam_step_wrapper", &fast_gs::optimizer::adam_step_wrapper);
     m.def("fused_ssim", [](Tensor a, Tensor b, std::string padding, bool train) { return fused_ssim(a, b, padding, train); });
     // the remaining gsplat:: operators of gsplat/Ops.h, called directly (the autograd classes above cover the other seven)
+    // gsplat::projection_ut_3dgs_fused with every camera model / shutter / distortion argument (enums as ints)
+    m.def("projection_ut", [](Tensor means, Tensor quats, Tensor scales, std::optional<Tensor> opacities, Tensor viewmats0,
+                              std::optional<Tensor> viewmats1, Tensor Ks, int width, int height, double eps2d, double near_plane,
+                              double far_plane, double radius_clip, bool calc_compensations, int camera_model, int rs_type,
+                              std::optional<Tensor> radial, std::optional<Tensor> tangential, std::optional<Tensor> prism) {
+        return gsplat::projection_ut_3dgs_fused(means, quats, scales, opacities, viewmats0, viewmats1, Ks, width, height,
+                                                (float)eps2d, (float)near_plane, (float)far_plane, (float)radius_clip,
+                                                calc_compensations, static_cast<gsplat::CameraModelType>(camera_model),
+                                                UnscentedTransformParameters{}, static_cast<ShutterType>(rs_type), radial,
+                                                tangential, prism);
+    });
+    m.def("raster_fwd", [](Tensor means, Tensor quats, Tensor scales, Tensor colors, Tensor opacities,
+                           std::optional<Tensor> backgrounds, int width, int height, Tensor viewmats0,
+                           std::optional<Tensor> viewmats1, Tensor Ks, int camera_model, int rs_type,
+                           std::optional<Tensor> radial, std::optional<Tensor> tangential, std::optional<Tensor> prism,
+                           Tensor tile_offsets, Tensor flatten_ids) {
+        return gsplat::rasterize_to_pixels_from_world_3dgs_fwd(
+            means, quats, scales, colors, opacities, backgrounds, std::nullopt, width, height, 16, viewmats0, viewmats1, Ks,
+            static_cast<gsplat::CameraModelType>(camera_model), UnscentedTransformParameters{},
+            static_cast<ShutterType>(rs_type), radial, tangential, prism, tile_offsets, flatten_ids);
+    });
+    m.def("raster_bwd", [](Tensor means, Tensor quats, Tensor scales, Tensor colors, Tensor opacities,
+                           std::optional<Tensor> backgrounds, int width, int height, Tensor viewmats0,
+                           std::optional<Tensor> viewmats1, Tensor Ks, int camera_model, int rs_type,
+                           std::optional<Tensor> radial, std::optional<Tensor> tangential, std::optional<Tensor> prism,
+                           Tensor tile_offsets, Tensor flatten_ids, Tensor render_alphas, Tensor last_ids,
+                           Tensor v_render_colors, Tensor v_render_alphas) {
+        return gsplat::rasterize_to_pixels_from_world_3dgs_bwd(
+            means, quats, scales, colors, opacities, backgrounds, std::nullopt, width, height, 16, viewmats0, viewmats1, Ks,
+            static_cast<gsplat::CameraModelType>(camera_model), UnscentedTransformParameters{},
+            static_cast<ShutterType>(rs_type), radial, tangential, prism, tile_offsets, flatten_ids, render_alphas, last_ids,
+            v_render_colors, v_render_alphas);
+    });
     m.def("quats_to_rotmats", &gsplat::quats_to_rotmats);
     m.def("relocation", &gsplat::relocation);
     m.def("add_noise", &gsplat::add_noise);

@@ -176,3 +176,132 @@ def test_intersect_ops_on_both_backends(mods):
     for x, y in zip(a, b):
         assert x.shape == y.shape and torch.equal(x, y)
     assert torch.equal(ref.intersect_offset(a[1], Cc, tw, th), b200.intersect_offset(b[1], Cc, tw, th))
+
+
+CAMERA_CASES = [
+    dict(name="opencv_radial_tangential", model=0, rs=4, radial=[-0.12, 0.03, 0.002, 0.01, -0.004, 0.0005],
+         tangential=[0.002, -0.0015], prism=None, vm1=False),
+    dict(name="opencv_thin_prism", model=0, rs=4, radial=[-0.05, 0.01, 0.0, 0.0, 0.0, 0.0], tangential=None,
+         prism=[0.003, -0.001, -0.002, 0.0005], vm1=False),
+    dict(name="fisheye", model=2, rs=4, radial=[-0.02, 0.004, -0.0006, 0.00003], tangential=None, prism=None, vm1=False),
+    dict(name="fisheye_k4_zero", model=2, rs=4, radial=[0.05, -0.01, 0.002, 0.0], tangential=None, prism=None, vm1=False),
+    dict(name="pinhole_rolling_top_bottom", model=0, rs=0, radial=None, tangential=None, prism=None, vm1=True),
+    dict(name="pinhole_rolling_right_left", model=0, rs=3, radial=None, tangential=None, prism=None, vm1=True),
+    dict(name="fisheye_rolling_left_right", model=2, rs=1, radial=[-0.02, 0.004, 0.0, 0.0], tangential=None, prism=None,
+         vm1=True),
+    dict(name="opencv_rolling_bottom_top", model=0, rs=2, radial=[-0.08, 0.02, 0.0, 0.0, 0.0, 0.0],
+         tangential=[0.001, 0.001], prism=None, vm1=True),
+]
+
+
+@pytest.mark.parametrize("case", CAMERA_CASES, ids=[c["name"] for c in CAMERA_CASES])
+def test_projection_camera_models_on_both_backends(mods, case):
+    """gsplat::projection_ut_3dgs_fused for the camera models the 3DGUT path exists for (gsplat/Cameras.cuh:416-1024:
+    OpenCV pinhole distortion, fisheye) and rolling shutter (:346-413), host layer vs the reference CUDA build."""
+    ref, b200 = mods
+    n, w, h = 30000, 640, 480
+    sc = scene.make_scene(n, 2, w, h, 0, seed=23, sigma_px=4.0)
+    means, q, s, op, _ = sc.activated()
+    vm0 = T(sc.viewmats[:1])
+    vm1 = None
+    if case["vm1"]:  # end-of-frame pose: a small rotation about y plus a translation
+        a = 0.03
+        d = np.array([[np.cos(a), 0, np.sin(a), 0.02], [0, 1, 0, -0.01], [-np.sin(a), 0, np.cos(a), 0.015], [0, 0, 0, 1]])
+        vm1 = T((d @ sc.viewmats[0].astype(np.float64))[None])
+    K = sc.Ks[:1].copy()
+    if case["model"] == 2:
+        K[0, 0, 0] = K[0, 1, 1] = 0.45 * w  # wide field of view
+    opt = lambda v: None if v is None else T(np.array([v], np.float32))  # noqa: E731
+    args = (T(means), T(q), T(s), T(op), vm0, vm1, T(K), w, h, 0.3, 0.01, 1e4, 0.0, True, case["model"], case["rs"],
+            opt(case["radial"]), opt(case["tangential"]), opt(case["prism"]))
+    a_ = ref.projection_ut(*args)
+    b_ = b200.projection_ut(*args)
+    rr, rb = a_[0], b_[0]
+    vis_r, vis_b = (rr > 0).all(-1), (rb > 0).all(-1)
+    n_vis = int(vis_r.sum())
+    assert n_vis > 2000, (case["name"], n_vis)
+    assert int((vis_r != vis_b).sum()) <= max(3, n_vis // 500), (case["name"], int((vis_r != vis_b).sum()), n_vis)
+    both = vis_r & vis_b
+    assert int((rr[both] - rb[both]).abs().max()) <= 1
+    rep = {}
+    gate(rep, "means2d", b_[1][both], a_[1][both], 1e-4, 0.999)
+    gate(rep, "depths", b_[2][both], a_[2][both], 1e-5, 0.999)
+    gate(rep, "conics", b_[3][both], a_[3][both], 2e-3, 0.99)
+    gate(rep, "compensations", b_[4][both], a_[4][both], 1e-3, 0.99)
+    print(case["name"], n_vis, rep)
+
+
+@pytest.mark.parametrize("case", CAMERA_CASES, ids=[c["name"] for c in CAMERA_CASES])
+def test_rasterize_camera_models_on_both_backends(mods, case):
+    """rasterize_to_pixels_from_world_3dgs_fwd / _bwd along per-pixel rays (distortion, fisheye, rolling shutter): host
+    layer vs the reference CUDA build, both on the reference's own projection + tile lists."""
+    ref, b200 = mods
+    n, w, h = 12000, 320, 240
+    sc = scene.make_scene(n, 2, w, h, 0, seed=29, sigma_px=4.0)
+    means, q, s, op, _ = sc.activated()
+    vm0 = T(sc.viewmats[:1])
+    vm1 = None
+    if case["vm1"]:
+        a = 0.03
+        d = np.array([[np.cos(a), 0, np.sin(a), 0.02], [0, 1, 0, -0.01], [-np.sin(a), 0, np.cos(a), 0.015], [0, 0, 0, 1]])
+        vm1 = T((d @ sc.viewmats[0].astype(np.float64))[None])
+    K = sc.Ks[:1].copy()
+    if case["model"] == 2:
+        K[0, 0, 0] = K[0, 1, 1] = 0.45 * w
+    opt = lambda v: None if v is None else T(np.array([v], np.float32))  # noqa: E731
+    rad, tan, pri = opt(case["radial"]), opt(case["tangential"]), opt(case["prism"])
+    tm, tq, ts, to, tK = T(means), T(q), T(s), T(op), T(K)
+    radii, m2d, dep, con, _ = ref.projection_ut(tm, tq, ts, to, vm0, vm1, tK, w, h, 0.3, 0.01, 1e4, 0.0, False,
+                                                case["model"], case["rs"], rad, tan, pri)
+    tw, th = (w + 15) // 16, (h + 15) // 16
+    _, ids, flat = ref.intersect_tile(m2d, radii, dep, 1, 16, tw, th, True)
+    offs = ref.intersect_offset(ids, 1, tw, th)
+    assert flat.numel() > 20_000
+    g = torch.Generator(device="cuda").manual_seed(4)
+    colors = torch.rand((1, n, 3), device="cuda", generator=g)
+    bg = T(np.array([[0.1, 0.2, 0.3]]))
+    fargs = (tm, tq, ts, colors, to[None].contiguous(), bg, w, h, vm0, vm1, tK, case["model"], case["rs"], rad, tan, pri,
+             offs, flat)
+    a_ = ref.raster_fwd(*fargs)
+    b_ = b200.raster_fwd(*fargs)
+    rep = {}
+    gate(rep, "render_rgb", b_[0], a_[0], 1e-4, 0.999)
+    gate(rep, "render_alpha", b_[1], a_[1], 1e-4, 0.999)
+    assert float((a_[2] != b_[2]).float().mean()) <= 2e-3
+    vC = torch.randn(a_[0].shape, device="cuda", generator=g)
+    vA = torch.randn(a_[1].shape, device="cuda", generator=g)
+    ga = ref.raster_bwd(*fargs, a_[1], a_[2], vC, vA)
+    gb = b200.raster_bwd(*fargs, b_[1], b_[2], vC, vA)
+    for nm, x, y in zip(("v_means", "v_quats", "v_scales", "v_colors", "v_opacities"), gb, ga):
+        gate(rep, "bwd_" + nm, x, y, 1e-3, 0.99)
+    print(case["name"], int(flat.numel()), rep)
+
+
+def test_rasterize_four_channels_on_both_backends(mods):
+    """channels = 4 (RGB + depth, rasterizer.cpp:272-300) and 1 (depth only) through the op surface."""
+    ref, b200 = mods
+    n, w, h = 8000, 256, 192
+    sc = scene.make_scene(n, 1, w, h, 0, seed=31, sigma_px=4.0)
+    means, q, s, op, _ = sc.activated()
+    tm, tq, ts, to, tK, vm0 = T(means), T(q), T(s), T(op), T(sc.Ks[:1]), T(sc.viewmats[:1])
+    radii, m2d, dep, con, _ = ref.projection_ut(tm, tq, ts, to, vm0, None, tK, w, h, 0.3, 0.01, 1e4, 0.0, False, 0, 4, None,
+                                                None, None)
+    tw, th = (w + 15) // 16, (h + 15) // 16
+    _, ids, flat = ref.intersect_tile(m2d, radii, dep, 1, 16, tw, th, True)
+    offs = ref.intersect_offset(ids, 1, tw, th)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for ch in (4, 1):
+        colors = torch.rand((1, n, ch), device="cuda", generator=g)
+        bg = torch.rand((1, ch), device="cuda", generator=g)
+        fargs = (tm, tq, ts, colors, to[None].contiguous(), bg, w, h, vm0, None, tK, 0, 4, None, None, None, offs, flat)
+        a_, b_ = ref.raster_fwd(*fargs), b200.raster_fwd(*fargs)
+        rep = {}
+        gate(rep, "render", b_[0], a_[0], 1e-4, 0.999)
+        gate(rep, "alpha", b_[1], a_[1], 1e-4, 0.999)
+        vC = torch.randn(a_[0].shape, device="cuda", generator=g)
+        vA = torch.randn(a_[1].shape, device="cuda", generator=g)
+        ga = ref.raster_bwd(*fargs, a_[1], a_[2], vC, vA)
+        gb = b200.raster_bwd(*fargs, b_[1], b_[2], vC, vA)
+        for nm, x, y in zip(("v_means", "v_quats", "v_scales", "v_colors", "v_opacities"), gb, ga):
+            gate(rep, f"bwd_{nm}", x, y, 1e-3, 0.99)
+        print("channels", ch, rep)
