@@ -363,7 +363,12 @@ int lfs_adam_p2p_zero_unowned(float* arena, int64_t n_floats, int world, int ran
 int lfs_trainer_set_profile(void* trainer, int enable);
 int lfs_trainer_get_profile(void* trainer, float* mean_ms /* [LFS_PROF_STAGES] */, int* counts /* or NULL */);
 
-/* library options: "blend_tma" = 0/1 (stage per-tile records with cp.async.bulk + mbarrier; default 1) */
+/* library options (A/B switches between kernels that compute the same thing; the defaults are the measured best):
+ *   "fwd_variant"  0 forward blend with TMA-gathered records (cp.async.bulk + mbarrier), 1 register-staged gather
+ *   "bwd_variant"  0 software-pipelined backward blend, 1 lock-step backward blend
+ *   "sort_variant" 0 histogram / scan / scatter radix passes, 1 onesweep (decoupled look-back) passes
+ *   "exact_cull"   1 trainer drops tile instances that provably hold no alpha >= 1/255, 0 the reference's AABB rule
+ *   "pre_bwd_split" 1 per-Gaussian backward as two launches (SH, geometry), 0 one launch */
 int lfs_set_option(const char* name, int value);
 
 #ifdef __cplusplus

@@ -183,7 +183,7 @@ def load() -> C.CDLL:
             fn.argtypes = args
         if lib.lfs_abi_version() != ABI_VERSION:
             raise RuntimeError("lfs_b200 ABI version mismatch")
-        # tuning switches for A/B measurements, e.g. LFS_OPTIONS="blend_fused=0,blend_tma=1" (see lfs_set_option)
+        # tuning switches for A/B measurements, e.g. LFS_OPTIONS="fwd_variant=1,bwd_variant=1" (see lfs_set_option)
         for item in filter(None, os.environ.get("LFS_OPTIONS", "").split(",")):
             key, _, val = item.partition("=")
             if lib.lfs_set_option(key.strip().encode(), int(val or "1")) != LFS_OK:

@@ -42,10 +42,6 @@ extern "C" int lfs_abi_version(void) { return LFS_ABI_VERSION; }
 extern "C" uint64_t lfs_launch_count(void) { return lfs::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int lfs_set_option(const char* name, int value) {
-    if (name && std::string(name) == "blend_tma") {
-        lfs::raster_options().use_tma = value ? 1 : 0;
-        return LFS_OK;
-    }
     if (name && std::string(name) == "fwd_variant") {
         lfs::raster_options().fwd_variant = value;
         return LFS_OK;
@@ -64,10 +60,6 @@ extern "C" int lfs_set_option(const char* name, int value) {
     }
     if (name && std::string(name) == "sort_variant") {
         lfs::set_sort_variant(value);
-        return LFS_OK;
-    }
-    if (name && std::string(name) == "blend_fused") {
-        lfs::raster_options().fuse_expand = value ? 1 : 0;
         return LFS_OK;
     }
     lfs::set_error("set_option: unknown option '%s'", name ? name : "(null)");

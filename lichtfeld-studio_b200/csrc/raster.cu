@@ -11,28 +11,9 @@ RasterOptions& raster_options() {
     return o;
 }
 
-// ------------------------------------------------------------------------------------------------------
-// expand: one thread per sorted instance -> tile-local rational-quadratic record
-// ------------------------------------------------------------------------------------------------------
-constexpr int kExThreads = 256;
-
-__device__ __forceinline__ uint32_t find_tile(const int32_t* __restrict__ off, uint32_t n, uint32_t j) {
-    // largest t in [0, n) with off[t] <= j
-    uint32_t lo = 0, hi = n - 1;
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi + 1) >> 1;
-        if ((uint32_t)__ldg(off + mid) <= j)
-            lo = mid;
-        else
-            hi = mid - 1;
-    }
-    return lo;
-}
-
-
-// Tile-local expansion of one GaussRec into the 12 rational-quadratic coefficients (see raster.cuh).  Used by the
-// stand-alone expand kernel AND inlined into the fused forward / backward blends, so every operation is spelled with
-// explicit fmaf / __fmul_rn: the three call sites must produce the same coefficient BITS (a pair has to get the same
+// Tile-local expansion of one GaussRec into the 12 rational-quadratic coefficients (see raster.cuh), inlined into the
+// forward and backward blends, so every operation is spelled with
+// explicit fmaf / __fmul_rn: the call sites must produce the same coefficient BITS (a pair has to get the same
 // alpha in the forward and in the backward), which rules out leaving FMA contraction to the optimiser.
 __device__ __forceinline__ float dot_rn(const f3 a, const f3 b) {
     return fmaf(a.z, b.z, fmaf(a.y, b.y, __fmul_rn(a.x, b.x)));
@@ -83,53 +64,6 @@ __device__ __forceinline__ void expand_record_ewa(const float4 g0, const float4 
     Cc = make_float4(fmaxf(g1.w, 0.f), fmaxf(g2.x, 0.f), 0.f, 0.f);
 }
 
-__global__ void __launch_bounds__(kExThreads)
-    k_expand_instances(const GaussRec* __restrict__ gauss, const int32_t* __restrict__ inst_gid,
-                       const int32_t* __restrict__ tile_off, const uint32_t* __restrict__ sorted_tile_keys,
-                       const ViewCam* __restrict__ cams, const uint32_t n_tiles_per_cam, const uint32_t tile_w,
-                       const uint32_t C, const uint32_t n_cap, const uint32_t* __restrict__ n_dev,
-                       InstRec* __restrict__ inst) {
-    uint32_t n = n_cap;
-    if (n_dev) {
-        const uint32_t nd = *n_dev;
-        n = nd < n_cap ? nd : n_cap;
-    }
-    const uint32_t n_tiles_total = C * n_tiles_per_cam;
-    for (uint32_t j = blockIdx.x * kExThreads + threadIdx.x; j < n; j += gridDim.x * kExThreads) {
-        const uint32_t g = (uint32_t)__ldg(inst_gid + j);
-        const uint32_t ft = sorted_tile_keys ? __ldg(sorted_tile_keys + j) : find_tile(tile_off, n_tiles_total, j);
-        const uint32_t cam = ft / n_tiles_per_cam, t = ft - cam * n_tiles_per_cam;
-        const uint32_t ty = t / tile_w, tx = t - ty * tile_w;
-        const float cxp = cams[cam].cx, cyp = cams[cam].cy;
-        const float Xo = (float)(tx * kTile + kTile / 2) - cxp;
-        const float Yo = (float)(ty * kTile + kTile / 2) - cyp;
-
-        const float4* gp = reinterpret_cast<const float4*>(gauss + g);
-        const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1), g2 = __ldg(gp + 2), g3 = __ldg(gp + 3);
-        float4 A, B, Cc;
-        expand_record(g0, g1, g2, Xo, Yo, A, B, Cc);
-        float4* out = reinterpret_cast<float4*>(inst + j);
-        out[0] = A;
-        out[1] = B;
-        out[2] = Cc;
-        out[3] = g3; // opacity, rgb
-    }
-}
-
-int launch_expand_instances(const RasterBuffers& rb, const ViewCam* cams_dev, uint32_t n_tiles_per_cam,
-                            uint32_t tile_w, uint32_t n_inst_cap, const uint32_t* n_inst_dev,
-                            const uint32_t* sorted_tile_keys, uint32_t C, uint32_t N, cudaStream_t stream) {
-    (void)N;
-    if (n_inst_cap == 0)
-        return LFS_OK;
-    const unsigned want = div_up(n_inst_cap, kExThreads);
-    const unsigned grid = want < (unsigned)(num_sms() * 32) ? want : (unsigned)(num_sms() * 32);
-    k_expand_instances<<<grid, kExThreads, 0, stream>>>(rb.gauss, rb.inst_gid, rb.tile_off, sorted_tile_keys, cams_dev,
-                                                        n_tiles_per_cam, tile_w, C, n_inst_cap, n_inst_dev, rb.inst);
-    LFS_LAUNCH_OK("k_expand_instances");
-    return LFS_OK;
-}
-
 // ------------------------------------------------------------------------------------------------------
 // bucket bookkeeping
 // ------------------------------------------------------------------------------------------------------
@@ -161,7 +95,7 @@ int launch_bucket_offsets(const RasterBuffers& rb, uint32_t n_tiles_total, uint3
 // ------------------------------------------------------------------------------------------------------
 // forward blend
 // ------------------------------------------------------------------------------------------------------
-constexpr int kBatch = 64; // InstRec per smem stage (4 KB)
+constexpr int kBatch = 64; // records per shared-memory stage (4 KB)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -221,22 +155,19 @@ __device__ __forceinline__ void store_rec_pk(float4* d, const float4 A, const fl
     d[3] = make_float4(E.y, E.z, E.w, E.x);
 }
 
-template <int MODE, bool EWA, int MINB = 1, bool PK = false> // MODE 0: register-staged InstRec, 1: TMA-staged InstRec,
-                                             // 2: fused expansion (GaussRec gather); EWA: fastgs-surface records (2-D
-                                             // conic, D == 1), MODE 2 only; MINB: minimum resident CTAs per SM (register
-                                             // cap); PK: FFMA2 evaluation of (N', D) (MODE 2, not EWA)
-__global__ void __launch_bounds__(kFwdThreads, MINB)
+// Register-staged variant (round 1's kernel, kept for A/B measurements: lfs_set_option("fwd_variant", 1)): the GaussRec of
+// the next batch is gathered with LDG.128 into registers one batch ahead.  EWA: fastgs-surface records (2-D conic, D == 1);
+// PK: FFMA2 evaluation of (N', D) (not EWA).
+template <bool EWA, bool PK = false>
+__global__ void __launch_bounds__(kFwdThreads)
     k_blend_fwd(const RasterBuffers rb, const ViewCam* __restrict__ cams, const uint32_t width, const uint32_t height, const uint32_t tile_w,
                 const uint32_t tile_h, const bool write_ckpt, const float* __restrict__ backgrounds,
                 const uint8_t* __restrict__ masks, float* __restrict__ renders, float* __restrict__ alphas,
                 int32_t* __restrict__ last_ids) {
-    constexpr bool USE_TMA = (MODE == 1);
-    constexpr bool FUSED = (MODE == 2);
     __shared__ __align__(128) float4 s_rec[2][kBatch * 4];
     __shared__ __align__(16) float4 s_state[kTilePix]; // (r, g, b, T) per pixel
     __shared__ uint32_t s_ncon[kTilePix];
     __shared__ uint8_t s_list[2][kTilePix];
-    __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ uint32_t s_warp_tot[kFwdThreads / 32];
     __shared__ uint32_t s_nact[2];
 
@@ -300,62 +231,36 @@ __global__ void __launch_bounds__(kFwdThreads, MINB)
         compact(keep, ids, cur);
     }
 
-    const float4* gsrc = reinterpret_cast<const float4*>(rb.inst + start);
-    float Xo = 0.f, Yo = 0.f;
-    uint32_t gid_next = 0; // FUSED: flattened Gaussian id this thread expands for the NEXT batch
-    if (FUSED && EWA) {
+    float Xo, Yo;
+    uint32_t gid_next = 0; // flattened Gaussian id this thread expands for the NEXT batch
+    if (EWA) {
         Xo = (float)(tx * kTile + kTile / 2), Yo = (float)(ty * kTile + kTile / 2); // tile centre in pixel units
-    } else if (FUSED) {
+    } else {
         Xo = (float)(tx * kTile + kTile / 2) - cams[cam].cx;
         Yo = (float)(ty * kTile + kTile / 2) - cams[cam].cy;
     }
     const int nbatch = (cnt + kBatch - 1) / kBatch;
-
-    if (USE_TMA) {
-        if (tid == 0) {
-            mbar_init(&s_bar[0], 1);
-            mbar_init(&s_bar[1], 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-        if (tid == 0) {
-            for (int k = 0; k < 2 && k < nbatch; ++k) {
-                const uint32_t nrec = (uint32_t)min(kBatch, cnt - k * kBatch);
-                mbar_expect_tx(&s_bar[k], nrec * (uint32_t)sizeof(InstRec));
-                tma_load_1d(&s_rec[k][0], gsrc + (size_t)k * kBatch * 4, nrec * (uint32_t)sizeof(InstRec), &s_bar[k]);
+    if (nbatch > 0) {
+        if ((int)tid < min(kBatch, cnt)) {
+            const float4* gp = reinterpret_cast<const float4*>(rb.gauss + (uint32_t)__ldg(rb.inst_gid + start + tid));
+            float4 A, B, Cc;
+            if (EWA) {
+                expand_record_ewa(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), Xo, Yo, A, B, Cc);
+            } else {
+                expand_record(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), Xo, Yo, A, B, Cc);
+                if (PK)
+                    store_rec_pk(&s_rec[0][4 * tid], A, B, Cc, __ldg(gp + 3));
+                else
+                    s_rec[0][4 * tid + 3] = __ldg(gp + 3);
             }
+            if (!PK)
+                s_rec[0][4 * tid] = A, s_rec[0][4 * tid + 1] = B, s_rec[0][4 * tid + 2] = Cc;
         }
-    } else if (FUSED) {
-        if (nbatch > 0) {
-            if ((int)tid < min(kBatch, cnt)) {
-                const float4* gp = reinterpret_cast<const float4*>(rb.gauss + (uint32_t)__ldg(rb.inst_gid + start + tid));
-                float4 A, B, Cc;
-                if (EWA) {
-                    expand_record_ewa(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), Xo, Yo, A, B, Cc);
-                } else {
-                    expand_record(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), Xo, Yo, A, B, Cc);
-                    if (PK)
-                        store_rec_pk(&s_rec[0][4 * tid], A, B, Cc, __ldg(gp + 3));
-                    else
-                        s_rec[0][4 * tid + 3] = __ldg(gp + 3);
-                }
-                if (!PK)
-                    s_rec[0][4 * tid] = A, s_rec[0][4 * tid + 1] = B, s_rec[0][4 * tid + 2] = Cc;
-            }
-            if ((int)tid < cnt - kBatch)
-                gid_next = (uint32_t)__ldg(rb.inst_gid + start + kBatch + tid);
-            __syncthreads();
-        }
-    } else if (nbatch > 0) {
-        const int nf4 = min(kBatch, cnt) * 4;
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if ((int)(tid + q * kFwdThreads) < nf4)
-                s_rec[0][tid + q * kFwdThreads] = ld_nc4(gsrc + tid + q * kFwdThreads);
+        if ((int)tid < cnt - kBatch)
+            gid_next = (uint32_t)__ldg(rb.inst_gid + start + kBatch + tid);
         __syncthreads();
     }
 
-    int consumed = 0;
     for (int kb = 0; kb < nbatch; ++kb) {
         const int buf = kb & 1;
         const uint32_t n_act = s_nact[cur];
@@ -384,29 +289,17 @@ __global__ void __launch_bounds__(kFwdThreads, MINB)
         }
         const uint32_t mine = live;
 
+        // gather the next batch's GaussRec (this thread's record) now; it is expanded after the blend below
         float4 pre[4];
-        int next_f4 = 0;
-        if (USE_TMA) {
-            mbar_wait(&s_bar[buf], (uint32_t)((kb >> 1) & 1));
-            consumed = kb + 1;
-        } else if (FUSED) {
-            // gather the next batch's GaussRec (this thread's record) now; it is expanded after the blend below
-            next_f4 = (kb + 1 < nbatch) ? min(kBatch, cnt - (kb + 1) * kBatch) : 0;
-            if ((int)tid < next_f4) {
-                const float4* gp = reinterpret_cast<const float4*>(rb.gauss + gid_next);
-                pre[0] = __ldg(gp), pre[1] = __ldg(gp + 1), pre[2] = __ldg(gp + 2);
-                if (!EWA)
-                    pre[3] = __ldg(gp + 3);
-            }
-            if ((int)tid < cnt - (kb + 2) * kBatch)
-                gid_next = (uint32_t)__ldg(rb.inst_gid + start + (kb + 2) * kBatch + tid);
-        } else {
-            next_f4 = (kb + 1 < nbatch) ? min(kBatch, cnt - (kb + 1) * kBatch) * 4 : 0;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if ((int)(tid + q * kFwdThreads) < next_f4)
-                    pre[q] = ld_nc4(gsrc + (size_t)(kb + 1) * kBatch * 4 + tid + q * kFwdThreads);
+        const int next_f4 = (kb + 1 < nbatch) ? min(kBatch, cnt - (kb + 1) * kBatch) : 0;
+        if ((int)tid < next_f4) {
+            const float4* gp = reinterpret_cast<const float4*>(rb.gauss + gid_next);
+            pre[0] = __ldg(gp), pre[1] = __ldg(gp + 1), pre[2] = __ldg(gp + 2);
+            if (!EWA)
+                pre[3] = __ldg(gp + 3);
         }
+        if ((int)tid < cnt - (kb + 2) * kBatch)
+            gid_next = (uint32_t)__ldg(rb.inst_gid + start + (kb + 2) * kBatch + tid);
 
         if (live) {
             const float4* s = &s_rec[buf][0];
@@ -494,27 +387,20 @@ __global__ void __launch_bounds__(kFwdThreads, MINB)
                 s_state[pid[k]] = make_float4(r[k], g[k], b[k], T[k]);
                 s_ncon[pid[k]] = ncon[k];
             }
-        if (FUSED) {
-            if ((int)tid < next_f4) {
-                float4 A, B, Cc;
-                float4* d = &s_rec[buf ^ 1][4 * tid];
-                if (EWA) {
-                    expand_record_ewa(pre[0], pre[1], pre[2], Xo, Yo, A, B, Cc);
-                } else {
-                    expand_record(pre[0], pre[1], pre[2], Xo, Yo, A, B, Cc);
-                    if (PK)
-                        store_rec_pk(d, A, B, Cc, pre[3]);
-                    else
-                        d[3] = pre[3];
-                }
-                if (!PK)
-                    d[0] = A, d[1] = B, d[2] = Cc;
+        if ((int)tid < next_f4) {
+            float4 A, B, Cc;
+            float4* d = &s_rec[buf ^ 1][4 * tid];
+            if (EWA) {
+                expand_record_ewa(pre[0], pre[1], pre[2], Xo, Yo, A, B, Cc);
+            } else {
+                expand_record(pre[0], pre[1], pre[2], Xo, Yo, A, B, Cc);
+                if (PK)
+                    store_rec_pk(d, A, B, Cc, pre[3]);
+                else
+                    d[3] = pre[3];
             }
-        } else if (!USE_TMA) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if ((int)(tid + q * kFwdThreads) < next_f4)
-                    s_rec[buf ^ 1][tid + q * kFwdThreads] = pre[q];
+            if (!PK)
+                d[0] = A, d[1] = B, d[2] = Cc;
         }
         // rebuild the active list only when some pixel finished in this batch (compact() syncs the block)
         const int changed = __syncthreads_or((int)(live != mine));
@@ -522,21 +408,6 @@ __global__ void __launch_bounds__(kFwdThreads, MINB)
             compact(live, pid, cur ^ 1);
             cur ^= 1;
         }
-        if (USE_TMA && tid == 0 && kb + 2 < nbatch && s_nact[cur] != 0) {
-            const uint32_t nr2 = (uint32_t)min(kBatch, cnt - (kb + 2) * kBatch);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(&s_bar[buf], nr2 * (uint32_t)sizeof(InstRec));
-            tma_load_1d(&s_rec[buf][0], gsrc + (size_t)(kb + 2) * kBatch * 4, nr2 * (uint32_t)sizeof(InstRec),
-                        &s_bar[buf]);
-        }
-    }
-    // early exit: one more batch may still be in flight into this CTA's shared memory -- drain it
-    if (USE_TMA && tid == 0 && consumed < nbatch && consumed >= 1)
-        mbar_wait(&s_bar[consumed & 1], (uint32_t)((consumed >> 1) & 1));
-    if (USE_TMA && tid == 0 && consumed == 0 && nbatch > 0) { // loop never ran (no active pixel): drain both
-        mbar_wait(&s_bar[0], 0u);
-        if (nbatch > 1)
-            mbar_wait(&s_bar[1], 0u);
     }
     __syncthreads();
 
@@ -880,28 +751,12 @@ int launch_blend_fwd(const RasterBuffers& rb, const ViewCam* cams_dev, uint32_t 
     if (C == 0 || tile_w == 0 || tile_h == 0)
         return LFS_OK;
     dim3 grid(tile_w * tile_h, C);
-    if (raster_options().fuse_expand && raster_options().fwd_variant == 4)
+    if (raster_options().fwd_variant == 1)
+        k_blend_fwd<false, true><<<grid, kFwdThreads, 0, stream>>>(rb, cams_dev, width, height, tile_w, tile_h, write_ckpt,
+                                                                  backgrounds, masks, renders, alphas, last_ids);
+    else
         k_blend_fwd_tg<false><<<grid, kFwdThreads, 0, stream>>>(rb, cams_dev, width, height, tile_w, tile_h, write_ckpt,
                                                                backgrounds, masks, renders, alphas, last_ids);
-    else if (raster_options().fuse_expand && raster_options().fwd_variant == 1)
-        k_blend_fwd<2, false, 10><<<grid, kFwdThreads, 0, stream>>>(rb, cams_dev, width, height, tile_w, tile_h, write_ckpt,
-                                                                   backgrounds, masks, renders, alphas, last_ids);
-    else if (raster_options().fuse_expand && raster_options().fwd_variant == 3)
-        k_blend_fwd<2, false, 1, true><<<grid, kFwdThreads, 0, stream>>>(rb, cams_dev, width, height, tile_w, tile_h,
-                                                                        write_ckpt, backgrounds, masks, renders, alphas,
-                                                                        last_ids);
-    else if (raster_options().fuse_expand && raster_options().fwd_variant == 2)
-        k_blend_fwd<2, false, 12><<<grid, kFwdThreads, 0, stream>>>(rb, cams_dev, width, height, tile_w, tile_h, write_ckpt,
-                                                                   backgrounds, masks, renders, alphas, last_ids);
-    else if (raster_options().fuse_expand)
-        k_blend_fwd<2, false><<<grid, kFwdThreads, 0, stream>>>(rb, cams_dev, width, height, tile_w, tile_h, write_ckpt,
-                                                      backgrounds, masks, renders, alphas, last_ids);
-    else if (raster_options().use_tma)
-        k_blend_fwd<1, false><<<grid, kFwdThreads, 0, stream>>>(rb, cams_dev, width, height, tile_w, tile_h, write_ckpt,
-                                                      backgrounds, masks, renders, alphas, last_ids);
-    else
-        k_blend_fwd<0, false><<<grid, kFwdThreads, 0, stream>>>(rb, cams_dev, width, height, tile_w, tile_h, write_ckpt,
-                                                      backgrounds, masks, renders, alphas, last_ids);
     LFS_LAUNCH_OK("k_blend_fwd");
     return LFS_OK;
 }
@@ -910,11 +765,11 @@ int launch_blend_fwd_ewa(const RasterBuffers& rb, uint32_t width, uint32_t heigh
                          bool write_ckpt, cudaStream_t stream) {
     if (tile_w == 0 || tile_h == 0)
         return LFS_OK;
-    if (raster_options().fwd_variant == 4)
-        k_blend_fwd_tg<true><<<dim3(tile_w * tile_h, 1), kFwdThreads, 0, stream>>>(
+    if (raster_options().fwd_variant == 1)
+        k_blend_fwd<true><<<dim3(tile_w * tile_h, 1), kFwdThreads, 0, stream>>>(
             rb, nullptr, width, height, tile_w, tile_h, write_ckpt, nullptr, nullptr, nullptr, nullptr, nullptr);
     else
-        k_blend_fwd<2, true><<<dim3(tile_w * tile_h, 1), kFwdThreads, 0, stream>>>(
+        k_blend_fwd_tg<true><<<dim3(tile_w * tile_h, 1), kFwdThreads, 0, stream>>>(
             rb, nullptr, width, height, tile_w, tile_h, write_ckpt, nullptr, nullptr, nullptr, nullptr, nullptr);
     LFS_LAUNCH_OK("k_blend_fwd<ewa>");
     return LFS_OK;
@@ -1045,8 +900,10 @@ __device__ __forceinline__ void bwd_chain_rule(const RasterBuffers& rb, const Vi
 // blend_backward_cu (kernels_backward.cuh:240-449) passed in the slots v_means -> grad_mean2d [N,2],
 // v_quats -> grad_conic [N,3] (a, b, c; b is the TRUE derivative, twice the reference's stored value),
 // v_colors -> grad_color [N,3], v_opacities -> grad_raw_opacity [N]; quats / scales / means / cams are unused.
-template <bool FUSED, int kBwdWarps, int kMinBlocks, bool EWA = false, bool PK = false>
-__global__ void __launch_bounds__(kBwdWarps * 32, kMinBlocks)
+// Lock-step variant (round 1's kernel, kept for A/B measurements: lfs_set_option("bwd_variant", 1)): alpha and chain of a
+// step run back to back.
+template <int kBwdWarps, bool EWA = false, bool PK = false>
+__global__ void __launch_bounds__(kBwdWarps * 32)
     k_blend_bwd(const RasterBuffers rb, const ViewCam* __restrict__ cams, const float4* __restrict__ v_pix,
                 const float* __restrict__ quats, const float* __restrict__ scales, const float* __restrict__ means,
                 const uint32_t N, const uint32_t width, const uint32_t height, const uint32_t tile_w,
@@ -1088,13 +945,10 @@ __global__ void __launch_bounds__(kBwdWarps * 32, kMinBlocks)
             const float4* gp = reinterpret_cast<const float4*>(rb.gauss + g);
             expand_record_ewa(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), Xo, Yo, A, B, Cc);
             E = make_float4(B.z, B.w, Cc.x, Cc.y);
-        } else if (FUSED) {
+        } else {
             const float4* gp = reinterpret_cast<const float4*>(rb.gauss + g);
             expand_record(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), Xo, Yo, A, B, Cc);
             E = __ldg(gp + 3);
-        } else {
-            const float4* rp = reinterpret_cast<const float4*>(rb.inst + inst);
-            A = ld_nc4(rp), B = ld_nc4(rp + 1), Cc = ld_nc4(rp + 2), E = ld_nc4(rp + 3);
         }
     }
 
@@ -1496,33 +1350,14 @@ int launch_blend_bwd(const RasterBuffers& rb, const ViewCam* cams_dev, const flo
     (void)C;
     if (n_bucket_cap == 0)
         return LFS_OK;
-#define LFS_BWD_LAUNCH(F, W, MB)                                                                                      \
-    k_blend_bwd<F, W, MB><<<div_up(n_bucket_cap, W), W * 32, 0, stream>>>(                                            \
-        rb, cams_dev, v_pix, quats, scales, means, N, width, height, tile_w, tile_h, n_bucket_cap, n_buckets_dev,      \
-        v_means, v_quats, v_scales, v_colors, v_opacities)
-    const int variant = raster_options().bwd_variant;
-    if (!raster_options().fuse_expand) {
-        LFS_BWD_LAUNCH(false, 4, 1);
-    } else if (variant == 1) {
-        LFS_BWD_LAUNCH(true, 4, 8);
-    } else if (variant == 2) {
-        LFS_BWD_LAUNCH(true, 2, 16);
-    } else if (variant == 3) {
-        LFS_BWD_LAUNCH(true, 1, 32);
-    } else if (variant == 4) {
-        LFS_BWD_LAUNCH(true, 2, 1);
-    } else if (variant == 6) { // software-pipelined + FFMA2
+    if (raster_options().bwd_variant == 1)
+        k_blend_bwd<4, false, true><<<div_up(n_bucket_cap, 4), 4 * 32, 0, stream>>>(
+            rb, cams_dev, v_pix, quats, scales, means, N, width, height, tile_w, tile_h, n_bucket_cap, n_buckets_dev,
+            v_means, v_quats, v_scales, v_colors, v_opacities);
+    else
         k_blend_bwd_sp<false, 4><<<div_up(n_bucket_cap, 4), 4 * 32, 0, stream>>>(
             rb, cams_dev, v_pix, quats, scales, means, N, width, height, tile_w, tile_h, n_bucket_cap, n_buckets_dev,
             v_means, v_quats, v_scales, v_colors, v_opacities);
-    } else if (variant == 5) { // FFMA2 body
-        k_blend_bwd<true, 4, 1, false, true><<<div_up(n_bucket_cap, 4), 4 * 32, 0, stream>>>(
-            rb, cams_dev, v_pix, quats, scales, means, N, width, height, tile_w, tile_h, n_bucket_cap, n_buckets_dev,
-            v_means, v_quats, v_scales, v_colors, v_opacities);
-    } else {
-        LFS_BWD_LAUNCH(true, 4, 1);
-    }
-#undef LFS_BWD_LAUNCH
     LFS_LAUNCH_OK("k_blend_bwd");
     return LFS_OK;
 }
@@ -1532,12 +1367,12 @@ int launch_blend_bwd_ewa(const RasterBuffers& rb, const float4* v_pix, uint32_t 
                          float* v_mean2d, float* v_conic, float* v_color, float* v_raw_opacity, cudaStream_t stream) {
     if (n_bucket_cap == 0)
         return LFS_OK;
-    if (raster_options().bwd_variant == 6)
-        k_blend_bwd_sp<true, 4><<<div_up(n_bucket_cap, 4), 4 * 32, 0, stream>>>(
+    if (raster_options().bwd_variant == 1)
+        k_blend_bwd<4, true><<<div_up(n_bucket_cap, 4), 4 * 32, 0, stream>>>(
             rb, nullptr, v_pix, nullptr, nullptr, nullptr, N, width, height, tile_w, tile_h, n_bucket_cap, n_buckets_dev,
             v_mean2d, v_conic, nullptr, v_color, v_raw_opacity);
     else
-        k_blend_bwd<true, 4, 1, true><<<div_up(n_bucket_cap, 4), 4 * 32, 0, stream>>>(
+        k_blend_bwd_sp<true, 4><<<div_up(n_bucket_cap, 4), 4 * 32, 0, stream>>>(
             rb, nullptr, v_pix, nullptr, nullptr, nullptr, N, width, height, tile_w, tile_h, n_bucket_cap, n_buckets_dev,
             v_mean2d, v_conic, nullptr, v_color, v_raw_opacity);
     LFS_LAUNCH_OK("k_blend_bwd<ewa>");

@@ -13,7 +13,7 @@
 //
 //   GaussRec (64 B, one per camera-Gaussian pair): vx, vy, w2 (columns of M R^T scaled by 1/fx, 1/fy, 1),
 //                                                  gro, opacity, rgb
-//   InstRec  (64 B, one per sorted tile-Gaussian instance, contiguous per tile):
+//   per sorted (tile, Gaussian) instance, computed inside the blend kernels from a gather of the GaussRec:
 //        N'(dx,dy) = n0 + n1x dx + n1y dy + n2xx dx^2 + n2xy dx dy + n2yy dy^2   (already x -1/2 log2 e)
 //        D (dx,dy) = d0 + d1x dx + ...                                             (> 0)
 //        alpha = min(0.999, opacity * 2^(N'/D)),  dx,dy = pixel centre - tile centre in [-7.5, 7.5]
@@ -32,14 +32,6 @@ struct alignas(16) GaussRec {
 };
 static_assert(sizeof(GaussRec) == 64, "GaussRec must be 64 bytes");
 
-struct alignas(16) InstRec {
-    float n0, n1x, n1y, n2xx; // float4 A
-    float n2xy, n2yy, d0, d1x; // float4 B
-    float d1y, d2xx, d2xy, d2yy; // float4 C
-    float opacity, r, g, b; // float4 E
-};
-static_assert(sizeof(InstRec) == 64, "InstRec must be 64 bytes");
-
 constexpr float kNScale = -0.72134752044448170368f; // -0.5 * log2(e)
 constexpr float kLn2 = 0.69314718055994530942f;
 constexpr float kAlphaMin = 1.0f / 255.0f;
@@ -51,8 +43,7 @@ struct RasterBuffers {
     const GaussRec* gauss;     // [C*N]
     const int32_t* tile_off;   // [n_tiles_total + 1] (start of every (camera, tile); last = n_inst)
     const int32_t* inst_gid;   // [n_inst] flattened (camera*N + gaussian) id per sorted instance
-    // per-instance / per-bucket scratch
-    InstRec* inst;             // [n_inst_cap]
+    // per-bucket scratch
     uint32_t* bucket_off;      // [n_tiles_total + 1] exclusive scan of ceil(count/32)
     uint32_t* bucket_tile;     // [n_bucket_cap]
     float4* ckpt;              // [n_bucket_cap * 256]
@@ -62,21 +53,15 @@ struct RasterBuffers {
     int32_t* n_contrib;        // [C*H*W] tile-local index + 1 of the last contributor (0 = none)
 };
 
-// Tunables (process-wide; set through lfs_set_option).
+// Tunables (process-wide; set through lfs_set_option).  The *_variant switches select kernels that compute the same
+// thing (A/B measurements); they may be changed at any time.
 struct RasterOptions {
-    int use_tma = 1; // stage InstRec batches with cp.async.bulk + mbarrier (1) or register-staged loads (0)
-    int fwd_variant = 0; // forward blend register cap under test (0: none, 1: 10 CTAs/SM, 2: 12 CTAs/SM)
-    int bwd_variant = 0; // backward blend launch shape under test (warps per CTA / register cap), see launch_blend_bwd
+    int fwd_variant = 0; // forward blend: 0 TMA-gathered records (default), 1 register-staged gather (round 1)
+    int bwd_variant = 0; // backward blend: 0 software-pipelined (default), 1 lock-step (round 1)
     int pre_bwd_split = 1; // trainer: SH / geometry halves of the per-Gaussian backward as two launches (A/B switch)
     int exact_cull = 1; // trainer: drop (tile, Gaussian) instances that provably hold no alpha >= 1/255 (intersect.cuh CullRec)
-    int fuse_expand = 1; // blends gather GaussRec and expand in-kernel (no InstRec array, no expand launch)
 };
 RasterOptions& raster_options();
-
-int launch_expand_instances(const RasterBuffers& rb, const ViewCam* cams_dev /* [C] device */, uint32_t n_tiles_per_cam,
-                            uint32_t tile_w, uint32_t n_inst_cap, const uint32_t* n_inst_dev,
-                            const uint32_t* sorted_tile_keys /* nullable: per-instance tile id within camera */,
-                            uint32_t C, uint32_t N, cudaStream_t stream);
 
 int launch_bucket_offsets(const RasterBuffers& rb, uint32_t n_tiles_total, uint32_t* n_buckets_dev, void* scan_scratch,
                           uint32_t* counts_tmp, cudaStream_t stream);

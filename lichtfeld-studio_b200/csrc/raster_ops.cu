@@ -120,7 +120,6 @@ struct RasterScratch {
     ViewCam* cams;
     GaussRec* gauss;
     int32_t* tile_off;
-    InstRec* inst;
     uint32_t* bucket_off;
     uint32_t* counts_tmp;
     uint32_t* n_buckets;
@@ -143,7 +142,6 @@ static RasterScratch carve_scratch(void* blob, uint32_t C, uint32_t N, uint32_t 
     s.cams = c.take<ViewCam>(C);
     s.gauss = c.take<GaussRec>((size_t)C * N);
     s.tile_off = c.take<int32_t>(n_tiles_total + 1);
-    s.inst = raster_options().fuse_expand ? nullptr : c.take<InstRec>(n_isects ? n_isects : 1); // unused when fused
     s.bucket_off = c.take<uint32_t>(n_tiles_total + 1);
     s.counts_tmp = c.take<uint32_t>(n_tiles_total + 1);
     s.n_buckets = c.take<uint32_t>(4);
@@ -205,7 +203,6 @@ static int raster_front(const RasterScratch& s, RasterBuffers& rb, const float* 
     rb.gauss = s.gauss;
     rb.tile_off = s.tile_off;
     rb.inst_gid = flatten_ids;
-    rb.inst = s.inst;
     rb.bucket_off = s.bucket_off;
     rb.bucket_tile = s.bucket_tile;
     rb.ckpt = s.ckpt;
@@ -213,11 +210,6 @@ static int raster_front(const RasterScratch& s, RasterBuffers& rb, const float* 
     rb.pix_state = s.pix_state;
     rb.n_contrib = s.n_contrib;
     int rc = LFS_OK;
-    if (!general && !raster_options().fuse_expand) {
-        rc = launch_expand_instances(rb, s.cams, n_tiles, tile_w, (uint32_t)n_isects, nullptr, nullptr, C, N, stream);
-        if (rc)
-            return rc;
-    }
     if (bwd) {
         rc = launch_bucket_offsets(rb, n_tiles_total, s.n_buckets, s.scan_scratch, s.counts_tmp, stream);
         if (rc)

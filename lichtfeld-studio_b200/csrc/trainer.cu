@@ -49,7 +49,6 @@ struct Trainer {
     uint32_t *tk_a, *tk_b, *tv_a, *tv_b;
     int32_t* tile_off;
     uint32_t *bucket_off, *bucket_counts, *bucket_tile, *tile_max;
-    InstRec* inst;
     float4* ckpt;
     float4* pix_state;
     int32_t* n_contrib;
@@ -98,7 +97,6 @@ static size_t trainer_carve(Trainer& t, void* base) {
     t.bucket_counts = c.take<uint32_t>(t.n_tiles + 1);
     t.bucket_tile = c.take<uint32_t>(t.bucket_cap);
     t.tile_max = c.take<uint32_t>(t.n_tiles);
-    t.inst = c.take<InstRec>(t.inst_cap);
     t.ckpt = c.take<float4>((size_t)t.bucket_cap * kTilePix);
     t.pix_state = c.take<float4>(npix);
     t.n_contrib = c.take<int32_t>(npix);
@@ -973,7 +971,6 @@ extern "C" int lfs_trainer_view_forward(void* h, const float* params_arena, cons
     rb.gauss = t->gauss;
     rb.tile_off = t->tile_off;
     rb.inst_gid = reinterpret_cast<const int32_t*>(t->sorted_vals);
-    rb.inst = t->inst;
     rb.bucket_off = t->bucket_off;
     rb.bucket_tile = t->bucket_tile;
     rb.ckpt = t->ckpt;
@@ -984,12 +981,6 @@ extern "C" int lfs_trainer_view_forward(void* h, const float* params_arena, cons
     rc = launch_bucket_offsets(rb, t->n_tiles, t->n_inst + 1, t->scan_scr, t->bucket_counts, stream);
     if (rc)
         return rc;
-    if (!raster_options().fuse_expand) {
-        rc = launch_expand_instances(rb, t->cam_dev, t->n_tiles, t->tile_w, t->inst_cap, t->n_inst, t->sorted_keys, 1,
-                                     N, stream);
-        if (rc)
-            return rc;
-    }
     t->mark(3, stream);
     rc = launch_blend_fwd(rb, t->cam_dev, 1, t->d.width, t->d.height, t->tile_w, t->tile_h, true, nullptr, nullptr, nullptr,
                           nullptr, nullptr, stream);
@@ -1073,7 +1064,6 @@ extern "C" int lfs_trainer_view_backward(void* h, const float* params_arena, flo
     rb.gauss = t->gauss;
     rb.tile_off = t->tile_off;
     rb.inst_gid = reinterpret_cast<const int32_t*>(t->sorted_vals);
-    rb.inst = t->inst;
     rb.bucket_off = t->bucket_off;
     rb.bucket_tile = t->bucket_tile;
     rb.ckpt = t->ckpt;

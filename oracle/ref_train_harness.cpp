@@ -295,14 +295,15 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("intersect_offset", &gsplat::intersect_offset);
     py::class_<GutHarness>(m, "GutHarness")
         .def(py::init<Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, std::vector<double>>())
-        .def("render", &GutHarness::render)
-        .def("train_step", &GutHarness::train_step)
-        .def("view_grads", &GutHarness::view_grads)
+        // the autograd engine must not be entered with the GIL held
+        .def("render", &GutHarness::render, py::call_guard<py::gil_scoped_release>())
+        .def("train_step", &GutHarness::train_step, py::call_guard<py::gil_scoped_release>())
+        .def("view_grads", &GutHarness::view_grads, py::call_guard<py::gil_scoped_release>())
         .def_readonly("last_n_isects", &GutHarness::last_n_isects);
     py::class_<Harness>(m, "Harness")
         .def(py::init<Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, std::vector<double>>())
-        .def("train_step", &Harness::train_step)
-        .def("view_grads", &Harness::view_grads)
+        .def("train_step", &Harness::train_step, py::call_guard<py::gil_scoped_release>())
+        .def("view_grads", &Harness::view_grads, py::call_guard<py::gil_scoped_release>())
         .def("params", &Harness::params)
         .def_readwrite("densification_info", &Harness::densification_info);
 }

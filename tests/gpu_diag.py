@@ -148,9 +148,9 @@ def _raster_case(n, w, h, seed, sigma_px, with_bg):
     return sc, means, q, s, op, r
 
 
-def diag_raster(n=1500, w=200, h=136, seed=9, sigma_px=4.0, with_bg=True, tma=1, fused=1):
-    L.load().lfs_set_option(b"blend_tma", tma)
-    L.load().lfs_set_option(b"blend_fused", fused)
+def diag_raster(n=1500, w=200, h=136, seed=9, sigma_px=4.0, with_bg=True, fwd_variant=0, bwd_variant=0):
+    L.load().lfs_set_option(b"fwd_variant", fwd_variant)
+    L.load().lfs_set_option(b"bwd_variant", bwd_variant)
     out = {}
     sc, means, q, s, op, r = _raster_case(n, w, h, seed, sigma_px, with_bg)
     bg = T(np.array([[0.3, 0.2, 0.1]])) if with_bg else None
@@ -210,10 +210,10 @@ def diag_adam(n=100003):
     return out
 
 
-def diag_trainer(n=3000, w=240, h=160, deg=3, views=2, seed=21, tma=1, fused=1, lambda_dssim=None, cull=1):
+def diag_trainer(n=3000, w=240, h=160, deg=3, views=2, seed=21, fwd_variant=0, bwd_variant=0, lambda_dssim=None, cull=1):
     L.load().lfs_set_option(b"exact_cull", cull)
-    L.load().lfs_set_option(b"blend_tma", tma)
-    L.load().lfs_set_option(b"blend_fused", fused)
+    L.load().lfs_set_option(b"fwd_variant", fwd_variant)
+    L.load().lfs_set_option(b"bwd_variant", bwd_variant)
     out = {}
     sc = scene.make_scene(n, views, w, h, deg, seed=seed, sigma_px=4.0)
     tr = SplatTrainer(n, w, h, deg, DEV)
@@ -325,11 +325,11 @@ def run_all(fast=False):
     rep = {}
     t0 = time.time()
     for name, fn in (("projection", diag_projection), ("sh", diag_sh), ("intersect", diag_intersect),
-                     ("raster_tma0", lambda: diag_raster(tma=0, fused=0)), ("raster_tma1", lambda: diag_raster(tma=1, fused=0)),
-                     ("raster_fused", lambda: diag_raster(fused=1)),
+                     ("raster_default", lambda: diag_raster()), ("raster_round1_kernels", lambda: diag_raster(fwd_variant=1, bwd_variant=1)),
                      ("raster_nobg_dense", lambda: diag_raster(n=4000, w=96, h=80, seed=4, sigma_px=7.0, with_bg=False)),
                      ("adam", diag_adam), ("trainer", diag_trainer), ("ref_fastgs", diag_ref_fastgs),
-                     ("trainer_tma0", lambda: diag_trainer(n=1200, w=100, h=84, deg=2, views=1, seed=2, tma=0, fused=0))):
+                     ("trainer_round1_kernels", lambda: diag_trainer(n=1200, w=100, h=84, deg=2, views=1, seed=2, fwd_variant=1,
+                                                                     bwd_variant=1))):
         try:
             t = time.time()
             rep[name] = fn()

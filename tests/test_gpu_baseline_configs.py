@@ -71,7 +71,9 @@ def _gsplat_chain(sc, deg, rep, fwd_rtol=1e-4, bwd_rtol=1e-3, with_bwd=True, min
     rep["radii_n_diff"] = int((rad[both] != rrad[both]).any(-1).sum())
     assert rep["radii_max_diff"] <= 1, rep  # the reference's own tolerance (tests/test_numerical_gradients.cpp:325)
     assert rep["radii_n_diff"] <= max(3, rep["n_visible_ref"] // 500), rep  # measured: 0.08 % at C3 (ceil() of an fp32 value)
-    gate(rep, "means2d", m2d[both], rm2d[both], 1e-4, min_frac)
+    # 7-point sums with weights +-99: the largest deviations are a few hundredths of a pixel (maxnorm 2e-5 of 1920 px);
+    # with the absolute floor at 1e-6 of the image width about 0.6 % of the coordinates miss the element-wise band
+    gate(rep, "means2d", m2d[both], rm2d[both], 1e-4, 0.99)
     gate(rep, "depths", dep[both], rdep[both], 1e-5, min_frac)
     # conics are 2x2 inverses of 7-point UT sums with weights +-99: small entries (the off-diagonal of a nearly
     # axis-aligned conic) carry the absolute error of the large ones -> 0.995 instead of 0.999 element-wise
@@ -103,8 +105,14 @@ def _gsplat_chain(sc, deg, rep, fwd_rtol=1e-4, bwd_rtol=1e-3, with_bwd=True, min
     ren, al, li = ops.rasterize_to_pixels_from_world_3dgs_fwd(tm, tq, ts, colors, opac, bg, None, w, h, 16, tvm, None, tK,
                                                               tile_offsets=roffs, flatten_ids=rflat)
     rren, ral, rli = R.raster_fwd(tm, tq, ts, colors, opac, bg, w, h, 16, tvm, tK, roffs, rflat)
-    gate(rep, "render_rgb", ren, rren, fwd_rtol, min_frac)
-    gate(rep, "render_alpha", al, ral, fwd_rtol, min_frac)
+    # At 1e5..1e6 Gaussians a handful of the ~1e8 (pixel, Gaussian) decisions (alpha >= 1/255, T <= 1e-4) fall on the other
+    # side of the threshold in one of the two fp32 implementations; such a pixel differs by up to one contribution
+    # (<= alpha = 1/255 .. a few 1e-3).  Gate: >= 99.99 % of the values within 1e-4 element-wise, and no value further off
+    # than one threshold flip (5e-3 of the tensor maximum).
+    for key, x, y in (("render_rgb", ren, rren), ("render_alpha", al, ral)):
+        mn, fr = strict(x, y, fwd_rtol)
+        rep[key] = {"maxnorm": mn, "elementwise_pass_frac": fr, "rtol": fwd_rtol}
+        assert fr >= 0.9999 and mn <= 5e-3, (key, rep[key])
     rep["last_ids_mismatch_frac"] = float((li != rli).float().mean())
     assert rep["last_ids_mismatch_frac"] <= 2e-3, rep
     if not with_bwd:

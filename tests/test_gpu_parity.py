@@ -49,12 +49,19 @@ def test_intersect_bit_exact():
     assert r["big_sorted_n"] > 100000 and r["empty_sorted_n"] == 0
 
 
-BLEND_MODES = [(0, 0), (1, 0), (1, 1)]  # (blend_tma, blend_fused): register-staged, TMA-staged, fused expansion
+BLEND_MODES = [(0, 0), (1, 1)]  # (fwd_variant, bwd_variant): the default kernels, round 1's kernels (kept for A/B)
 
 
-@pytest.mark.parametrize("tma,fused", BLEND_MODES)
-def test_rasterize_fwd_bwd(tma, fused):
-    r = D.diag_raster(tma=tma, fused=fused)
+def _reset_variants():
+    D.L.load().lfs_set_option(b"fwd_variant", 0)
+    D.L.load().lfs_set_option(b"bwd_variant", 0)
+    D.L.load().lfs_set_option(b"exact_cull", 1)
+
+
+@pytest.mark.parametrize("fv,bv", BLEND_MODES)
+def test_rasterize_fwd_bwd(fv, bv):
+    r = D.diag_raster(fwd_variant=fv, bwd_variant=bv)
+    _reset_variants()
     assert r["n_isects"] > 5000
     assert r["fwd_rgb_rel"] <= 1e-4 and r["fwd_alpha_rel"] <= 1e-4, r
     assert r["fwd_last_ids_mismatch"] <= r["n_pixels"] // 500, r
@@ -82,15 +89,13 @@ def test_adam():
         assert r["ref_update_rel"] <= 1e-5, r
 
 
-@pytest.mark.parametrize("tma,fused,lam,cull", [m + (None, 0) for m in BLEND_MODES] + [(1, 1, None, 1), (1, 1, 0.2, 1),
-                                                                                  (1, 1, 1.0, 1)])
-def test_fused_trainer_step(tma, fused, lam, cull):
+@pytest.mark.parametrize("fv,bv,lam,cull", [m + (None, 0) for m in BLEND_MODES] + [(0, 0, None, 1), (0, 0, 0.2, 1),
+                                                                              (0, 0, 1.0, 1), (1, 1, 0.2, 1)])
+def test_fused_trainer_step(fv, bv, lam, cull):
     """lam = None: L1 loss; otherwise the reference's L1 + fused-SSIM loss with lambda_dssim = lam.
     cull = 1: exact tile culling (fewer instances, same image and gradients); cull = 0: the reference's AABB rule."""
-    r = D.diag_trainer(tma=tma, fused=fused, lambda_dssim=lam, cull=cull)
-    D.L.load().lfs_set_option(b"blend_tma", 1)
-    D.L.load().lfs_set_option(b"blend_fused", 1)
-    D.L.load().lfs_set_option(b"exact_cull", 1)
+    r = D.diag_trainer(fwd_variant=fv, bwd_variant=bv, lambda_dssim=lam, cull=cull)
+    _reset_variants()
     assert r["pack_roundtrip_exact"]
     for v in (0, 1):
         # fused step vs the same device code composed op by op (strict) ...
@@ -149,11 +154,11 @@ def test_unsupported_configurations_fail_loudly():
     from lichtfeld_studio_b200 import ops
     sc, means, q, s, op, shs = D.make_inputs(64, 1, 64, 64, 0)
     T = D.T
-    with pytest.raises(L.LfsUnsupported):
+    with pytest.raises(L.LfsUnsupported):  # ORTHO: the reference's UT projection has no such branch either
         ops.projection_ut_3dgs_fused(T(means), T(q), T(s), T(op), T(sc.viewmats), None, T(sc.Ks), 64, 64, 0.3, 0.01,
-                                     1e4, 0.0, False, camera_model=2)
-    with pytest.raises(L.LfsUnsupported):
+                                     1e4, 0.0, False, camera_model=1)
+    with pytest.raises(L.LfsError):  # fisheye takes radial coefficients only
         ops.projection_ut_3dgs_fused(T(means), T(q), T(s), T(op), T(sc.viewmats), None, T(sc.Ks), 64, 64, 0.3, 0.01,
-                                     1e4, 0.0, False, radial_coeffs=T(np.zeros((1, 6))))
+                                     1e4, 0.0, False, camera_model=2, tangential_coeffs=T(np.zeros((1, 2))))
     with pytest.raises(ValueError):
         ops.spherical_harmonics_fwd(0, T(means).cpu(), T(shs))
