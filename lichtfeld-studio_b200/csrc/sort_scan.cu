@@ -528,7 +528,10 @@ int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint3
     *result_in_b = 0;
     if (n_cap == 0 || n_bits <= 0)
         return LFS_OK;
-    if (g_sort_variant == 1 && n_bits <= kOsBits * kOsMaxPass && n_cap < (1u << 30))
+    // variant 1: onesweep for every sort; variant 2: only where it does not add a pass (<= 16 key bits: the tile sort; the
+    // 32-bit depth sort keeps three 11-bit passes instead of four 8-bit ones)
+    if ((g_sort_variant == 1 || (g_sort_variant == 2 && n_bits <= 2 * kOsBits)) && n_bits <= kOsBits * kOsMaxPass &&
+        n_cap < (1u << 30))
         return radix_sort_pairs_onesweep(keys_a, vals_a, keys_b, vals_b, n_cap, n_dev, begin_bit, n_bits, scratch,
                                          result_in_b, stream);
     // per-device attribute; cheap enough to set on every call (one process may drive several devices)
