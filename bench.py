@@ -279,18 +279,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
-        tr.loss_dev.zero_()
-        for v in my_views:
-            tr.forward(sc.viewmats[v], sc.Ks[v], deg, bg)
-            tr.loss_ssim_l1(targets_dev[v], LAMBDA_DSSIM)
-            tr.backward()
-        if world > 1:
-            if tr.p2p:
-                tr._h_grads.barrier(channel=0)
-            else:
-                dist.all_reduce(tr.grads, op=dist.ReduceOp.SUM)
-        tr.adam_step(n_views=V)
+    targets_resident = [targets_dev.get(v, targets_host[v]) for v in range(V)]
+
+    def step_resident():  # same public call as the e2e leg, targets already in HBM, loss left on the device
+        tr.train_step(sc.viewmats, sc.Ks, targets_resident, bg, deg, world, rank, read_loss=False,
+                      lambda_dssim=LAMBDA_DSSIM, view_costs=view_costs)
 
     def step_e2e():
         tr.train_step(sc.viewmats, sc.Ks, targets_host, bg, deg, world, rank, read_loss=True, view_costs=view_costs)
@@ -324,12 +317,14 @@ def main():
     # per-kernel timing for the roofline: a PROFILING pass outside the timed regions.  Every stage is bracketed by CUDA
     # events and the backward blocks on the stream, so consecutive views do not overlap here: the stage times sum to a
     # little more than ms_per_step / views (in the timed run the tail of a view overlaps the head of the next).
+    tr.lanes_enabled = False  # stage times: one view at a time (the timed runs keep tr.n_lanes views in flight)
     tr.set_profile(True)
     for _ in range(2):
         step_resident()
     torch.cuda.synchronize()
     prof = tr.get_profile()
     tr.set_profile(False)
+    tr.lanes_enabled = True
 
     if rank != 0:
         if world > 1:
@@ -367,7 +362,7 @@ def main():
         "config": {"workload": workload, "gaussians": n, "views_per_step": V, "width": W, "height": H, "sh_degree": deg,
                    "parallelism": f"view-sharded dp{world}" + ("" if view_costs is None else " (views assigned by instance "
                                   "count, equal counts per rank)") + f": {dp_mode}",
-                   "instances_per_view": I, "l2": "per-step working set (params+grads+Adam state+records) >= 1 GB, "
+                   "views_in_flight": tr.n_lanes, "instances_per_view": I, "l2": "per-step working set (params+grads+Adam state+records) >= 1 GB, "
                                                   "larger than the 126 MB L2: no flush needed"},
         "clocks": clk,
         "e2e": {"value": V / ms_e2e * 1e3, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
@@ -375,7 +370,7 @@ def main():
                 "note": "SplatTrainer.train_step: pinned uint8 HWC targets copied per view on a side stream, "
                         "loss scalar read back per step"},
         "gpu_launches": launches,
-        "roofline": {"kernel": "k_blend_bwd", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"kernel": "k_blend_bwd_sp", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": peak_src, "algorithmic_bytes": bwd_bytes, "launch_ms": bwd_ms,
                      "note": "algorithmic bytes = 172*I + 24*P per view (BASELINE.md s5); the kernel is FP32/SFU and "

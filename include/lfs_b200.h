@@ -72,8 +72,11 @@ uint64_t lfs_launch_count(void);
  * means [N,3], quats [N,4] wxyz, scales [N,3], opacities [N] or NULL, viewmats0 [C,4,4] row-major w2c,
  * Ks [C,3,3].  Outputs radii [C,N,2] i32, means2d [C,N,2], depths [C,N], conics [C,N,3],
  * compensations [C,N] or NULL.  Culled entries: radii = 0, other outputs untouched (as the reference).
- * Supported: LFS_PINHOLE, LFS_GLOBAL, no distortion (viewmats1 / radial / tangential / thin_prism NULL);
- * anything else returns LFS_ERR_UNSUPPORTED. */
+ * Camera models: LFS_PINHOLE with optional OpenCV distortion (radial_coeffs [C,6], tangential_coeffs [C,2],
+ * thin_prism_coeffs [C,4], any of them NULL), LFS_FISHEYE (radial_coeffs [C,4]; tangential / thin prism must be
+ * NULL as in the reference's fisheye model), and every rolling-shutter type with viewmats1 [C,4,4] as the pose
+ * at the end of the exposure (gsplat/Cameras.cuh semantics).  LFS_ORTHO returns LFS_ERR_UNSUPPORTED (the
+ * reference's UT projection has no orthographic model either). */
 int lfs_projection_ut_3dgs_fused(const float* means, const float* quats, const float* scales,
                                  const float* opacities, const float* viewmats0, const float* viewmats1,
                                  const float* Ks, uint32_t N, uint32_t C, uint32_t image_width,
@@ -120,9 +123,12 @@ int lfs_intersect_offset(const int64_t* isect_ids, int64_t n_isects, uint32_t C,
  * means [N,3], quats [N,4] (normalised), scales [N,3], colors [C,N,channels], opacities [C,N],
  * backgrounds [C,channels] or NULL, masks [C,th,tw] bool bytes or NULL, tile_offsets [C,th,tw] i32,
  * flatten_ids [n_isects] i32 -> renders [C,H,W,channels], alphas [C,H,W,1], last_ids [C,H,W] i32.
- * Supported: channels == 3, tile_size == 16, LFS_PINHOLE, LFS_GLOBAL, no distortion.  For C > 1 the
- * gaussian id of a flattened index g is g % N (the reference kernel is single-camera).
- * Scratch (per-instance records) is requested through `alloc` with tag 0. */
+ * tile_size == 16.  Any `channels` >= 1 (processed in groups of three through the same kernels; the
+ * reference instantiates CDIM 1..5, 8, 9, 16, 17, 32, 33, ...).  Undistorted global-shutter pinhole cameras take
+ * the per-tile polynomial kernels; distortion, fisheye and rolling shutter take the per-pixel-ray kernels
+ * (csrc/raster_rays.cu); LFS_ORTHO returns LFS_ERR_UNSUPPORTED.  For C > 1 the gaussian id of a flattened
+ * index g is g % N (the reference kernel is single-camera).
+ * Scratch (per-gaussian records, pixel rays) is requested through `alloc` with tag 0. */
 int lfs_rasterize_to_pixels_from_world_3dgs_fwd(
     const float* means, const float* quats, const float* scales, const float* colors, const float* opacities,
     const float* backgrounds, const uint8_t* masks, uint32_t N, uint32_t C, uint32_t channels,
@@ -134,7 +140,7 @@ int lfs_rasterize_to_pixels_from_world_3dgs_fwd(
 
 /* Replaces gsplat::rasterize_to_pixels_from_world_3dgs_bwd / launch_..._bwd_kernel<CDIM>
  * (gsplat/Ops.h:131-166, gsplat/Rasterization.h:137-174, kernel gsplat/RasterizeToPixelsFromWorld3DGSBwd.cu:17-372).
- * Outputs v_means [N,3], v_quats [N,4], v_scales [N,3], v_colors [C,N,3], v_opacities [C,N] are fully
+ * Outputs v_means [N,3], v_quats [N,4], v_scales [N,3], v_colors [C,N,channels], v_opacities [C,N] are fully
  * written (zero-filled then accumulated, like the reference's at::zeros_like + atomics). */
 int lfs_rasterize_to_pixels_from_world_3dgs_bwd(
     const float* means, const float* quats, const float* scales, const float* colors, const float* opacities,
@@ -320,6 +326,11 @@ int lfs_trainer_view_loss_ssim_l1(void* trainer, const void* target, int target_
 int lfs_trainer_view_set_grad(void* trainer, const float* v_image, const float* v_alpha, void* stream);
 /* backward of the last forward: grads_arena += d loss / d raw parameters */
 int lfs_trainer_view_backward(void* trainer, const float* params_arena, float* grads_arena, void* stream);
+/* The same in two halves.  _blend (blend backward) only touches the handle's own scratch; _params (SH / projection /
+ * activation VJPs) read-modify-writes grads_arena.  A caller that runs consecutive views on two streams, one trainer
+ * handle per stream and both on the same arenas, orders only the _params halves with events (trainer.py train_step). */
+int lfs_trainer_view_backward_blend(void* trainer, void* stream);
+int lfs_trainer_view_backward_params(void* trainer, const float* params_arena, float* grads_arena, void* stream);
 /* blocks on `stream`; returns LFS_ERR_CAPACITY if the last forward overflowed instance_capacity */
 int lfs_trainer_stats(void* trainer, uint64_t* n_instances, uint64_t* n_buckets, void* stream);
 /* Non-blocking overflow check for training loops: every forward records the largest instance count any view has needed

@@ -137,6 +137,8 @@ SIGNATURES = {
     "lfs_trainer_view_loss_ssim_l1": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_float, _vp, _vp]),
     "lfs_trainer_view_set_grad": (C.c_int, [_vp, _vp, _vp, _vp]),
     "lfs_trainer_view_backward": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "lfs_trainer_view_backward_blend": (C.c_int, [_vp, _vp]),
+    "lfs_trainer_view_backward_params": (C.c_int, [_vp, _vp, _vp, _vp]),
     "lfs_trainer_set_profile": (C.c_int, [_vp, C.c_int]),
     "lfs_trainer_get_profile": (C.c_int, [_vp, C.POINTER(_f), C.POINTER(C.c_int)]),
     "lfs_trainer_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), _vp]),

@@ -1054,11 +1054,14 @@ extern "C" int lfs_trainer_view_set_grad(void* h, const float* v_image, const fl
     return LFS_OK;
 }
 
-extern "C" int lfs_trainer_view_backward(void* h, const float* params_arena, float* grads_arena, void* stream_) {
+// The backward of a view in two halves, so that a caller running two views on two streams (each view on its own trainer
+// handle, both accumulating into one gradient arena) can order just the second halves: the blend backward only touches
+// per-handle scratch, the per-Gaussian kernels read-modify-write the shared gradient arena.
+extern "C" int lfs_trainer_view_backward_blend(void* h, void* stream_) {
     Trainer* t = static_cast<Trainer*>(h);
     cudaStream_t stream = (cudaStream_t)stream_;
-    LFS_CHECK_ARG(t && params_arena && grads_arena, "trainer_view_backward: null pointer");
-    LFS_CHECK_ARG(t->sorted_vals != nullptr, "trainer_view_backward: no forward has been run");
+    LFS_CHECK_ARG(t, "trainer_view_backward_blend: null handle");
+    LFS_CHECK_ARG(t->sorted_vals != nullptr, "trainer_view_backward_blend: no forward has been run");
     const uint32_t N = t->d.n_gaussians;
     RasterBuffers rb{};
     rb.gauss = t->gauss;
@@ -1077,6 +1080,15 @@ extern "C" int lfs_trainer_view_backward(void* h, const float* params_arena, flo
     if (rc)
         return rc;
     t->mark(6, stream);
+    return LFS_OK;
+}
+
+extern "C" int lfs_trainer_view_backward_params(void* h, const float* params_arena, float* grads_arena, void* stream_) {
+    Trainer* t = static_cast<Trainer*>(h);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LFS_CHECK_ARG(t && params_arena && grads_arena, "trainer_view_backward_params: null pointer");
+    LFS_CHECK_ARG(t->sorted_vals != nullptr, "trainer_view_backward_params: no forward has been run");
+    const uint32_t N = t->d.n_gaussians;
     if (!raster_options().pre_bwd_split) {
         k_preprocess_bwd<<<div_up(N, 256), 256, 0, stream>>>(params_arena, grads_arena, t->pl, N, t->cam_host,
                                                              (int)t->active_degree, t->counts, t->v_means, t->v_quats,
@@ -1114,6 +1126,12 @@ extern "C" int lfs_trainer_view_backward(void* h, const float* params_arena, flo
         }
     }
     return LFS_OK;
+}
+
+extern "C" int lfs_trainer_view_backward(void* h, const float* params_arena, float* grads_arena, void* stream) {
+    LFS_CHECK_ARG(h && params_arena && grads_arena, "trainer_view_backward: null pointer");
+    const int rc = lfs_trainer_view_backward_blend(h, stream);
+    return rc ? rc : lfs_trainer_view_backward_params(h, params_arena, grads_arena, stream);
 }
 
 extern "C" int lfs_trainer_set_profile(void* h, int enable) {

@@ -34,7 +34,9 @@ class SplatTrainer:
     def __init__(self, n_gaussians: int, width: int, height: int, sh_degree_max: int = 3, device="cuda:0",
                  instance_capacity: int = 0, lrs: Optional[dict] = None, betas=(0.9, 0.999), eps: float = 1e-15,
                  iterations: int = 30000, eps2d=0.3, near_plane=0.01, far_plane=1e4, radius_clip=0.0,
-                 scale_reg: float = 0.0, opacity_reg: float = 0.0):
+                 scale_reg: float = 0.0, opacity_reg: float = 0.0, view_streams: Optional[int] = None):
+        """view_streams: how many views train_step keeps in flight (each on its own stream and its own per-view scratch;
+        default 2, LFS_VIEW_STREAMS overrides).  The single-view calls (forward / loss_* / backward) use lane 0."""
         self.lib = load()
         self.device = torch.device(device)
         self.N, self.W, self.H, self.deg_max = n_gaussians, width, height, sh_degree_max
@@ -42,13 +44,19 @@ class SplatTrainer:
         self.Np = (n_gaussians + 3) // 4 * 4
         self.desc = TrainerDesc(n_gaussians, sh_degree_max, width, height, eps2d, near_plane, far_plane, radius_clip,
                                 UTParams.default(), instance_capacity)
-        self.h = None
+        if view_streams is None:
+            view_streams = int(os.environ.get("LFS_VIEW_STREAMS", "2"))
+        self.n_lanes = max(1, min(4, int(view_streams)))
+        self._hs = [None] * self.n_lanes
+        self._cur = 0
+        self.lanes_enabled = True  # False: train_step runs its views one after the other on the current stream
         self._create_handle()
         n_floats = int(self.lib.lfs_trainer_arena_floats(C.byref(self.desc)))
         assert n_floats == (11 + 3 * self.K) * self.Np
         mk = lambda: torch.zeros(n_floats, dtype=torch.float32, device=self.device)
         self.params, self.grads, self.exp_avg, self.exp_avg_sq = mk(), mk(), mk(), mk()
-        self.loss_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._loss_lanes = torch.zeros(self.n_lanes, dtype=torch.float32, device=self.device)
+        self.loss_dev = self._loss_lanes[0:1]  # lane 0 is what the single-view calls accumulate into
         # planar segment table in the reference's group order
         planes = [3, 3, 3 * (self.K - 1), 3, 4, 1]
         self.seg_begin = [0]
@@ -64,20 +72,31 @@ class SplatTrainer:
         self.iteration = 0
         self.means_gamma = math.pow(0.01, 1.0 / iterations)  # strategy_utils.cpp:47-55 (means group only)
         self.copy_stream = torch.cuda.Stream(device=self.device)
-        self._tgt = [torch.empty((height, width, 3), dtype=torch.uint8, device=self.device) for _ in range(2)]
-        self._tgt_ready = [torch.cuda.Event() for _ in range(2)]
-        self._tgt_free = [torch.cuda.Event() for _ in range(2)]
+        self._lane_streams = [torch.cuda.Stream(device=self.device) for _ in range(self.n_lanes)] if self.n_lanes > 1 else []
+        n_slots = 2 * self.n_lanes
+        self._tgt = [torch.empty((height, width, 3), dtype=torch.uint8, device=self.device) for _ in range(n_slots)]
+        self._tgt_ready = [torch.cuda.Event() for _ in range(n_slots)]
+        self._tgt_free = [torch.cuda.Event() for _ in range(n_slots)]
+        self._ev_start = torch.cuda.Event()
+        self._ev_grads = [torch.cuda.Event() for _ in range(self.n_lanes)]  # "this lane's last gradient RMW is enqueued"
         self._loss_pinned = torch.zeros(1, dtype=torch.float32).pin_memory()
         self.p2p = False
 
+    @property
+    def h(self):
+        return self._hs[self._cur]
+
     def _create_handle(self) -> None:
-        old, self.h = self.h, None
-        if old:
-            self.lib.lfs_trainer_destroy(old)
+        """(Re-)creates the per-view scratch of every lane from self.desc."""
+        for k in range(self.n_lanes):
+            old, self._hs[k] = self._hs[k], None
+            if old:
+                self.lib.lfs_trainer_destroy(old)
         with torch.cuda.device(self.device):
-            self.h = self.lib.lfs_trainer_create(C.byref(self.desc))
-        if not self.h:
-            raise _lib.LfsError(-4, self.lib.lfs_last_error().decode())
+            for k in range(self.n_lanes):
+                self._hs[k] = self.lib.lfs_trainer_create(C.byref(self.desc))
+                if not self._hs[k]:
+                    raise _lib.LfsError(-4, self.lib.lfs_last_error().decode())
 
     # ---- instance capacity (tile-Gaussian pairs per view) ---------------------------------------------------------
     @property
@@ -88,9 +107,12 @@ class SplatTrainer:
         """Non-blocking: raises LfsError(LFS_ERR_CAPACITY) once a view whose tile instances did not fit has been seen
         (lfs_trainer_poll_capacity).  forward() / train_step() call it, so an overflow never goes unnoticed for more than
         one step.  Returns the largest per-view instance count observed so far."""
-        hw = C.c_uint64(0)
-        check(self.lib.lfs_trainer_poll_capacity(self.h, C.byref(hw)))
-        return int(hw.value)
+        worst = 0
+        for h in self._hs:
+            hw = C.c_uint64(0)
+            check(self.lib.lfs_trainer_poll_capacity(h, C.byref(hw)))
+            worst = max(worst, int(hw.value))
+        return worst
 
     def ensure_capacity(self, viewmats, Ks, active_sh_degree: Optional[int] = None, headroom: float = 1.25) -> int:
         """Blocking calibration (outside any timed region): renders the given views once, and if one of them needs more
@@ -138,9 +160,10 @@ class SplatTrainer:
         self.p2p = True
 
     def __del__(self):
-        h, self.h = getattr(self, "h", None), None
-        if h:
-            self.lib.lfs_trainer_destroy(h)
+        hs, self._hs = getattr(self, "_hs", []), []
+        for h in hs:
+            if h:
+                self.lib.lfs_trainer_destroy(h)
 
     # ---- parameters ------------------------------------------------------------------------------------
     def _stream(self) -> int:
@@ -300,19 +323,21 @@ class SplatTrainer:
 
     def loss_l1(self, target: torch.Tensor, scale: Optional[float] = None, fmt: int = IMG_U8_HWC) -> None:
         s = 1.0 / (3.0 * self.W * self.H) if scale is None else scale
-        check(self.lib.lfs_trainer_view_loss_l1(self.h, target.data_ptr(), fmt, s, self.loss_dev.data_ptr(),
-                                                self._stream()))
+        check(self.lib.lfs_trainer_view_loss_l1(self.h, target.data_ptr(), fmt, s, self._loss_ptr(), self._stream()))
 
     def loss_ssim_l1(self, target: torch.Tensor, lambda_dssim: float = 0.2, weight: float = 1.0,
                      fmt: int = IMG_U8_HWC) -> None:
         """The reference's photometric loss (src/training/trainer.cpp:103-131): (1 - l) * L1 + l * (1 - SSIM_valid);
         lambda_dssim = 0.2 is eval/default_optimization_params.json."""
         check(self.lib.lfs_trainer_view_loss_ssim_l1(self.h, target.data_ptr(), fmt, lambda_dssim, weight,
-                                                     self.loss_dev.data_ptr(), self._stream()))
+                                                     self._loss_ptr(), self._stream()))
 
     def set_grad(self, v_image: torch.Tensor, v_alpha: Optional[torch.Tensor] = None) -> None:
         check(self.lib.lfs_trainer_view_set_grad(self.h, v_image.data_ptr(),
                                                  None if v_alpha is None else v_alpha.data_ptr(), self._stream()))
+
+    def _loss_ptr(self) -> int:
+        return self._loss_lanes.data_ptr() + 4 * self._cur
 
     def backward(self) -> None:
         check(self.lib.lfs_trainer_view_backward(self.h, self.params.data_ptr(), self.grads.data_ptr(),
@@ -405,27 +430,60 @@ class SplatTrainer:
                    bg=(0.0, 0.0, 0.0), active_sh_degree: Optional[int] = None, world_size: int = 1, rank: int = 0,
                    read_loss: bool = True, lambda_dssim: Optional[float] = 0.2,
                    view_costs: Optional[Sequence[float]] = None):
-        """targets_pinned: pinned host uint8 [H,W,3] tensors, one per view of the GLOBAL batch; this rank renders
+        """targets_pinned: pinned host uint8 [H,W,3] tensors (or tensors already on the device), one per view of the GLOBAL
+        batch (entries of views other ranks render are not touched); this rank renders
         views rank, rank + world_size, ... (or the cost-balanced partition of dp.shard_views when view_costs is given).
         Host->device copies run on a side stream, double buffered."""
         main = torch.cuda.current_stream(self.device)
-        self.loss_dev.zero_()
+        self._loss_lanes.zero_()
         my_views = dp.shard_views(len(targets_pinned), world_size, rank, view_costs)
+        L = self.n_lanes if (len(my_views) > 1 and self.lanes_enabled) else 1
+        n_slots = 2 * L
+        if L > 1:
+            self._ev_start.record(main)  # the lanes start behind the previous optimiser step
+        last_grads = None
         for i, v in enumerate(my_views):
-            slot = i & 1
-            with torch.cuda.stream(self.copy_stream):
-                if i >= 2:
-                    self.copy_stream.wait_event(self._tgt_free[slot])
-                self._tgt[slot].copy_(targets_pinned[v], non_blocking=True)
-                self._tgt_ready[slot].record(self.copy_stream)
-            self.forward(viewmats[v], Ks[v], active_sh_degree, bg)
-            main.wait_event(self._tgt_ready[slot])
-            if lambda_dssim is None:
-                self.loss_l1(self._tgt[slot])
-            else:
-                self.loss_ssim_l1(self._tgt[slot], lambda_dssim)
-            self._tgt_free[slot].record(main)
-            self.backward()
+            slot, lane = i % n_slots, i % L
+            st = self._lane_streams[lane] if L > 1 else main
+            resident = targets_pinned[v].is_cuda  # already in HBM (bench.py's device-resident leg): no staging copy
+            if not resident:
+                with torch.cuda.stream(self.copy_stream):
+                    if i >= n_slots:
+                        self.copy_stream.wait_event(self._tgt_free[slot])
+                    self._tgt[slot].copy_(targets_pinned[v], non_blocking=True)
+                    self._tgt_ready[slot].record(self.copy_stream)
+            target = targets_pinned[v] if resident else self._tgt[slot]
+            self._cur = lane
+            with torch.cuda.stream(st):
+                if L > 1 and i < L:
+                    st.wait_event(self._ev_start)
+                self.forward(viewmats[v], Ks[v], active_sh_degree, bg)
+                if not resident:
+                    st.wait_event(self._tgt_ready[slot])
+                if lambda_dssim is None:
+                    self.loss_l1(target)
+                else:
+                    self.loss_ssim_l1(target, lambda_dssim)
+                if not resident:
+                    self._tgt_free[slot].record(st)
+                if L == 1:
+                    self.backward()
+                else:
+                    # the blend backward works on this lane's scratch; only the per-Gaussian kernels, which read-modify-write
+                    # the shared gradient arena, are ordered behind the previous view's
+                    check(self.lib.lfs_trainer_view_backward_blend(self.h, self._stream()))
+                    if last_grads is not None:
+                        st.wait_event(last_grads)
+                    check(self.lib.lfs_trainer_view_backward_params(self.h, self.params.data_ptr(),
+                                                                    self.grads.data_ptr(), self._stream()))
+                    self._views_since_step += 1
+                    last_grads = self._ev_grads[lane]
+                    last_grads.record(st)
+        self._cur = 0
+        if L > 1:
+            for lane in range(min(L, len(my_views))):
+                main.wait_event(self._ev_grads[lane])
+            self.loss_dev += self._loss_lanes[1:].sum()
         if world_size > 1:
             if self.p2p:
                 self._h_grads.barrier(channel=0)  # all ranks finished their backward passes; then the fused step

@@ -16,6 +16,7 @@
 #define PFX orc32_
 #include "lfs_oracle_impl.h"
 #include "lfs_oracle_fastgs_impl.h"
+#include "lfs_oracle_legacy2d_impl.h"
 #undef REAL
 #undef PFX
 
@@ -23,6 +24,7 @@
 #define PFX orc64_
 #include "lfs_oracle_impl.h"
 #include "lfs_oracle_fastgs_impl.h"
+#include "lfs_oracle_legacy2d_impl.h"
 #undef REAL
 #undef PFX
 
