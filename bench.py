@@ -137,13 +137,15 @@ def cpu_reference_leg(scene_obj, seconds: float):
                       f"{dt:.2f} s per view (no crop, no extrapolation; the Adam step is not in the sample)"}
 
 
-def reference_gpu_leg(path: str, config: str, n_gaussians: int, views: int, steps: int):
+def reference_gpu_leg(path: str, config: str, n_gaussians: int, views: int, steps: int, module: str = "ref"):
     """The reference's OWN training step on the same scene, cameras, loss and batch structure, in a child process:
     tools/ref_train.py drives oracle/ref_train_harness.cpp, i.e. the reference's FastGSRasterize (path 'fastgs') or
     SphericalHarmonicsFunction / fully_fused_projection_with_ut / GUTRasterizationFunction (path 'gut') autograd
     Functions, its fused_ssim and its FusedAdam, all compiled UNCHANGED, on the reference's own CUDA backends.  A
-    baseline timed beside ours as the north_star asks -- never part of the product path."""
-    cmd = [sys.executable, os.path.join(ROOT, "tools", "ref_train.py"), "--module", "ref", "--path", path, "--config",
+    baseline timed beside ours as the north_star asks -- never part of the product path.
+    module 'b200': the SAME unchanged reference caller code linked against this library's host layer instead (the drop-in
+    configuration a maintainer gets by switching the backend)."""
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "ref_train.py"), "--module", module, "--path", path, "--config",
            config, "--views", str(views), "--steps", str(max(2, min(steps, 4))), "--warmup", "1"]
     if n_gaussians:
         cmd += ["--n-gaussians", str(n_gaussians)]
@@ -404,6 +406,16 @@ def main():
                 line[key] = (line["value"] / v) if v else None
         except Exception as e:
             line["reference_gpu"] = {"error": repr(e)}
+        try:  # drop-in: the reference's unchanged autograd Functions / fused_ssim / FusedAdam on THIS library's backend
+            line["drop_in"] = {}
+            for name, path in (("gsplat", "gut"), ("fastgs", "fastgs")):
+                d = reference_gpu_leg(path, a.config, a.n_gaussians, vpg, a.steps, module="b200")
+                ref_v = (line.get("reference_gpu") or {}).get(name, {}).get("value")
+                if d.get("value") and ref_v:
+                    d["vs_reference_same_callers"] = d["value"] / ref_v
+                line["drop_in"][name] = d
+        except Exception as e:
+            line["drop_in"] = {"error": repr(e)}
         try:  # the EWA (fastgs) surface of this library on the same workload, op level (forward + backward per view)
             r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_fastgs.py"), a.config, "2", "2"],
                                capture_output=True, text=True, timeout=300)

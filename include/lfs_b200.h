@@ -224,6 +224,55 @@ int lfs_relocation(const float* opacities, const float* scales, const int32_t* r
 int lfs_add_noise(const float* raw_opacities, const float* raw_scales, const float* raw_quats, const float* noise,
                   float* means, float current_lr, uint32_t n, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * legacy 2-D operator surface: the ops the reference's gtest files call
+ * (tests/test_basic.cpp:54-128,347-358; tests/test_gsplat_ops.cpp:76-96,174-189,276-287; tests/test_rasterization.cpp:
+ * 110-121) and whose launchers gsplat/Rasterization.h:16-63 still declares, but whose kernels are no longer in the
+ * reference tree.  Semantics: tests/torch_impl.cpp:38-218 (the reference's CPU statement), the culling tail of
+ * ProjectionUT3DGSFused.cu:142-199, and the blend loop of RasterizeToPixelsFromWorld3DGS{Fwd,Bwd}.cu with the 2-D conic
+ * response sigma = 1/2 (a dx^2 + c dy^2) + b dx dy.
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* quats [N,4] wxyz (normalised inside), scales [N,3] -> covars / precis [N,3,3], or [N,6] (xx,xy,xz,yy,yz,zz) if triu.
+ * Either output may be NULL (the reference's compute_covar / compute_preci flags). */
+int lfs_quat_scale_to_covar_preci_fwd(const float* quats, const float* scales, uint32_t N, int triu, float* covars,
+                                      float* precis, void* stream);
+/* v_covars / v_precis in the forward's layout (either may be NULL) -> v_quats [N,4], v_scales [N,3] (overwritten). */
+int lfs_quat_scale_to_covar_preci_bwd(const float* quats, const float* scales, uint32_t N, int triu,
+                                      const float* v_covars, const float* v_precis, float* v_quats, float* v_scales,
+                                      void* stream);
+
+/* Fused pinhole EWA projection.  means [N,3]; covars [N,3,3] or NULL (then quats [N,4] + scales [N,3]); opacities [N] or
+ * NULL (NULL: fixed 3.33 sigma extent); viewmats [C,4,4]; Ks [C,3,3].  Outputs as lfs_projection_ut_3dgs_fused:
+ * radii [C,N,2] i32 (always written, 0 = culled), means2d [C,N,2], depths [C,N], conics [C,N,3], compensations [C,N] or
+ * NULL; culled entries of the float outputs are left untouched.  camera_model must be LFS_PINHOLE. */
+int lfs_projection_ewa_3dgs_fused_fwd(const float* means, const float* covars, const float* quats, const float* scales,
+                                      const float* opacities, const float* viewmats, const float* Ks, uint32_t N,
+                                      uint32_t C, uint32_t image_width, uint32_t image_height, float eps2d,
+                                      float near_plane, float far_plane, float radius_clip, int camera_model,
+                                      int32_t* radii, float* means2d, float* depths, float* conics, float* compensations,
+                                      void* stream);
+
+/* 2-D alpha blend (gsplat/Rasterization.h:16-36).  means2d [C,N,2], conics [C,N,3], colors [C,N,channels],
+ * opacities [C,N], backgrounds [C,channels] or NULL, masks [C,th,tw] bool bytes or NULL, tile_offsets [C,th,tw],
+ * flatten_ids [n_isects] (indices into [C*N]) -> renders [C,H,W,channels], alphas [C,H,W,1], last_ids [C,H,W].
+ * tile_size == 16, 1 <= channels <= 40. */
+int lfs_rasterize_to_pixels_3dgs_fwd(const float* means2d, const float* conics, const float* colors,
+                                     const float* opacities, const float* backgrounds, const uint8_t* masks, uint32_t C,
+                                     uint32_t N, uint32_t channels, uint32_t image_width, uint32_t image_height,
+                                     uint32_t tile_size, const int32_t* tile_offsets, const int32_t* flatten_ids,
+                                     int64_t n_isects, float* renders, float* alphas, int32_t* last_ids, void* stream);
+/* Backward (gsplat/Rasterization.h:38-63).  Outputs are fully written (zero-filled, then accumulated):
+ * v_means2d_abs [C,N,2] or NULL (the absgrad variant), v_means2d [C,N,2], v_conics [C,N,3], v_colors [C,N,channels],
+ * v_opacities [C,N]. */
+int lfs_rasterize_to_pixels_3dgs_bwd(const float* means2d, const float* conics, const float* colors,
+                                     const float* opacities, const float* backgrounds, const uint8_t* masks, uint32_t C,
+                                     uint32_t N, uint32_t channels, uint32_t image_width, uint32_t image_height,
+                                     uint32_t tile_size, const int32_t* tile_offsets, const int32_t* flatten_ids,
+                                     int64_t n_isects, const float* render_alphas, const int32_t* last_ids,
+                                     const float* v_render_colors, const float* v_render_alphas, float* v_means2d_abs,
+                                     float* v_means2d, float* v_conics, float* v_colors, float* v_opacities, void* stream);
+
 /* ---- fastgs (EWA) rasterizer surface ----------------------------------------------------------------------
  * Replaces fast_gs::rasterization::forward (fastgs/rasterization/include/forward.h:13-38, src/forward.cu:15-199;
  * called by forward_wrapper, src/rasterization_api.cu:15-89, which fast_rasterize() binds,

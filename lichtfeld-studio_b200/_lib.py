@@ -114,6 +114,13 @@ SIGNATURES = {
         [_vp] * 7 + [_u32] * 6 + [_vp] * 3 + [C.c_int, C.POINTER(UTParams), C.c_int] + [_vp] * 3 + [_vp, _vp, _i64]
         + [_vp] * 4 + [ALLOC_FN, _vp] + [_vp] * 5 + [_vp],
     ),
+    "lfs_quat_scale_to_covar_preci_fwd": (C.c_int, [_vp, _vp, _u32, C.c_int, _vp, _vp, _vp]),
+    "lfs_quat_scale_to_covar_preci_bwd": (C.c_int, [_vp, _vp, _u32, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "lfs_projection_ewa_3dgs_fused_fwd": (
+        C.c_int, [_vp] * 7 + [_u32] * 4 + [_f] * 4 + [C.c_int] + [_vp] * 5 + [_vp]),
+    "lfs_rasterize_to_pixels_3dgs_fwd": (C.c_int, [_vp] * 6 + [_u32] * 6 + [_vp, _vp, _i64] + [_vp] * 3 + [_vp]),
+    "lfs_rasterize_to_pixels_3dgs_bwd": (
+        C.c_int, [_vp] * 6 + [_u32] * 6 + [_vp, _vp, _i64] + [_vp] * 4 + [_vp] * 5 + [_vp]),
     "lfs_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _f, _vp]),
     "lfs_adam_step_multi": (
         C.c_int,

@@ -31,6 +31,12 @@ __host__ __device__ __forceinline__ quat4 quat_inverse(const quat4 q) { // glm::
     const float d = q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z;
     return quat4{q.w / d, -q.x / d, -q.y / d, -q.z / d};
 }
+// glm::slerp.  The reference builds its kernels with --use_fast_math (gsplat/CMakeLists.txt:76), which turns glm's sin()
+// and the division into sin.approx / div.approx: for the small angle between the two shutter poses sin.approx's ABSOLUTE
+// error (2^-21.4) is a RELATIVE error of ~2e-5 of sin(angle), i.e. the interpolated quaternion comes out with a norm that
+// is off by that much, and mat3_cast / rotate of it move a ray by ~1e-4 of a Gaussian's extent.  Parity means reproducing
+// the deployed arithmetic, so the device path uses the same approximate instructions (with sinf the rolling-shutter
+// renders of tests/test_gpu_boundary.py are 4e-3 away from the reference build).
 __host__ __device__ inline quat4 quat_slerp(const quat4 x, const quat4 y, const float a) {
     float c = x.w * y.w + x.x * y.x + x.y * y.y + x.z * y.z;
     quat4 z = y;
@@ -38,12 +44,20 @@ __host__ __device__ inline quat4 quat_slerp(const quat4 x, const quat4 y, const 
         z = quat4{-y.w, -y.x, -y.y, -y.z};
         c = -c;
     }
-    if (c > 1.f - FLT_EPSILON) // nearly parallel: component-wise lerp (glm does not renormalise)
-        return quat4{x.w + a * (z.w - x.w), x.x + a * (z.x - x.x), x.y + a * (z.y - x.y), x.z + a * (z.z - x.z)};
+    if (c > 1.f - FLT_EPSILON) { // nearly parallel: glm::mix per component (glm does not renormalise)
+        const float b = 1.f - a;
+        return quat4{x.w * b + z.w * a, x.x * b + z.x * a, x.y * b + z.y * a, x.z * b + z.z * a};
+    }
     const float ang = acosf(c);
-    const float s0 = sinf((1.f - a) * ang), s1 = sinf(a * ang), is = 1.0f / sinf(ang);
-    return quat4{(s0 * x.w + s1 * z.w) * is, (s0 * x.x + s1 * z.x) * is, (s0 * x.y + s1 * z.y) * is,
-                 (s0 * x.z + s1 * z.z) * is};
+#ifdef __CUDA_ARCH__
+    const float s0 = __sinf((1.f - a) * ang), s1 = __sinf(a * ang), sd = __sinf(ang);
+    return quat4{__fdividef(s0 * x.w + s1 * z.w, sd), __fdividef(s0 * x.x + s1 * z.x, sd), __fdividef(s0 * x.y + s1 * z.y, sd),
+                 __fdividef(s0 * x.z + s1 * z.z, sd)};
+#else
+    const float s0 = sinf((1.f - a) * ang), s1 = sinf(a * ang), sd = sinf(ang);
+    return quat4{(s0 * x.w + s1 * z.w) / sd, (s0 * x.x + s1 * z.x) / sd, (s0 * x.y + s1 * z.y) / sd,
+                 (s0 * x.z + s1 * z.z) / sd};
+#endif
 }
 // rotation matrix of a quaternion (glm::mat3_cast), rows R[0..2]
 __host__ __device__ __forceinline__ void quat_to_mat3(const quat4 q, float R[9]) {

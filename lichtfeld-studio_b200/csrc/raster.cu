@@ -1199,6 +1199,12 @@ __global__ void __launch_bounds__(kBwdWarps * 32)
     float2 G0 = make_float2(0.f, 0.f), G1 = G0, G2 = G0, G3 = G0, G4 = G0, G5 = G0, GC = G0; // (dN', dD) and (r, g)
     float acb = 0.f, aop = 0.f;
     float T = 0.f, u = 0.f;
+    {   // lanes ahead of / behind the pixel list read ring slots no stage() has written yet: they run with zero weights,
+        // but 0 * NaN is NaN, so the slots must hold finite numbers (shared memory is not cleared between kernels)
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        ringA[warp][lane] = ringA[warp][lane + 32] = z4;
+        ringB[warp][lane] = ringB[warp][lane + 32] = z4;
+    }
 
     const float4* ck = rb.ckpt + (size_t)b * kTilePix;
     int m = 0;

@@ -407,6 +407,13 @@ __global__ void __launch_bounds__(kGBwdWarps * 32)
     float vM[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, vMmu[3] = {0.f, 0.f, 0.f};
     float acr = 0.f, acg = 0.f, acb = 0.f, aop = 0.f;
     float T = 0.f, u = 0.f;
+    {   // lanes ahead of / behind the pixel list read ring slots no stage() has written yet: they run with zero weights,
+        // but 0 * NaN is NaN, so the slots must hold finite numbers (shared memory is not cleared between kernels)
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        ringA[warp][lane] = ringA[warp][lane + 32] = z4;
+        ringB[warp][lane] = ringB[warp][lane + 32] = z4;
+        ringC[warp][lane] = ringC[warp][lane + 32] = z4;
+    }
 
     const float4* ck = rb.ckpt + (size_t)b * kTilePix;
     const RayRec* rays_cam = rays + (size_t)cam * width * height;

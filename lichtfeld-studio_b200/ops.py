@@ -249,6 +249,128 @@ def rasterize_to_pixels_from_world_3dgs_bwd(means, quats, scales, colors, opacit
     return v_means, v_quats, v_scales, v_colors, v_opacities
 
 
+# ---- legacy 2-D op surface the reference's gtest files call ------------------------------
+@_on_tensor_device
+def quat_scale_to_covar_preci_fwd(quats, scales, compute_covar: bool = True, compute_preci: bool = True,
+                                  triu: bool = False):
+    """gsplat::quat_scale_to_covar_preci_fwd as tests/test_basic.cpp:54-67 calls it -> (covars, precis); an output that was
+    not requested is an empty tensor."""
+    lib = load()
+    _chk(quats, "quats"), _chk(scales, "scales")
+    N, dev = quats.shape[0], quats.device
+    shape = (N, 6) if triu else (N, 3, 3)
+    mk = lambda want: torch.empty(shape if want else (0,), dtype=torch.float32, device=dev)  # noqa: E731
+    covars, precis = mk(compute_covar), mk(compute_preci)
+    if compute_covar or compute_preci:
+        check(lib.lfs_quat_scale_to_covar_preci_fwd(_p(quats), _p(scales), N, int(triu),
+                                                    _p(covars) if compute_covar else None,
+                                                    _p(precis) if compute_preci else None, _stream()))
+    return covars, precis
+
+
+@_on_tensor_device
+def quat_scale_to_covar_preci_bwd(quats, scales, triu: bool, v_covars=None, v_precis=None):
+    """gsplat::quat_scale_to_covar_preci_bwd (tests/test_basic.cpp:80-81) -> (v_quats, v_scales)."""
+    lib = load()
+    _chk(quats, "quats"), _chk(scales, "scales")
+    vc = v_covars if (v_covars is not None and v_covars.numel()) else None
+    vp = v_precis if (v_precis is not None and v_precis.numel()) else None
+    for t, nme in ((vc, "v_covars"), (vp, "v_precis")):
+        if t is not None:
+            _chk(t, nme)
+    v_quats, v_scales = torch.zeros_like(quats), torch.zeros_like(scales)
+    if vc is not None or vp is not None:
+        check(lib.lfs_quat_scale_to_covar_preci_bwd(_p(quats), _p(scales), quats.shape[0], int(triu), _p(vc), _p(vp),
+                                                    _p(v_quats), _p(v_scales), _stream()))
+    return v_quats, v_scales
+
+
+@_on_tensor_device
+def projection_ewa_3dgs_fused_fwd(means, covars, quats, scales, opacities, viewmats, Ks, image_width: int,
+                                  image_height: int, eps2d: float, near_plane: float, far_plane: float,
+                                  radius_clip: float, calc_compensations: bool, camera_model=PINHOLE):
+    """gsplat::projection_ewa_3dgs_fused_fwd (tests/test_basic.cpp:114-128)
+    -> (radii [C,N,2], means2d, depths, conics, compensations or empty).  An empty `covars` selects quats + scales."""
+    lib = load()
+    _chk(means, "means"), _chk(viewmats, "viewmats"), _chk(Ks, "Ks")
+    cov = covars if (covars is not None and covars.numel()) else None
+    if cov is not None:
+        _chk(cov, "covars")
+    else:
+        _chk(quats, "quats"), _chk(scales, "scales")
+    op = opacities if (opacities is not None and opacities.numel()) else None
+    if op is not None:
+        _chk(op, "opacities")
+    N, Cc, dev = means.shape[0], viewmats.shape[0], means.device
+    radii = torch.empty((Cc, N, 2), dtype=torch.int32, device=dev)
+    means2d = torch.zeros((Cc, N, 2), dtype=torch.float32, device=dev)
+    depths = torch.zeros((Cc, N), dtype=torch.float32, device=dev)
+    conics = torch.zeros((Cc, N, 3), dtype=torch.float32, device=dev)
+    comp = torch.zeros((Cc, N), dtype=torch.float32, device=dev) if calc_compensations else torch.empty(0, device=dev)
+    check(lib.lfs_projection_ewa_3dgs_fused_fwd(
+        _p(means), _p(cov), _p(quats) if cov is None else None, _p(scales) if cov is None else None, _p(op), _p(viewmats),
+        _p(Ks), N, Cc, image_width, image_height, eps2d, near_plane, far_plane, radius_clip, camera_model, _p(radii),
+        _p(means2d), _p(depths), _p(conics), _p(comp) if calc_compensations else None, _stream()))
+    return radii, means2d, depths, conics, comp
+
+
+def _masks_u8(masks):
+    if masks is None or masks.numel() == 0:
+        return None
+    _chk(masks, "masks", torch.bool)
+    return masks.view(torch.uint8)
+
+
+@_on_tensor_device
+def rasterize_to_pixels_3dgs_fwd(means2d, conics, colors, opacities, backgrounds, masks, image_width: int,
+                                 image_height: int, tile_size: int, tile_offsets, flatten_ids):
+    """gsplat::rasterize_to_pixels_3dgs_fwd (tests/test_basic.cpp:347-358) -> (renders, alphas, last_ids)."""
+    lib = load()
+    for t, nme in ((means2d, "means2d"), (conics, "conics"), (colors, "colors"), (opacities, "opacities")):
+        _chk(t, nme)
+    _chk(tile_offsets, "tile_offsets", torch.int32), _chk(flatten_ids, "flatten_ids", torch.int32)
+    bg = backgrounds if (backgrounds is not None and backgrounds.numel()) else None
+    if bg is not None:
+        _chk(bg, "backgrounds")
+    Cc, N, ch, dev = tile_offsets.shape[0], means2d.shape[-2], colors.shape[-1], means2d.device
+    renders = torch.empty((Cc, image_height, image_width, ch), dtype=torch.float32, device=dev)
+    alphas = torch.empty((Cc, image_height, image_width, 1), dtype=torch.float32, device=dev)
+    last_ids = torch.empty((Cc, image_height, image_width), dtype=torch.int32, device=dev)
+    check(lib.lfs_rasterize_to_pixels_3dgs_fwd(
+        _p(means2d), _p(conics), _p(colors), _p(opacities), _p(bg), _p(_masks_u8(masks)), Cc, N, ch, image_width,
+        image_height, tile_size, _p(tile_offsets), _p(flatten_ids), flatten_ids.numel(), _p(renders), _p(alphas),
+        _p(last_ids), _stream()))
+    return renders, alphas, last_ids
+
+
+@_on_tensor_device
+def rasterize_to_pixels_3dgs_bwd(means2d, conics, colors, opacities, backgrounds, masks, image_width: int,
+                                 image_height: int, tile_size: int, tile_offsets, flatten_ids, render_alphas, last_ids,
+                                 v_render_colors, v_render_alphas, absgrad: bool = False):
+    """gsplat::rasterize_to_pixels_3dgs_bwd (launcher gsplat/Rasterization.h:38-63)
+    -> (v_means2d_abs or empty, v_means2d, v_conics, v_colors, v_opacities)."""
+    lib = load()
+    for t, nme in ((means2d, "means2d"), (conics, "conics"), (colors, "colors"), (opacities, "opacities"),
+                   (render_alphas, "render_alphas"), (v_render_colors, "v_render_colors"),
+                   (v_render_alphas, "v_render_alphas")):
+        _chk(t, nme)
+    _chk(tile_offsets, "tile_offsets", torch.int32), _chk(flatten_ids, "flatten_ids", torch.int32)
+    _chk(last_ids, "last_ids", torch.int32)
+    bg = backgrounds if (backgrounds is not None and backgrounds.numel()) else None
+    if bg is not None:
+        _chk(bg, "backgrounds")
+    Cc, N, ch, dev = tile_offsets.shape[0], means2d.shape[-2], colors.shape[-1], means2d.device
+    v_abs = torch.empty_like(means2d) if absgrad else torch.empty(0, device=dev)
+    v_means2d, v_conics = torch.empty_like(means2d), torch.empty_like(conics)
+    v_colors, v_opacities = torch.empty_like(colors), torch.empty_like(opacities)
+    check(lib.lfs_rasterize_to_pixels_3dgs_bwd(
+        _p(means2d), _p(conics), _p(colors), _p(opacities), _p(bg), _p(_masks_u8(masks)), Cc, N, ch, image_width,
+        image_height, tile_size, _p(tile_offsets), _p(flatten_ids), flatten_ids.numel(), _p(render_alphas), _p(last_ids),
+        _p(v_render_colors), _p(v_render_alphas), _p(v_abs) if absgrad else None, _p(v_means2d), _p(v_conics),
+        _p(v_colors), _p(v_opacities), _stream()))
+    return v_abs, v_means2d, v_conics, v_colors, v_opacities
+
+
 @_on_tensor_device
 def adam_step(param, exp_avg, exp_avg_sq, param_grad, lr, beta1, beta2, eps, bias_correction1_rcp,
               bias_correction2_sqrt_rcp):

@@ -31,6 +31,9 @@
 #include "fused_adam.hpp"
 #include "kernels/fused_ssim.cuh"
 #include "rasterization_api.h"
+#ifdef LFS_B200_LEGACY_OPS
+#include "gsplat_legacy_ops.h" // lichtfeld-studio_b200/host: the legacy 2-D ops exist on this project's backend only
+#endif
 
 #include <ATen/cuda/CUDAContext.h>
 #include <torch/extension.h>
@@ -293,6 +296,21 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         return gsplat::intersect_tile(means2d, radii, depths, {}, {}, C, tile_size, tw, th, sort);
     });
     m.def("intersect_offset", &gsplat::intersect_offset);
+#ifdef LFS_B200_LEGACY_OPS
+    // legacy 2-D op surface of the reference's gtests: host layer -> C ABI -> csrc/legacy2d.cu
+    m.def("quat_scale_to_covar_preci_fwd", &gsplat::quat_scale_to_covar_preci_fwd);
+    m.def("quat_scale_to_covar_preci_bwd", &gsplat::quat_scale_to_covar_preci_bwd);
+    m.def("projection_ewa_3dgs_fused_fwd",
+          [](Tensor means, std::optional<Tensor> covars, std::optional<Tensor> quats, std::optional<Tensor> scales,
+             std::optional<Tensor> opacities, Tensor viewmats, Tensor Ks, int w, int h, double eps2d, double near_p,
+             double far_p, double clip, bool comp) {
+              return gsplat::projection_ewa_3dgs_fused_fwd(means, covars, quats, scales, opacities, viewmats, Ks, (uint32_t)w,
+                                                           (uint32_t)h, (float)eps2d, (float)near_p, (float)far_p, (float)clip,
+                                                           comp, gsplat::CameraModelType::PINHOLE);
+          });
+    m.def("rasterize_to_pixels_3dgs_fwd", &gsplat::rasterize_to_pixels_3dgs_fwd);
+    m.def("rasterize_to_pixels_3dgs_bwd", &gsplat::rasterize_to_pixels_3dgs_bwd);
+#endif
     py::class_<GutHarness>(m, "GutHarness")
         .def(py::init<Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, std::vector<double>>())
         // the autograd engine must not be entered with the GIL held

@@ -152,6 +152,84 @@ def raster_world_bwd(means, quats, scales, colors, opacities, backgrounds, tile_
     return v_means, v_quats, v_scales, v_colors, v_opac
 
 
+# ---- legacy 2-D op surface (oracle/lfs_oracle_legacy2d_impl.h) ---------------------------------
+def quat_scale_to_covar_preci_fwd(quats, scales, compute_covar=True, compute_preci=True, triu=False, prec=64):
+    dt, pfx, _ = _dt(prec)
+    quats, scales = _a(quats, dt), _a(scales, dt)
+    N = quats.shape[0]
+    shape = (N, 6) if triu else (N, 3, 3)
+    cov = np.zeros(shape, dt) if compute_covar else None
+    pre = np.zeros(shape, dt) if compute_preci else None
+    getattr(lib(), pfx + "quat_scale_to_covar_preci_fwd")(C.c_int(N), _p(quats), _p(scales), C.c_int(int(triu)), _p(cov),
+                                                          _p(pre))
+    return cov, pre
+
+
+def quat_scale_to_covar_preci_bwd(quats, scales, triu, v_covars, v_precis, prec=64):
+    dt, pfx, _ = _dt(prec)
+    quats, scales, v_covars, v_precis = _a(quats, dt), _a(scales, dt), _a(v_covars, dt), _a(v_precis, dt)
+    N = quats.shape[0]
+    v_quats, v_scales = np.zeros((N, 4), dt), np.zeros((N, 3), dt)
+    getattr(lib(), pfx + "quat_scale_to_covar_preci_bwd")(C.c_int(N), _p(quats), _p(scales), C.c_int(int(triu)),
+                                                          _p(v_covars), _p(v_precis), _p(v_quats), _p(v_scales))
+    return v_quats, v_scales
+
+
+def projection_ewa(means, covars, quats, scales, opacities, viewmats, Ks, width, height, eps2d=0.3, near=0.01, far=1e4,
+                   radius_clip=0.0, calc_compensations=False, prec=64):
+    dt, pfx, cf = _dt(prec)
+    means, covars, quats, scales = _a(means, dt), _a(covars, dt), _a(quats, dt), _a(scales, dt)
+    opacities, viewmats, Ks = _a(opacities, dt), _a(viewmats, dt), _a(Ks, dt)
+    N, Cc = means.shape[0], Ks.shape[0]
+    radii = np.zeros((Cc, N, 2), np.int32)
+    means2d, depths, conics = np.zeros((Cc, N, 2), dt), np.zeros((Cc, N), dt), np.zeros((Cc, N, 3), dt)
+    comp = np.zeros((Cc, N), dt) if calc_compensations else None
+    getattr(lib(), pfx + "projection_ewa")(
+        C.c_int(Cc), C.c_int(N), _p(means), _p(covars), _p(quats), _p(scales), _p(opacities), _p(viewmats), _p(Ks),
+        C.c_int(width), C.c_int(height), cf(eps2d), cf(near), cf(far), cf(radius_clip), _p(radii), _p(means2d), _p(depths),
+        _p(conics), _p(comp))
+    return radii, means2d, depths, conics, comp
+
+
+def raster_2d_fwd(means2d, conics, colors, opacities, backgrounds, tile_masks, width, height, tile_size, tile_offsets,
+                  flatten_ids, prec=64):
+    dt, pfx, _ = _dt(prec)
+    means2d, conics, colors, opacities = _a(means2d, dt), _a(conics, dt), _a(colors, dt), _a(opacities, dt)
+    backgrounds = _a(backgrounds, dt)
+    tile_masks = None if tile_masks is None else _a(tile_masks, np.uint8)
+    tile_offsets, flatten_ids = _a(tile_offsets, np.int32), _a(flatten_ids, np.int32)
+    Cc, N, CH = means2d.shape[0], means2d.shape[1], colors.shape[-1]
+    renders = np.zeros((Cc, height, width, CH), dt)
+    alphas = np.zeros((Cc, height, width, 1), dt)
+    last_ids = np.zeros((Cc, height, width), np.int32)
+    getattr(lib(), pfx + "raster_2d_fwd")(
+        C.c_int(Cc), C.c_int(N), C.c_int(CH), _p(means2d), _p(conics), _p(colors), _p(opacities), _p(backgrounds),
+        _p(tile_masks), C.c_int(width), C.c_int(height), C.c_int(tile_size), _p(tile_offsets), _p(flatten_ids),
+        C.c_int64(flatten_ids.shape[0]), _p(renders), _p(alphas), _p(last_ids))
+    return renders, alphas, last_ids
+
+
+def raster_2d_bwd(means2d, conics, colors, opacities, backgrounds, tile_masks, width, height, tile_size, tile_offsets,
+                  flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas, absgrad=False, prec=64):
+    dt, pfx, _ = _dt(prec)
+    means2d, conics, colors, opacities = _a(means2d, dt), _a(conics, dt), _a(colors, dt), _a(opacities, dt)
+    backgrounds = _a(backgrounds, dt)
+    tile_masks = None if tile_masks is None else _a(tile_masks, np.uint8)
+    tile_offsets, flatten_ids = _a(tile_offsets, np.int32), _a(flatten_ids, np.int32)
+    render_alphas, last_ids = _a(render_alphas, dt), _a(last_ids, np.int32)
+    v_render_colors, v_render_alphas = _a(v_render_colors, dt), _a(v_render_alphas, dt)
+    Cc, N, CH = means2d.shape[0], means2d.shape[1], colors.shape[-1]
+    v_m = np.zeros((Cc, N, 2), np.float64)
+    v_abs = np.zeros((Cc, N, 2), np.float64) if absgrad else None
+    v_con, v_col, v_op = np.zeros((Cc, N, 3), np.float64), np.zeros((Cc, N, CH), np.float64), np.zeros((Cc, N), np.float64)
+    getattr(lib(), pfx + "raster_2d_bwd")(
+        C.c_int(Cc), C.c_int(N), C.c_int(CH), _p(means2d), _p(conics), _p(colors), _p(opacities), _p(backgrounds),
+        _p(tile_masks), C.c_int(width), C.c_int(height), C.c_int(tile_size), _p(tile_offsets), _p(flatten_ids),
+        _p(render_alphas), _p(last_ids), _p(v_render_colors), _p(v_render_alphas), _p(v_m), _p(v_abs), _p(v_con), _p(v_col),
+        _p(v_op))
+    return v_m, v_abs, v_con, v_col, v_op
+
+
 def adam_step(param, exp_avg, exp_avg_sq, grad, lr, beta1, beta2, eps, bc1_rcp, bc2_sqrt_rcp, prec=64):
     """Returns updated copies (param, exp_avg, exp_avg_sq)."""
     dt, pfx, cf = _dt(prec)

@@ -251,10 +251,14 @@ def fastgs_torch_module(which="ref"):
     layer ('b200')."""
     import glob
     import importlib.util
+    import sys
     name = {"ref": "ref_fastgs_torch", "b200": "b200_fastgs_torch"}[which]
+    if name in sys.modules:  # a pybind11 module registers its types once per process
+        return sys.modules[name]
     hits = glob.glob(os.path.join(_REF, name + "*.so"))
     assert hits, f"oracle/_ref/{name}*.so missing"
     spec = importlib.util.spec_from_file_location(name, hits[0])
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
+    sys.modules[name] = mod
     return mod

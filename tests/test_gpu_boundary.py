@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 import gpu_diag as D  # noqa: E402
 import ref_libs as R  # noqa: E402
 from lichtfeld_studio_b200 import scene  # noqa: E402
-from test_gpu_baseline_configs import gate, strict  # noqa: E402
+from test_gpu_baseline_configs import gate, gate_render, strict  # noqa: E402
 
 T = D.T
 LRS = [0.00016, 0.0025, 0.0025 / 20, 0.005, 0.001, 0.05]
@@ -62,8 +62,8 @@ def test_fastgs_callers_on_both_backends(mods):
     nb = (sc.sh_degree + 1) ** 2
     a = hr.view_grads(c["w2c"], c["campos"], c["k"], c["gt"], bg, 0.2, nb, sc.width, sc.height)
     b = hb.view_grads(c["w2c"], c["campos"], c["k"], c["gt"], bg, 0.2, nb, sc.width, sc.height)
-    gate(rep, "image", b[0], a[0], 1e-4, 0.999)
-    gate(rep, "alpha", b[1], a[1], 1e-4, 0.999)
+    gate_render(rep, "image", b[0], a[0])
+    gate_render(rep, "alpha", b[1], a[1])
     assert abs(float(a[2]) - float(b[2])) <= 1e-5 * abs(float(a[2])), (float(a[2]), float(b[2]))
     for name, x, y in zip(GRADS, b[3:], a[3:]):
         gate(rep, "grad_" + name, x, y, 1e-3, 0.99)
@@ -104,8 +104,8 @@ def test_gut_callers_on_both_backends(mods):
     assert hr.last_n_isects > 50_000 and abs(hr.last_n_isects - hb.last_n_isects) <= 2 + hr.last_n_isects // 2000
     # whole pipeline on each side's own projection: a radius that rounds the other way adds / removes a tile instance
     # (+-1 px is the reference's own tolerance), hence 5e-4 here; the per-stage gates on identical inputs are 1e-4
-    gate(rep, "image", b[0], a[0], 5e-4, 0.999)
-    gate(rep, "alpha", b[1], a[1], 5e-4, 0.999)
+    gate_render(rep, "image", b[0], a[0], 5e-4)
+    gate_render(rep, "alpha", b[1], a[1], 5e-4)
     assert abs(float(a[3]) - float(b[3])) <= 1e-4 * abs(float(a[3]))
     for name, x, y in zip(GRADS, b[4:], a[4:]):
         gate(rep, "grad_" + name, x, y, 2e-3, 0.98)
@@ -258,8 +258,8 @@ def test_rasterize_camera_models_on_both_backends(mods, case):
     a_ = ref.raster_fwd(*fargs)
     b_ = b200.raster_fwd(*fargs)
     rep = {}
-    gate(rep, "render_rgb", b_[0], a_[0], 1e-4, 0.999)
-    gate(rep, "render_alpha", b_[1], a_[1], 1e-4, 0.999)
+    gate_render(rep, "render_rgb", b_[0], a_[0])
+    gate_render(rep, "render_alpha", b_[1], a_[1])
     assert float((a_[2] != b_[2]).float().mean()) <= 2e-3
     vC = torch.randn(a_[0].shape, device="cuda", generator=g)
     vA = torch.randn(a_[1].shape, device="cuda", generator=g)
@@ -289,8 +289,8 @@ def test_rasterize_four_channels_on_both_backends(mods):
         fargs = (tm, tq, ts, colors, to[None].contiguous(), bg, w, h, vm0, None, tK, 0, 4, None, None, None, offs, flat)
         a_, b_ = ref.raster_fwd(*fargs), b200.raster_fwd(*fargs)
         rep = {}
-        gate(rep, "render", b_[0], a_[0], 1e-4, 0.999)
-        gate(rep, "alpha", b_[1], a_[1], 1e-4, 0.999)
+        gate_render(rep, "render", b_[0], a_[0])
+        gate_render(rep, "alpha", b_[1], a_[1])
         vC = torch.randn(a_[0].shape, device="cuda", generator=g)
         vA = torch.randn(a_[1].shape, device="cuda", generator=g)
         ga = ref.raster_bwd(*fargs, a_[1], a_[2], vC, vA)
