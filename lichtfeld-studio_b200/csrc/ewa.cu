@@ -466,6 +466,7 @@ static FgInst carve_inst(void* blob, uint32_t n_inst) {
 }
 struct FgBucket {
     uint32_t* bucket_tile;
+    uint32_t* live;
     float4* ckpt;
     size_t bytes;
 };
@@ -474,6 +475,7 @@ static FgBucket carve_bucket(void* blob, uint32_t n_buckets) {
     FgBucket b;
     const uint32_t n = n_buckets ? n_buckets : 1;
     b.bucket_tile = c.take<uint32_t>(n);
+    b.live = c.take<uint32_t>(live_list_words(n));
     b.ckpt = c.take<float4>((size_t)n * kTilePix);
     b.bytes = c.total();
     return b;
@@ -584,6 +586,7 @@ extern "C" int lfs_fastgs_forward(const float* means, const float* scales_raw, c
     }
     const FgBucket B = carve_bucket(bucket_blob, h_nb);
     rb.bucket_tile = B.bucket_tile;
+    rb.live = B.live;
     rb.ckpt = B.ckpt;
     rc = launch_blend_fwd_ewa(rb, (uint32_t)width, (uint32_t)height, tile_w, tile_h, true, stream);
     if (rc)
@@ -645,6 +648,7 @@ extern "C" int lfs_fastgs_backward(const float* grad_image, const float* grad_al
     rb.inst_gid = reinterpret_cast<const int32_t*>(instance_selector ? I.tv_b : I.tv_a);
     rb.bucket_off = T.bucket_off;
     rb.bucket_tile = B.bucket_tile;
+    rb.live = B.live;
     rb.ckpt = B.ckpt;
     rb.tile_max_contrib = T.tile_max;
     rb.pix_state = T.pix_state;

@@ -158,6 +158,24 @@ __device__ __forceinline__ void store_rec_pk(float4* d, const float4 A, const fl
 // Register-staged variant (round 1's kernel, kept for A/B measurements: lfs_set_option("fwd_variant", 1)): the GaussRec of
 // the next batch is gathered with LDG.128 into registers one batch ahead.  EWA: fastgs-surface records (2-D conic, D == 1);
 // PK: FFMA2 evaluation of (N', D) (not EWA).
+// Forward epilogue: the buckets of this tile that some pixel reaches (n_contrib > 32 * bucket) go onto the live list of the
+// backward.  s_base: one shared word the caller no longer needs.
+__device__ __forceinline__ void append_live_buckets(const RasterBuffers& rb, const bool write_ckpt, const uint32_t boff,
+                                                    const uint32_t cnt_raw, const uint32_t tile_max, const uint32_t tid,
+                                                    const uint32_t n_threads, uint32_t* s_base) {
+    if (!write_ckpt || rb.live == nullptr)
+        return;
+    const uint32_t nb = (cnt_raw + kBucket - 1) / kBucket;
+    const uint32_t n_live = min(nb, (tile_max + kBucket - 1) / kBucket);
+    __syncthreads();
+    if (tid == 0)
+        *s_base = n_live ? atomicAdd(rb.live, n_live) : 0u;
+    __syncthreads();
+    const uint32_t base = *s_base;
+    for (uint32_t k = tid; k < n_live; k += n_threads)
+        rb.live[2 + base + k] = boff + k;
+}
+
 template <bool EWA, bool PK = false>
 __global__ void __launch_bounds__(kFwdThreads)
     k_blend_fwd(const RasterBuffers rb, const ViewCam* __restrict__ cams, const uint32_t width, const uint32_t height, const uint32_t tile_w,
@@ -446,8 +464,10 @@ __global__ void __launch_bounds__(kFwdThreads)
     if (lane == 0)
         s_warp_tot[warp] = m;
     __syncthreads();
+    const uint32_t tile_max = max(s_warp_tot[0], s_warp_tot[1]);
     if (tid == 0)
-        rb.tile_max_contrib[ft] = max(s_warp_tot[0], s_warp_tot[1]);
+        rb.tile_max_contrib[ft] = tile_max;
+    append_live_buckets(rb, write_ckpt, boff, (uint32_t)cnt_raw, tile_max, tid, kFwdThreads, &s_nact[0]);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -741,8 +761,10 @@ __global__ void __launch_bounds__(kFwdThreads)
     if (lane == 0)
         s_warp_tot[warp] = m;
     __syncthreads();
+    const uint32_t tile_max = max(s_warp_tot[0], s_warp_tot[1]);
     if (tid == 0)
-        rb.tile_max_contrib[ft] = max(s_warp_tot[0], s_warp_tot[1]);
+        rb.tile_max_contrib[ft] = tile_max;
+    append_live_buckets(rb, write_ckpt, boff, (uint32_t)cnt_raw, tile_max, tid, kFwdThreads, &s_nact[0]);
 }
 
 int launch_blend_fwd(const RasterBuffers& rb, const ViewCam* cams_dev, uint32_t C, uint32_t width, uint32_t height,
@@ -750,6 +772,8 @@ int launch_blend_fwd(const RasterBuffers& rb, const ViewCam* cams_dev, uint32_t 
                      float* renders, float* alphas, int32_t* last_ids, cudaStream_t stream) {
     if (C == 0 || tile_w == 0 || tile_h == 0)
         return LFS_OK;
+    if (rb.live && write_ckpt) // live-bucket count and the backward's work counter
+        LFS_CUDA_OK(cudaMemsetAsync(rb.live, 0, 2 * sizeof(uint32_t), stream));
     dim3 grid(tile_w * tile_h, C);
     if (raster_options().fwd_variant == 1)
         k_blend_fwd<false, true><<<grid, kFwdThreads, 0, stream>>>(rb, cams_dev, width, height, tile_w, tile_h, write_ckpt,
@@ -765,6 +789,8 @@ int launch_blend_fwd_ewa(const RasterBuffers& rb, uint32_t width, uint32_t heigh
                          bool write_ckpt, cudaStream_t stream) {
     if (tile_w == 0 || tile_h == 0)
         return LFS_OK;
+    if (rb.live && write_ckpt)
+        LFS_CUDA_OK(cudaMemsetAsync(rb.live, 0, 2 * sizeof(uint32_t), stream));
     if (raster_options().fwd_variant == 1)
         k_blend_fwd<true><<<dim3(tile_w * tile_h, 1), kFwdThreads, 0, stream>>>(
             rb, nullptr, width, height, tile_w, tile_h, write_ckpt, nullptr, nullptr, nullptr, nullptr, nullptr);
@@ -1148,23 +1174,17 @@ struct BwdEval { // everything the chain / gradient half of a step needs, produc
     bool pass;                // the forward evaluated this pair and alpha >= 1/255
 };
 
-template <bool EWA, int kBwdWarps>
-__global__ void __launch_bounds__(kBwdWarps * 32)
-    k_blend_bwd_sp(const RasterBuffers rb, const ViewCam* __restrict__ cams, const float4* __restrict__ v_pix,
-                   const float* __restrict__ quats, const float* __restrict__ scales, const float* __restrict__ means,
-                   const uint32_t N, const uint32_t width, const uint32_t height, const uint32_t tile_w,
-                   const uint32_t tile_h, const uint32_t n_bucket_cap, const uint32_t* __restrict__ n_buckets_dev,
-                   float* __restrict__ v_means, float* __restrict__ v_quats, float* __restrict__ v_scales,
-                   float* __restrict__ v_colors, float* __restrict__ v_opacities) {
-    __shared__ float4 ringA[kBwdWarps][64]; // (v_r, v_g, v_b, dx)
-    __shared__ float4 ringB[kBwdWarps][64]; // (dy, bits(n_rel), T0, u0)
-    __shared__ uint8_t s_pix[kBwdWarps][kTilePix];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t b = blockIdx.x * kBwdWarps + warp;
-    uint32_t nbk = *n_buckets_dev;
-    nbk = nbk < n_bucket_cap ? nbk : n_bucket_cap;
-    if (b >= nbk)
-        return;
+// one bucket, one warp; ringA / ringB / s_pix are this warp's shared-memory slices
+template <bool EWA>
+__device__ __forceinline__ void bwd_sp_bucket(const uint32_t b, const int lane, float4* __restrict__ ringA_w,
+                                              float4* __restrict__ ringB_w, uint8_t* __restrict__ s_pix_w,
+                                              const RasterBuffers& rb, const ViewCam* __restrict__ cams,
+                                              const float4* __restrict__ v_pix, const float* __restrict__ quats,
+                                              const float* __restrict__ scales, const float* __restrict__ means,
+                                              const uint32_t N, const uint32_t width, const uint32_t height,
+                                              const uint32_t tile_w, const uint32_t tile_h, float* __restrict__ v_means,
+                                              float* __restrict__ v_quats, float* __restrict__ v_scales,
+                                              float* __restrict__ v_colors, float* __restrict__ v_opacities) {
     const uint32_t n_tiles = tile_w * tile_h;
     const uint32_t ft = rb.bucket_tile[b];
     const uint32_t cam = ft / n_tiles, tile = ft - cam * n_tiles;
@@ -1202,8 +1222,8 @@ __global__ void __launch_bounds__(kBwdWarps * 32)
     {   // lanes ahead of / behind the pixel list read ring slots no stage() has written yet: they run with zero weights,
         // but 0 * NaN is NaN, so the slots must hold finite numbers (shared memory is not cleared between kernels)
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        ringA[warp][lane] = ringA[warp][lane + 32] = z4;
-        ringB[warp][lane] = ringB[warp][lane + 32] = z4;
+        ringA_w[lane] = ringA_w[lane + 32] = z4;
+        ringB_w[lane] = ringB_w[lane + 32] = z4;
     }
 
     const float4* ck = rb.ckpt + (size_t)b * kTilePix;
@@ -1219,7 +1239,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32)
                 kp = (uint32_t)__ldg(rb.n_contrib + ((size_t)cam * height + py) * width + px) > local_b * kBucket;
             const uint32_t mask = __ballot_sync(0xffffffffu, kp);
             if (kp)
-                s_pix[warp][m + __popc(mask & lt)] = (uint8_t)p;
+                s_pix_w[m + __popc(mask & lt)] = (uint8_t)p;
             m += __popc(mask);
         }
         __syncwarp();
@@ -1229,7 +1249,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32)
         __syncwarp(); // every lane is done reading the entries that are about to be replaced
         float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a4;
         if (i0 + lane < m) {
-            const int p = s_pix[warp][i0 + lane];
+            const int p = s_pix_w[i0 + lane];
             const uint32_t px = tx * kTile + (p & 15), py = ty * kTile + (p >> 4);
             const size_t pix = ((size_t)cam * height + py) * width + px;
             const int32_t nrel = __ldg(rb.n_contrib + pix) - (int32_t)(local_b * kBucket);
@@ -1240,14 +1260,14 @@ __global__ void __launch_bounds__(kBwdWarps * 32)
             a4 = make_float4(v4.x, v4.y, v4.z, (float)(p & 15) - 7.5f);
             b4 = make_float4((float)(p >> 4) - 7.5f, __int_as_float(nrel), c4.w, u0);
         }
-        ringA[warp][(i0 + lane) & 63] = a4;
-        ringB[warp][(i0 + lane) & 63] = b4;
+        ringA_w[(i0 + lane) & 63] = a4;
+        ringB_w[(i0 + lane) & 63] = b4;
         __syncwarp();
     };
     // the alpha half of step i for this lane (list position i - lane)
     auto eval = [&](const int i, BwdEval& e) {
         const int idx = i - lane;
-        const float4 ea = ringA[warp][idx & 63], eb = ringB[warp][idx & 63];
+        const float4 ea = ringA_w[idx & 63], eb = ringB_w[idx & 63];
         e.vr = ea.x, e.vg = ea.y, e.vb = ea.z, e.dx = ea.w, e.dy = eb.x, e.T0 = eb.z, e.u0 = eb.w;
         const bool act = valid && (uint32_t)idx < (uint32_t)m && lane < __float_as_int(eb.y);
         const float2 ND = poly2x2(make_float2(e.dx, e.dx), make_float2(e.dy, e.dy), P0, P1, P2, P3, P4, P5);
@@ -1348,6 +1368,58 @@ __global__ void __launch_bounds__(kBwdWarps * 32)
                    quats, scales, means, v_means, v_quats, v_scales, v_colors, v_opacities);
 }
 
+
+// Driver.  With a live-bucket list (rb.live: written by the forward, [0] = count, [1] = work counter, [2..] = bucket
+// ids) the grid is persistent -- kBwdBlocksPerSM CTAs per SM, every warp pulls the next live bucket with one atomic --
+// so that the ~86 % of the buckets no pixel reaches (C3: 32 k live of 232 k) cost nothing: with one warp per bucket they
+// still cost a CTA slot and three dependent loads each, and a CTA with one live and three dead buckets held the registers
+// of four warps (measured: 13.5 of the 20 possible warps per SM active).  Without the list: one warp per bucket.
+constexpr int kBwdBlocksPerSM = 5; // 94 registers x 128 threads
+template <bool EWA, int kBwdWarps>
+__global__ void __launch_bounds__(kBwdWarps * 32)
+    k_blend_bwd_sp(const RasterBuffers rb, const ViewCam* __restrict__ cams, const float4* __restrict__ v_pix,
+                   const float* __restrict__ quats, const float* __restrict__ scales, const float* __restrict__ means,
+                   const uint32_t N, const uint32_t width, const uint32_t height, const uint32_t tile_w,
+                   const uint32_t tile_h, const uint32_t n_bucket_cap, const uint32_t* __restrict__ n_buckets_dev,
+                   float* __restrict__ v_means, float* __restrict__ v_quats, float* __restrict__ v_scales,
+                   float* __restrict__ v_colors, float* __restrict__ v_opacities) {
+    __shared__ float4 ringA[kBwdWarps][64]; // (v_r, v_g, v_b, dx)
+    __shared__ float4 ringB[kBwdWarps][64]; // (dy, bits(n_rel), T0, u0)
+    __shared__ uint8_t s_pix[kBwdWarps][kTilePix];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t nbk = *n_buckets_dev;
+    nbk = nbk < n_bucket_cap ? nbk : n_bucket_cap;
+    if (rb.live == nullptr) {
+        const uint32_t b = blockIdx.x * kBwdWarps + warp;
+        if (b < nbk)
+            bwd_sp_bucket<EWA>(b, lane, ringA[warp], ringB[warp], s_pix[warp], rb, cams, v_pix, quats, scales, means, N,
+                               width, height, tile_w, tile_h, v_means, v_quats, v_scales, v_colors, v_opacities);
+        return;
+    }
+    const uint32_t n_live = min(rb.live[0], nbk);
+    for (;;) {
+        uint32_t w = 0;
+        if (lane == 0)
+            w = atomicAdd(rb.live + 1, 1u);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= n_live)
+            return;
+        const uint32_t b = rb.live[2 + w];
+        if (b < nbk)
+            bwd_sp_bucket<EWA>(b, lane, ringA[warp], ringB[warp], s_pix[warp], rb, cams, v_pix, quats, scales, means, N,
+                               width, height, tile_w, tile_h, v_means, v_quats, v_scales, v_colors, v_opacities);
+        __syncwarp();
+    }
+}
+
+static unsigned bwd_sp_grid(const RasterBuffers& rb, const uint32_t n_bucket_cap) {
+    const unsigned dense = div_up(n_bucket_cap, 4);
+    if (rb.live == nullptr || raster_options().bwd_variant == 1)
+        return dense;
+    const unsigned persistent = (unsigned)(num_sms() * kBwdBlocksPerSM);
+    return persistent < dense ? persistent : dense;
+}
+
 int launch_blend_bwd(const RasterBuffers& rb, const ViewCam* cams_dev, const float4* v_pix, const float* quats,
                      const float* scales, const float* means, uint32_t C, uint32_t N, uint32_t width, uint32_t height,
                      uint32_t tile_w, uint32_t tile_h, uint32_t n_bucket_cap, const uint32_t* n_buckets_dev,
@@ -1360,10 +1432,16 @@ int launch_blend_bwd(const RasterBuffers& rb, const ViewCam* cams_dev, const flo
         k_blend_bwd<4, false, true><<<div_up(n_bucket_cap, 4), 4 * 32, 0, stream>>>(
             rb, cams_dev, v_pix, quats, scales, means, N, width, height, tile_w, tile_h, n_bucket_cap, n_buckets_dev,
             v_means, v_quats, v_scales, v_colors, v_opacities);
-    else
-        k_blend_bwd_sp<false, 4><<<div_up(n_bucket_cap, 4), 4 * 32, 0, stream>>>(
-            rb, cams_dev, v_pix, quats, scales, means, N, width, height, tile_w, tile_h, n_bucket_cap, n_buckets_dev,
+    else {
+        RasterBuffers rbl = rb;
+        if (raster_options().bwd_variant == 2) // A/B: one warp per bucket, no live list
+            rbl.live = nullptr;
+        if (rbl.live) // work counter of the persistent grid (a forward may be followed by more than one backward)
+            LFS_CUDA_OK(cudaMemsetAsync(rbl.live + 1, 0, sizeof(uint32_t), stream));
+        k_blend_bwd_sp<false, 4><<<bwd_sp_grid(rbl, n_bucket_cap), 4 * 32, 0, stream>>>(
+            rbl, cams_dev, v_pix, quats, scales, means, N, width, height, tile_w, tile_h, n_bucket_cap, n_buckets_dev,
             v_means, v_quats, v_scales, v_colors, v_opacities);
+    }
     LFS_LAUNCH_OK("k_blend_bwd");
     return LFS_OK;
 }
@@ -1377,10 +1455,16 @@ int launch_blend_bwd_ewa(const RasterBuffers& rb, const float4* v_pix, uint32_t 
         k_blend_bwd<4, true><<<div_up(n_bucket_cap, 4), 4 * 32, 0, stream>>>(
             rb, nullptr, v_pix, nullptr, nullptr, nullptr, N, width, height, tile_w, tile_h, n_bucket_cap, n_buckets_dev,
             v_mean2d, v_conic, nullptr, v_color, v_raw_opacity);
-    else
-        k_blend_bwd_sp<true, 4><<<div_up(n_bucket_cap, 4), 4 * 32, 0, stream>>>(
-            rb, nullptr, v_pix, nullptr, nullptr, nullptr, N, width, height, tile_w, tile_h, n_bucket_cap, n_buckets_dev,
+    else {
+        RasterBuffers rbl = rb;
+        if (raster_options().bwd_variant == 2) // A/B: one warp per bucket, no live list
+            rbl.live = nullptr;
+        if (rbl.live) // work counter of the persistent grid (a forward may be followed by more than one backward)
+            LFS_CUDA_OK(cudaMemsetAsync(rbl.live + 1, 0, sizeof(uint32_t), stream));
+        k_blend_bwd_sp<true, 4><<<bwd_sp_grid(rbl, n_bucket_cap), 4 * 32, 0, stream>>>(
+            rbl, nullptr, v_pix, nullptr, nullptr, nullptr, N, width, height, tile_w, tile_h, n_bucket_cap, n_buckets_dev,
             v_mean2d, v_conic, nullptr, v_color, v_raw_opacity);
+    }
     LFS_LAUNCH_OK("k_blend_bwd<ewa>");
     return LFS_OK;
 }

@@ -48,6 +48,8 @@ struct RasterBuffers {
     uint32_t* bucket_tile;     // [n_bucket_cap]
     float4* ckpt;              // [n_bucket_cap * 256]
     uint32_t* tile_max_contrib; // [n_tiles_total]
+    uint32_t* live;            // [2 + n_bucket_cap] or null: [0] number of buckets some pixel reaches, [1] work counter of the
+                               // backward, [2..] their ids (appended by the forward, tile by tile)
     // per-pixel state
     float4* pix_state;         // [C*H*W] (rgb before background, T_final)
     int32_t* n_contrib;        // [C*H*W] tile-local index + 1 of the last contributor (0 = none)
@@ -62,6 +64,7 @@ struct RasterOptions {
     int exact_cull = 1; // trainer: drop (tile, Gaussian) instances that provably hold no alpha >= 1/255 (intersect.cuh CullRec)
 };
 RasterOptions& raster_options();
+static inline size_t live_list_words(uint32_t n_bucket_cap) { return 2 + (size_t)n_bucket_cap; }
 
 int launch_bucket_offsets(const RasterBuffers& rb, uint32_t n_tiles_total, uint32_t* n_buckets_dev, void* scan_scratch,
                           uint32_t* counts_tmp, cudaStream_t stream);

@@ -124,6 +124,7 @@ struct RasterScratch {
     uint32_t* counts_tmp;
     uint32_t* n_buckets;
     uint32_t* bucket_tile;
+    uint32_t* live;
     float4* ckpt;
     uint32_t* tile_max;
     float4* pix_state;
@@ -153,11 +154,13 @@ static RasterScratch carve_scratch(void* blob, uint32_t C, uint32_t N, uint32_t 
     const uint64_t n_bucket_cap = n_isects / kBucket + n_tiles_total + 1;
     if (bwd) {
         s.bucket_tile = c.take<uint32_t>(n_bucket_cap);
+        s.live = c.take<uint32_t>(live_list_words((uint32_t)n_bucket_cap));
         s.ckpt = c.take<float4>(n_bucket_cap * kTilePix);
         s.v_pix = c.take<float4>(n_pix);
         s.v_colors_group = channels != 3 ? c.take<float>(3 * (size_t)C * N) : nullptr;
     } else {
         s.bucket_tile = nullptr;
+        s.live = nullptr;
         s.ckpt = nullptr;
         s.v_pix = nullptr;
         s.v_colors_group = nullptr;
@@ -205,6 +208,7 @@ static int raster_front(const RasterScratch& s, RasterBuffers& rb, const float* 
     rb.inst_gid = flatten_ids;
     rb.bucket_off = s.bucket_off;
     rb.bucket_tile = s.bucket_tile;
+    rb.live = s.live;
     rb.ckpt = s.ckpt;
     rb.tile_max_contrib = s.tile_max;
     rb.pix_state = s.pix_state;

@@ -48,7 +48,7 @@ struct Trainer {
     uint32_t* n_inst; // [4] device counters: n_inst, n_buckets, high-water mark of n_inst since creation
     uint32_t *tk_a, *tk_b, *tv_a, *tv_b;
     int32_t* tile_off;
-    uint32_t *bucket_off, *bucket_counts, *bucket_tile, *tile_max;
+    uint32_t *bucket_off, *bucket_counts, *bucket_tile, *tile_max, *live;
     float4* ckpt;
     float4* pix_state;
     int32_t* n_contrib;
@@ -96,6 +96,7 @@ static size_t trainer_carve(Trainer& t, void* base) {
     t.bucket_off = c.take<uint32_t>(t.n_tiles + 1);
     t.bucket_counts = c.take<uint32_t>(t.n_tiles + 1);
     t.bucket_tile = c.take<uint32_t>(t.bucket_cap);
+    t.live = c.take<uint32_t>(live_list_words(t.bucket_cap));
     t.tile_max = c.take<uint32_t>(t.n_tiles);
     t.ckpt = c.take<float4>((size_t)t.bucket_cap * kTilePix);
     t.pix_state = c.take<float4>(npix);
@@ -975,6 +976,7 @@ extern "C" int lfs_trainer_view_forward(void* h, const float* params_arena, cons
     rb.bucket_tile = t->bucket_tile;
     rb.ckpt = t->ckpt;
     rb.tile_max_contrib = t->tile_max;
+    rb.live = t->live;
     rb.pix_state = t->pix_state;
     rb.n_contrib = t->n_contrib;
     t->mark(2, stream);
@@ -1071,6 +1073,7 @@ extern "C" int lfs_trainer_view_backward_blend(void* h, void* stream_) {
     rb.bucket_tile = t->bucket_tile;
     rb.ckpt = t->ckpt;
     rb.tile_max_contrib = t->tile_max;
+    rb.live = t->live;
     rb.pix_state = t->pix_state;
     rb.n_contrib = t->n_contrib;
     t->mark(5, stream);
