@@ -174,7 +174,7 @@ __device__ inline UTOut ut_project_general(const CamModel& cam, f3 mean, float4 
     o.ok = false;
     quat4 qc;
     f3 tc;
-    shutter_pose(cam, 0.5f, qc, tc);
+    shutter_pose<true>(cam, 0.5f, qc, tc); // one pose, the same input for every Gaussian: reproduces the reference's depth bits
     const f3 mean_c = quat_rotate(qc, mean) + tc;
     o.depth = mean_c.z;
     if (mean_c.z < near_plane || mean_c.z > far_plane)

@@ -49,10 +49,12 @@ std::tuple<at::Tensor, at::Tensor> quat_scale_to_covar_preci_bwd(const at::Tenso
     DEVICE_GUARD(quats);
     CHECK_INPUT(quats);
     CHECK_INPUT(scales);
-    if (present(v_covars))
+    if (present(v_covars)) { // CHECK_INPUT is two statements
         CHECK_INPUT(v_covars.value());
-    if (present(v_precis))
+    }
+    if (present(v_precis)) { // CHECK_INPUT is two statements
         CHECK_INPUT(v_precis.value());
+    }
     at::Tensor v_quats = at::zeros_like(quats), v_scales = at::zeros_like(scales);
     if (present(v_covars) || present(v_precis))
         lfs_ok(lfs_quat_scale_to_covar_preci_bwd(quats.data_ptr<float>(), scales.data_ptr<float>(), (uint32_t)quats.size(0),
@@ -80,8 +82,9 @@ projection_ewa_3dgs_fused_fwd(const at::Tensor means, const at::optional<at::Ten
         CHECK_INPUT(quats.value());
         CHECK_INPUT(scales.value());
     }
-    if (present(opacities))
+    if (present(opacities)) { // CHECK_INPUT is two statements
         CHECK_INPUT(opacities.value());
+    }
     const int64_t N = means.size(0), C = viewmats.size(0);
     auto opt = means.options();
     at::Tensor radii = at::empty({C, N, 2}, opt.dtype(at::kInt));
@@ -110,10 +113,12 @@ rasterize_to_pixels_3dgs_fwd(const at::Tensor means2d, const at::Tensor conics, 
     CHECK_INPUT(opacities);
     CHECK_INPUT(tile_offsets);
     CHECK_INPUT(flatten_ids);
-    if (present(backgrounds))
+    if (present(backgrounds)) { // CHECK_INPUT is two statements
         CHECK_INPUT(backgrounds.value());
-    if (present(masks))
+    }
+    if (present(masks)) { // CHECK_INPUT is two statements
         CHECK_INPUT(masks.value());
+    }
     const int64_t C = tile_offsets.size(0), N = means2d.size(-2), channels = colors.size(-1);
     auto opt = means2d.options();
     at::Tensor renders = at::empty({C, (int64_t)image_height, (int64_t)image_width, channels}, opt);
@@ -147,10 +152,12 @@ rasterize_to_pixels_3dgs_bwd(const at::Tensor means2d, const at::Tensor conics, 
     CHECK_INPUT(last_ids);
     CHECK_INPUT(v_render_colors);
     CHECK_INPUT(v_render_alphas);
-    if (present(backgrounds))
+    if (present(backgrounds)) { // CHECK_INPUT is two statements
         CHECK_INPUT(backgrounds.value());
-    if (present(masks))
+    }
+    if (present(masks)) { // CHECK_INPUT is two statements
         CHECK_INPUT(masks.value());
+    }
     const int64_t C = tile_offsets.size(0), N = means2d.size(-2), channels = colors.size(-1);
     at::Tensor v_means2d = at::empty_like(means2d), v_conics = at::empty_like(conics);
     at::Tensor v_colors = at::empty_like(colors), v_opacities = at::empty_like(opacities);
