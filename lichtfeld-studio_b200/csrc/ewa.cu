@@ -17,11 +17,9 @@ constexpr float kFgDilation = 0.3f;          // rasterization_config.h:16
 constexpr float kFgMinAlphaRcp = 255.0f;     // :17
 
 // kernel_utils.cuh:108-143 (mean already shifted by -0.5, :152): does the primitive reach alpha >= 1/255 in the tile?
-// __noinline__ on purpose: the count (k_fg_preprocess) and the emission (k_fg_emit) must take the same decision for the
-// same inputs, so both call ONE compiled body instead of two inlined copies the optimiser may contract differently.
-__device__ __noinline__ bool fg_will_contribute(const float mx, const float my, const float ca, const float cb,
-                                                   const float cc, const uint32_t tile_x, const uint32_t tile_y,
-                                                   const float power_threshold) {
+// The reference compiles with --use_fast_math, so its two divisions are div.approx: __fdividef here.
+__device__ __forceinline__ bool fg_tile_test(const float mx, const float my, const float ca, const float cb, const float cc,
+                                             const uint32_t tile_x, const uint32_t tile_y, const float power_threshold) {
     const float rminx = (float)(tile_x * kTile), rminy = (float)(tile_y * kTile);
     const float rmaxx = (float)((tile_x + 1) * kTile - 1), rmaxy = (float)((tile_y + 1) * kTile - 1);
     const float x_min_diff = rminx - mx;
@@ -35,11 +33,19 @@ __device__ __noinline__ bool fg_will_contribute(const float mx, const float my, 
     const float ccx = rmaxx + x_left * (rminx - rmaxx), ccy = rmaxy + y_above * (rminy - rmaxy);
     const float diffx = mx - ccx, diffy = my - ccy;
     const float dx = copysignf((float)(kTile - 1), x_min_diff), dy = copysignf((float)(kTile - 1), y_min_diff);
-    const float tx = not_in_y * __saturatef((dx * ca * diffx + dx * cb * diffy) / (dx * ca * dx));
-    const float ty = not_in_x * __saturatef((dy * cb * diffx + dy * cc * diffy) / (dy * cc * dy));
+    const float tx = not_in_y * __saturatef(__fdividef(dx * ca * diffx + dx * cb * diffy, dx * ca * dx));
+    const float ty = not_in_x * __saturatef(__fdividef(dy * cb * diffx + dy * cc * diffy, dy * cc * dy));
     const float ex = mx - (ccx + tx * dx), ey = my - (ccy + ty * dy);
     const float max_power = 0.5f * (ca * ex * ex + cc * ey * ey) + cb * ex * ey;
     return max_power <= power_threshold;
+}
+// Rectangles of more than 64 tiles (rare) are tested twice -- counted in k_fg_preprocess, re-walked in k_fg_emit -- and both
+// must take the same decision for the same inputs: ONE compiled body.  Smaller rectangles are tested once and remembered
+// as a 64-bit mask.
+__device__ __noinline__ bool fg_will_contribute(const float mx, const float my, const float ca, const float cb,
+                                                   const float cc, const uint32_t tile_x, const uint32_t tile_y,
+                                                   const float power_threshold) {
+    return fg_tile_test(mx, my, ca, cb, cc, tile_x, tile_y, power_threshold);
 }
 
 struct FgGeom { // shared by forward (kernels_forward.cuh:60-147) and backward (kernels_backward.cuh:56-126)
@@ -129,7 +135,8 @@ __global__ void __launch_bounds__(128)
                     const uint32_t grid_h, const int active, const int total_rest, const float w, const float h,
                     const float fx, const float fy, const float cx, const float cy, const float near_, const float far_,
                     GaussRec* __restrict__ gauss, TileRect* __restrict__ rects, int32_t* __restrict__ counts,
-                    uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ ident, uint32_t* __restrict__ n_visible) {
+                    unsigned long long* __restrict__ masks, uint32_t* __restrict__ depth_keys,
+                    uint32_t* __restrict__ ident, uint32_t* __restrict__ n_visible) {
     const uint32_t i = blockIdx.x * 128 + threadIdx.x;
     if (i >= N)
         return;
@@ -162,11 +169,22 @@ __global__ void __launch_bounds__(128)
     if (x1 <= x0 || y1 <= y0)
         return;
     uint32_t nt = 0;
-    for (uint32_t ty = y0; ty < y1; ++ty)
-        for (uint32_t tx = x0; tx < x1; ++tx)
-            nt += fg_will_contribute(mx - 0.5f, my - 0.5f, ca, cb, cc, tx, ty, pt) ? 1u : 0u;
+    unsigned long long mask = 0ull;
+    if ((x1 - x0) * (y1 - y0) <= 64u) { // row-major bit per tile of the rectangle; k_fg_emit walks the bits
+        unsigned long long bit = 1ull;
+        for (uint32_t ty = y0; ty < y1; ++ty)
+            for (uint32_t tx = x0; tx < x1; ++tx, bit <<= 1)
+                if (fg_tile_test(mx - 0.5f, my - 0.5f, ca, cb, cc, tx, ty, pt))
+                    mask |= bit;
+        nt = (uint32_t)__popcll(mask);
+    } else {
+        for (uint32_t ty = y0; ty < y1; ++ty)
+            for (uint32_t tx = x0; tx < x1; ++tx)
+                nt += fg_will_contribute(mx - 0.5f, my - 0.5f, ca, cb, cc, tx, ty, pt) ? 1u : 0u;
+    }
     if (nt == 0)
         return;
+    masks[i] = mask;
     // colour, kernel_utils.cuh:15-39
     f3 col = mk3(0.5f + 0.28209479177387814f * sh0[3 * (size_t)i], 0.5f + 0.28209479177387814f * sh0[3 * (size_t)i + 1],
                  0.5f + 0.28209479177387814f * sh0[3 * (size_t)i + 2]);
@@ -198,19 +216,31 @@ __global__ void __launch_bounds__(128)
 // run; see k_emit_instances for why this beats the warp-cooperative walk.
 __global__ void __launch_bounds__(256)
     k_fg_emit(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ off, const uint32_t n_gauss,
-              const TileRect* __restrict__ rects, const int32_t* __restrict__ counts, const GaussRec* __restrict__ gauss,
-              const uint32_t tile_w, const uint32_t n_cap, uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ vals) {
+              const TileRect* __restrict__ rects, const int32_t* __restrict__ counts,
+              const unsigned long long* __restrict__ masks, const GaussRec* __restrict__ gauss, const uint32_t tile_w,
+              const uint32_t n_cap, uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ vals) {
     for (uint32_t slot = blockIdx.x * 256 + threadIdx.x; slot < n_gauss; slot += gridDim.x * 256) {
         const uint32_t g = __ldg(perm + slot);
         const int32_t cnt = counts[g];
         if (cnt <= 0)
             continue;
         const TileRect r = rects[g];
+        uint32_t pos = __ldg(off + slot);
+        const uint32_t end = pos + (uint32_t)cnt; // never write past this Gaussian's share
+        if ((uint32_t)(r.x1 - r.x0) * (uint32_t)(r.y1 - r.y0) <= 64u) {
+            unsigned long long mask = masks[g];
+            for (uint32_t ty = r.y0; ty < r.y1 && mask; ++ty)
+                for (uint32_t tx = r.x0; tx < r.x1; ++tx, mask >>= 1)
+                    if ((mask & 1ull) && pos < end && pos < n_cap) {
+                        tile_keys[pos] = ty * tile_w + tx;
+                        vals[pos] = g;
+                        ++pos;
+                    }
+            continue;
+        }
         const float4* gp = reinterpret_cast<const float4*>(gauss + g);
         const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1), g2 = __ldg(gp + 2);
         const float mx = g0.x - 0.5f, my = g0.y - 0.5f, ca = g0.z, cb = g0.w, cc = g1.x, pt = g2.y;
-        uint32_t pos = __ldg(off + slot);
-        const uint32_t end = pos + (uint32_t)cnt; // never write past this Gaussian's share
         for (uint32_t ty = r.y0; ty < r.y1; ++ty)
             for (uint32_t tx = r.x0; tx < r.x1; ++tx)
                 if (fg_will_contribute(mx, my, ca, cb, cc, tx, ty, pt) && pos < end && pos < n_cap) {
@@ -408,6 +438,7 @@ struct FgPrim {
     GaussRec* gauss;
     TileRect* rects;
     int32_t* counts;
+    unsigned long long* masks; // contributing tiles of a rectangle of <= 64 tiles, row-major
     uint32_t *dk_a, *dk_b, *pm_a, *pm_b, *off, *counters;
     void *sort_scr, *scan_scr;
     size_t bytes;
@@ -418,6 +449,7 @@ static FgPrim carve_prim(void* blob, uint32_t N) {
     p.gauss = c.take<GaussRec>(N);
     p.rects = c.take<TileRect>(N);
     p.counts = c.take<int32_t>(N);
+    p.masks = c.take<unsigned long long>(N);
     p.dk_a = c.take<uint32_t>(N), p.dk_b = c.take<uint32_t>(N);
     p.pm_a = c.take<uint32_t>(N), p.pm_b = c.take<uint32_t>(N);
     p.off = c.take<uint32_t>(N);
@@ -522,7 +554,7 @@ extern "C" int lfs_fastgs_forward(const float* means, const float* scales_raw, c
         means, scales_raw, reinterpret_cast<const float4*>(rotations_raw), opacities_raw, sh_coefficients_0,
         sh_coefficients_rest, reinterpret_cast<const float4*>(w2c), cam_position, N, tile_w, tile_h, active_sh_bases,
         total_bases_sh_rest, (float)width, (float)height, focal_x, focal_y, center_x, center_y, near_plane, far_plane,
-        P.gauss, P.rects, P.counts, P.dk_a, P.pm_a, P.counters + 1);
+        P.gauss, P.rects, P.counts, P.masks, P.dk_a, P.pm_a, P.counters + 1);
     LFS_LAUNCH_OK("k_fg_preprocess");
     int in_b = 0;
     int rc = radix_sort_pairs(P.dk_a, P.pm_a, P.dk_b, P.pm_b, N, nullptr, 0, 32, P.sort_scr, &in_b, stream);
@@ -551,7 +583,8 @@ extern "C" int lfs_fastgs_forward(const float* means, const float* scales_raw, c
     if (n_inst > 0) {
         const unsigned want = div_up(N, 256);
         const unsigned grid = want < (unsigned)(num_sms() * 16) ? want : (unsigned)(num_sms() * 16);
-        k_fg_emit<<<grid, 256, 0, stream>>>(perm, P.off, N, P.rects, P.counts, P.gauss, tile_w, n_inst, I.tk_a, I.tv_a);
+        k_fg_emit<<<grid, 256, 0, stream>>>(perm, P.off, N, P.rects, P.counts, P.masks, P.gauss, tile_w, n_inst, I.tk_a,
+                                            I.tv_a);
         LFS_LAUNCH_OK("k_fg_emit");
         rc = radix_sort_pairs(I.tk_a, I.tv_a, I.tk_b, I.tv_b, n_inst, nullptr, 0, tile_key_bits(n_tiles), I.sort_scr, &in_b,
                               stream);
