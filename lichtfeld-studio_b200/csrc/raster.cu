@@ -159,12 +159,13 @@ __device__ __forceinline__ void store_rec_pk(float4* d, const float4 A, const fl
 // the next batch is gathered with LDG.128 into registers one batch ahead.  EWA: fastgs-surface records (2-D conic, D == 1);
 // PK: FFMA2 evaluation of (N', D) (not EWA).
 // Forward epilogue: the buckets of this tile that some pixel reaches (n_contrib > 32 * bucket) go onto the live list of the
-// backward.  s_base: one shared word the caller no longer needs.
-__device__ __forceinline__ void append_live_buckets(const RasterBuffers& rb, const bool write_ckpt, const uint32_t boff,
-                                                    const uint32_t cnt_raw, const uint32_t tile_max, const uint32_t tid,
-                                                    const uint32_t n_threads, uint32_t* s_base) {
-    if (!write_ckpt || rb.live == nullptr)
-        return;
+// backward.  Everything is re-read from global memory here so that nothing extra stays live across the blend loop.
+// s_base: one shared word the caller no longer needs.
+__device__ __noinline__ void append_live_buckets(const RasterBuffers& rb, const uint32_t ft, const uint32_t tile_max,
+                                                 const uint32_t tid, const uint32_t n_threads, uint32_t* s_base) {
+    const int32_t start = rb.tile_off[ft], end = rb.tile_off[ft + 1];
+    const uint32_t cnt_raw = end > start ? (uint32_t)(end - start) : 0u;
+    const uint32_t boff = rb.bucket_off[ft];
     const uint32_t nb = (cnt_raw + kBucket - 1) / kBucket;
     const uint32_t n_live = min(nb, (tile_max + kBucket - 1) / kBucket);
     __syncthreads();
@@ -467,7 +468,8 @@ __global__ void __launch_bounds__(kFwdThreads)
     const uint32_t tile_max = max(s_warp_tot[0], s_warp_tot[1]);
     if (tid == 0)
         rb.tile_max_contrib[ft] = tile_max;
-    append_live_buckets(rb, write_ckpt, boff, (uint32_t)cnt_raw, tile_max, tid, kFwdThreads, &s_nact[0]);
+    if (write_ckpt && rb.live != nullptr)
+        append_live_buckets(rb, ft, tile_max, tid, kFwdThreads, &s_nact[0]);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -764,7 +766,8 @@ __global__ void __launch_bounds__(kFwdThreads)
     const uint32_t tile_max = max(s_warp_tot[0], s_warp_tot[1]);
     if (tid == 0)
         rb.tile_max_contrib[ft] = tile_max;
-    append_live_buckets(rb, write_ckpt, boff, (uint32_t)cnt_raw, tile_max, tid, kFwdThreads, &s_nact[0]);
+    if (write_ckpt && rb.live != nullptr)
+        append_live_buckets(rb, ft, tile_max, tid, kFwdThreads, &s_nact[0]);
 }
 
 int launch_blend_fwd(const RasterBuffers& rb, const ViewCam* cams_dev, uint32_t C, uint32_t width, uint32_t height,
