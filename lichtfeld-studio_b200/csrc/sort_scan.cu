@@ -207,7 +207,13 @@ __global__ void __launch_bounds__(1024)
         base[d1] = excl + a;
 }
 
-__global__ void __launch_bounds__(kRsThreads)
+// MODE 0: peers of a lane by MATCH.ANY, (key, value) pairs held in registers.
+// MODE 1: peers by one ballot per digit bit -- a fixed cost, where MATCH.ANY iterates once per
+// DISTINCT value in the warp, and the tile keys of 32 consecutive instances (one Gaussian's run of neighbouring tiles) are
+// nearly all distinct -- and the values are read again when the pairs are reordered, which takes 16 registers out of the
+// ranking loop (3 CTAs per SM instead of 2).
+template <int MODE>
+__global__ void __launch_bounds__(kRsThreads, MODE == 1 ? 3 : 2)
     k_rs_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                  uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n_cap,
                  const uint32_t* __restrict__ n_dev, int shift, int ndig, uint32_t nblk,
@@ -231,15 +237,30 @@ __global__ void __launch_bounds__(kRsThreads)
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t wbase = blk_base + warp * (kRsItems * 32);
     uint32_t* wh = whist + warp * ndig;
-    uint32_t key[kRsItems], val[kRsItems], lrank[kRsItems];
+    uint32_t key[kRsItems], val[MODE == 0 ? kRsItems : 1], lrank[kRsItems];
+    const int nbits = 31 - __clz(ndig);
 #pragma unroll
     for (int r = 0; r < kRsItems; ++r) {
         const uint32_t i = wbase + r * 32 + lane;
         const bool valid = i < n;
         key[r] = valid ? __ldg(keys_in + i) : 0u;
-        val[r] = valid ? __ldg(vals_in + i) : 0u;
+        if (MODE == 0)
+            val[r] = valid ? __ldg(vals_in + i) : 0u;
         const uint32_t d = valid ? ((key[r] >> shift) & (uint32_t)(ndig - 1)) : (uint32_t)ndig;
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        uint32_t peers;
+        if (MODE == 0) {
+            peers = __match_any_sync(0xffffffffu, d);
+        } else {
+            peers = __ballot_sync(0xffffffffu, valid); // invalid lanes (tail of the last tile) only match each other
+            if (!valid)
+                peers = ~peers;
+#pragma unroll
+            for (int b = 0; b < kRsMaxBits; ++b)
+                if (b < nbits) {
+                    const uint32_t m = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+                    peers &= ((d >> b) & 1u) ? m : ~m;
+                }
+        }
         const uint32_t rank = __popc(peers & lt_mask);
         const int leader = __ffs(peers) - 1;
         uint32_t before = 0;
@@ -289,7 +310,7 @@ __global__ void __launch_bounds__(kRsThreads)
             const uint32_t d = (key[r] >> shift) & (uint32_t)(ndig - 1);
             const uint32_t lp = dstart[d] + wh[d] + lrank[r];
             skey[lp] = key[r];
-            sval[lp] = val[r];
+            sval[lp] = MODE == 0 ? val[r] : __ldg(vals_in + i);
         }
     }
     __syncthreads();
@@ -535,7 +556,7 @@ int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint3
         return radix_sort_pairs_onesweep(keys_a, vals_a, keys_b, vals_b, n_cap, n_dev, begin_bit, n_bits, scratch,
                                          result_in_b, stream);
     // per-device attribute; cheap enough to set on every call (one process may drive several devices)
-    LFS_CUDA_OK(cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LFS_CUDA_OK(cudaFuncSetAttribute(k_rs_scatter<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)rs_scatter_smem(1 << kRsMaxBits)));
     const RadixPlan plan = make_radix_plan(begin_bit, n_bits);
     const uint32_t nblk = div_up(n_cap, kRsTile);
@@ -552,8 +573,12 @@ int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint3
         LFS_LAUNCH_OK("k_rs_scan_rows");
         k_rs_scan_totals<<<1, 1024, 0, stream>>>(totals, base, ndig);
         LFS_LAUNCH_OK("k_rs_scan_totals");
-        k_rs_scatter<<<nblk, kRsThreads, rs_scatter_smem(ndig), stream>>>(
-            kin, vin, kout, vout, n_cap, n_dev, plan.shift[p], ndig, nblk, table, base);
+        if (g_sort_variant == 3)
+            k_rs_scatter<1><<<nblk, kRsThreads, rs_scatter_smem(ndig), stream>>>(
+                kin, vin, kout, vout, n_cap, n_dev, plan.shift[p], ndig, nblk, table, base);
+        else
+            k_rs_scatter<0><<<nblk, kRsThreads, rs_scatter_smem(ndig), stream>>>(
+                kin, vin, kout, vout, n_cap, n_dev, plan.shift[p], ndig, nblk, table, base);
         LFS_LAUNCH_OK("k_rs_scatter");
         uint32_t* t = kin;
         kin = kout;

@@ -49,7 +49,8 @@ static inline size_t radix_scratch_bytes(uint32_t n_cap) {
 // Sorts (keys, vals) by bits [begin_bit, begin_bit + n_bits) of the key, stable.
 // keys_a/vals_a hold the input; keys_b/vals_b are the alternate buffers.  Returns (through *result_in_b)
 // whether the sorted data ended in the b buffers.  `scratch` must hold radix_scratch_bytes(n_cap).
-void set_sort_variant(int v); // 0: hist / scan / scatter chain, 1: onesweep (single histogram + decoupled look-back passes)
+void set_sort_variant(int v); // 0: hist / scan / scatter chain, 1 / 2: onesweep (all sorts / short keys only), 3: chain with
+                              // ballot ranking in the scatter passes of <= 8 bits
 int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t n_cap,
                      const uint32_t* n_dev, int begin_bit, int n_bits, void* scratch, int* result_in_b,
                      cudaStream_t stream);
