@@ -124,6 +124,45 @@ __device__ __forceinline__ int fg_sh_basis(const int active, const float x, cons
     return 15;
 }
 
+// Block-cooperative copy of `rows` consecutive rows (row_floats floats each, first row `row0`) between an AoS tensor and
+// shared memory, 128-bit where the range allows (every block starts at a multiple of 128 rows).
+__device__ __forceinline__ void fg_stage_rows(const float* __restrict__ src, float* __restrict__ smem, const uint32_t row0,
+                                              const uint32_t n_rows_total, const uint32_t row_floats) {
+    if (row0 >= n_rows_total)
+        return;
+    const uint32_t rows = min(128u, n_rows_total - row0);
+    const uint32_t nfl = rows * row_floats;
+    const float* g = src + (size_t)row0 * row_floats;
+    if ((reinterpret_cast<uintptr_t>(g) & 15u) == 0) {
+        const uint32_t n4 = nfl >> 2;
+        for (uint32_t k = threadIdx.x; k < n4; k += blockDim.x)
+            reinterpret_cast<float4*>(smem)[k] = __ldg(reinterpret_cast<const float4*>(g) + k);
+        for (uint32_t k = (n4 << 2) + threadIdx.x; k < nfl; k += blockDim.x)
+            smem[k] = __ldg(g + k);
+    } else {
+        for (uint32_t k = threadIdx.x; k < nfl; k += blockDim.x)
+            smem[k] = __ldg(g + k);
+    }
+}
+__device__ __forceinline__ void fg_unstage_rows(float* __restrict__ dst, const float* __restrict__ smem, const uint32_t row0,
+                                                const uint32_t n_rows_total, const uint32_t row_floats) {
+    if (row0 >= n_rows_total)
+        return;
+    const uint32_t rows = min(128u, n_rows_total - row0);
+    const uint32_t nfl = rows * row_floats;
+    float* g = dst + (size_t)row0 * row_floats;
+    if ((reinterpret_cast<uintptr_t>(g) & 15u) == 0) {
+        const uint32_t n4 = nfl >> 2;
+        for (uint32_t k = threadIdx.x; k < n4; k += blockDim.x)
+            reinterpret_cast<float4*>(g)[k] = reinterpret_cast<const float4*>(smem)[k];
+        for (uint32_t k = (n4 << 2) + threadIdx.x; k < nfl; k += blockDim.x)
+            g[k] = smem[k];
+    } else {
+        for (uint32_t k = threadIdx.x; k < nfl; k += blockDim.x)
+            g[k] = smem[k];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // preprocess (kernels_forward.cuh:18-205)
 // ------------------------------------------------------------------------------------------------------
@@ -137,7 +176,13 @@ __global__ void __launch_bounds__(128)
                     GaussRec* __restrict__ gauss, TileRect* __restrict__ rects, int32_t* __restrict__ counts,
                     unsigned long long* __restrict__ masks, uint32_t* __restrict__ depth_keys,
                     uint32_t* __restrict__ ident, uint32_t* __restrict__ n_visible) {
+    // the higher SH bands of the block's 128 primitives are one contiguous range of the AoS tensor: copied with coalesced
+    // 128-bit loads (a thread reading its own 180-B row touches 32 sectors per load instruction of the warp)
+    __shared__ __align__(16) float s_sh[128 * 45];
     const uint32_t i = blockIdx.x * 128 + threadIdx.x;
+    if (active > 1)
+        fg_stage_rows(sh_rest, s_sh, blockIdx.x * 128u, N, 3u * (uint32_t)total_rest);
+    __syncthreads();
     if (i >= N)
         return;
     ident[i] = i;
@@ -193,7 +238,8 @@ __global__ void __launch_bounds__(128)
         const float inv = rsqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
         float b[15];
         const int nb = fg_sh_basis(active, d.x * inv, d.y * inv, d.z * inv, b);
-        const float* c = sh_rest + 3 * (size_t)i * total_rest;
+        const float* c = s_sh + 3 * (size_t)threadIdx.x * total_rest; // row stride 3 * total_rest floats: odd (9, 45), hence
+                                                                     // conflict-free, for SH degree 1 and 3
 #pragma unroll
         for (int j = 0; j < 15; ++j)
             if (j < nb) {
@@ -229,13 +275,21 @@ __global__ void __launch_bounds__(256)
         const uint32_t end = pos + (uint32_t)cnt; // never write past this Gaussian's share
         if ((uint32_t)(r.x1 - r.x0) * (uint32_t)(r.y1 - r.y0) <= 64u) {
             unsigned long long mask = masks[g];
-            for (uint32_t ty = r.y0; ty < r.y1 && mask; ++ty)
-                for (uint32_t tx = r.x0; tx < r.x1; ++tx, mask >>= 1)
-                    if ((mask & 1ull) && pos < end && pos < n_cap) {
-                        tile_keys[pos] = ty * tile_w + tx;
+            const uint32_t w = (uint32_t)(r.x1 - r.x0);
+            const unsigned long long row_mask = w == 64u ? ~0ull : ((1ull << w) - 1ull);
+            for (uint32_t ty = r.y0; ty < r.y1 && mask; ++ty, mask = w == 64u ? 0ull : (mask >> w)) {
+                unsigned long long row = mask & row_mask;
+                const uint32_t key0 = ty * tile_w + r.x0;
+                while (row) { // one iteration per contributing tile
+                    const uint32_t k = (uint32_t)__ffsll((long long)row) - 1u;
+                    row &= row - 1ull;
+                    if (pos < end && pos < n_cap) {
+                        tile_keys[pos] = key0 + k;
                         vals[pos] = g;
                         ++pos;
                     }
+                }
+            }
             continue;
         }
         const float4* gp = reinterpret_cast<const float4*>(gauss + g);
@@ -288,8 +342,15 @@ __global__ void __launch_bounds__(128)
                         float* __restrict__ g_shN, float* __restrict__ g_w2c, float* __restrict__ densification_info,
                         const uint32_t N, const int active, const int total_rest, const float w, const float h,
                         const float fx, const float fy, const float cx, const float cy) {
+    // sh_rest rows of the block come in, and the g_shN rows go out, through one shared buffer with coalesced 128-bit
+    // accesses: each thread overwrites its own row (coefficients -> gradients) once it has read it
+    __shared__ __align__(16) float s_sh[128 * 45];
     const uint32_t i = blockIdx.x * 128 + threadIdx.x;
     const bool on = i < N && counts[i] > 0;
+    const uint32_t row_floats = 3u * (uint32_t)total_rest;
+    if (active > 1)
+        fg_stage_rows(sh_rest, s_sh, blockIdx.x * 128u, N, row_floats);
+    __syncthreads();
     f3 dcam = mk3(0.f, 0.f, 0.f), mean = mk3(0.f, 0.f, 0.f);
     if (i < N && !on) { // the reference leaves torch::zeros there (rasterization_api.cu:120-125)
         g_means[3 * (size_t)i] = g_means[3 * (size_t)i + 1] = g_means[3 * (size_t)i + 2] = 0.f;
@@ -297,8 +358,8 @@ __global__ void __launch_bounds__(128)
         g_rot[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         g_opac[i] = 0.f;
         g_sh0[3 * (size_t)i] = g_sh0[3 * (size_t)i + 1] = g_sh0[3 * (size_t)i + 2] = 0.f;
-        for (int j = 0; j < 3 * total_rest; ++j)
-            g_shN[3 * (size_t)i * total_rest + j] = 0.f;
+        for (uint32_t j = 0; j < row_floats; ++j)
+            s_sh[threadIdx.x * row_floats + j] = 0.f;
     }
     if (on) {
         mean = mk3(means[3 * (size_t)i], means[3 * (size_t)i + 1], means[3 * (size_t)i + 2]);
@@ -307,7 +368,7 @@ __global__ void __launch_bounds__(128)
         g_sh0[3 * (size_t)i] = 0.28209479177387814f * gc.x, g_sh0[3 * (size_t)i + 1] = 0.28209479177387814f * gc.y;
         g_sh0[3 * (size_t)i + 2] = 0.28209479177387814f * gc.z;
         f3 dpos = mk3(0.f, 0.f, 0.f);
-        float* gN = g_shN + 3 * (size_t)i * total_rest;
+        float* gN = s_sh + threadIdx.x * row_floats;
         int nb = 0;
         if (active > 1) {
             const float xr = mean.x - cam_position[0], yr = mean.y - cam_position[1], zr = mean.z - cam_position[2];
@@ -315,7 +376,7 @@ __global__ void __launch_bounds__(128)
             const float x = xr * inv, y = yr * inv, z = zr * inv;
             float b[15];
             nb = fg_sh_basis(active, x, y, z, b);
-            const float* c = sh_rest + 3 * (size_t)i * total_rest;
+            const float* c = gN; // this thread's row: read here, overwritten by the gradients below
             float cg[15]; // <coefficient_j, grad_color>
 #pragma unroll
             for (int j = 0; j < 15; ++j) {
@@ -418,6 +479,9 @@ __global__ void __launch_bounds__(128)
             densification_info[(size_t)N + i] += sqrtf(sx * sx + sy * sy);
         }
     }
+    __syncthreads();
+    if (total_rest > 0)
+        fg_unstage_rows(g_shN, s_sh, blockIdx.x * 128u, N, row_floats);
     if (g_w2c) { // kernels_backward.cuh:162-175, one atomic per warp and entry instead of one per primitive
         float vals[12] = {dcam.x * mean.x, dcam.x * mean.y, dcam.x * mean.z, dcam.x, dcam.y * mean.x, dcam.y * mean.y,
                           dcam.y * mean.z, dcam.y, dcam.z * mean.x, dcam.z * mean.y, dcam.z * mean.z, dcam.z};
@@ -533,6 +597,8 @@ extern "C" int lfs_fastgs_forward(const float* means, const float* scales_raw, c
     LFS_CHECK_ARG(width > 0 && height > 0 && n_primitives > 0, "fastgs_forward: empty problem");
     LFS_CHECK_ARG(active_sh_bases == 1 || active_sh_bases == 4 || active_sh_bases == 9 || active_sh_bases == 16,
                   "fastgs_forward: active_sh_bases must be 1, 4, 9 or 16 (got %d)", active_sh_bases);
+    LFS_UNSUPPORTED(total_bases_sh_rest > 15, "fastgs_forward: %d higher SH bases (at most 15 = degree 3, as the reference)",
+                    total_bases_sh_rest);
     LFS_CHECK_ARG(active_sh_bases - 1 <= total_bases_sh_rest && (total_bases_sh_rest == 0 || sh_coefficients_rest),
                   "fastgs_forward: sh_coefficients_rest holds %d bases, %d are active", total_bases_sh_rest,
                   active_sh_bases - 1);
@@ -650,6 +716,8 @@ extern "C" int lfs_fastgs_backward(const float* grad_image, const float* grad_al
                   "fastgs_backward: null output");
     LFS_CHECK_ARG(n_instances >= 0 && n_buckets >= 0 && width > 0 && height > 0 && n_primitives > 0,
                   "fastgs_backward: bad sizes");
+    LFS_UNSUPPORTED(total_bases_sh_rest > 15, "fastgs_backward: %d higher SH bases (at most 15 = degree 3, as the reference)",
+                    total_bases_sh_rest);
     const uint32_t N = n_primitives;
     const uint32_t tile_w = (width + kTile - 1) / kTile, tile_h = (height + kTile - 1) / kTile, n_tiles = tile_w * tile_h;
     const uint32_t npix = (uint32_t)width * (uint32_t)height;

@@ -1,7 +1,14 @@
-"""Times the fastgs (EWA) SURFACE, forward + backward per view, ours (lfs_fastgs_forward/backward through ops.py) and
-the unmodified reference build (oracle/_ref/libfastgs_ref.so) on the same seeded scene:
-    python tools/bench_fastgs.py C2 [views] [reps]
-Prints one JSON line.  Both sides allocate per call and block on the instance / bucket counts, as the reference does."""
+"""Times the fastgs (EWA) OPERATOR SURFACE -- forward_wrapper + backward_wrapper of one view, the calls FastGSRasterize makes
+(fastgs/rasterization/include/rasterization_api.h) -- on the same seeded scene through
+
+    b200   oracle/_ref/b200_fastgs_torch*.so   the reference's symbols exported by this project's host layer
+    ref    oracle/_ref/ref_fastgs_torch*.so    the unmodified reference fastgs build (compute_90 PTX objects, see
+                                               profiles/r02_ref_fastgs_root_cause.txt)
+
+    python tools/bench_fastgs.py C3 [views] [reps]
+
+Both sides allocate their outputs and state blobs per call and block on the instance / bucket counts, as the reference does.
+Prints one JSON line.  TEST / BENCH INFRASTRUCTURE ONLY."""
 import json
 import os
 import sys
@@ -12,7 +19,8 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from lichtfeld_studio_b200 import ops, scene as S  # noqa: E402
+import ref_libs as R  # noqa: E402
+from lichtfeld_studio_b200 import scene as S  # noqa: E402
 
 cfg = sys.argv[1] if len(sys.argv) > 1 else "C2"
 n, V, W, H, deg = S.CONFIGS[cfg]
@@ -32,12 +40,18 @@ ga = torch.zeros((1, H, W), device=dev)
 nb = (deg + 1) ** 2
 
 
-def ours(v):
-    w2c, cp, fx, fy, cx, cy = cams[v]
-    img, al, ctx = ops.fastgs_forward(P["means"], P["scales"], P["rot"], P["op"], P["sh0"], P["shN"], w2c, cp, nb, W, H, fx,
-                                      fy, cx, cy, 0.01, 1e10)
-    g = ops.fastgs_backward(ctx, gi, ga, P["means"], P["scales"], P["rot"], P["shN"], w2c, cp)
-    return ctx.n_instances, img, g
+def make_step(mod):
+    dens = torch.zeros((2, n), device=dev)
+
+    def step(v):
+        w2c, cp, fx, fy, cx, cy = cams[v]
+        r = mod.forward_wrapper(P["means"], P["scales"], P["rot"], P["op"], P["sh0"], P["shN"], w2c, cp, nb, W, H, fx, fy, cx,
+                                cy, 0.01, 1e10)
+        g = mod.backward_wrapper(dens, gi, ga, r[0], r[1], P["means"], P["scales"], P["rot"], P["shN"], r[2], r[3], r[4], r[5],
+                                 w2c, cp, nb, W, H, fx, fy, cx, cy, 0.01, 1e10, r[6], r[7], r[8], r[9], r[10])
+        return (int(r[6]), int(r[7]), int(r[8])), r[0], g
+
+    return step
 
 
 def timeit(fn):
@@ -56,29 +70,21 @@ def timeit(fn):
     return best
 
 
-out = {"config": cfg, "gaussians": n, "width": W, "height": H, "views": views}
-n_inst, img, g = ours(0)
-out["instances_view0"] = n_inst
+out = {"config": cfg, "gaussians": n, "width": W, "height": H, "views": views,
+       "what": "forward_wrapper + backward_wrapper per view (op surface, allocations and blocking count reads included)"}
+ours = make_step(R.fastgs_torch_module("b200"))
+counts, img, g = ours(0)
+out["counts_view0"] = list(counts)
 out["ours_ms_per_view"] = timeit(ours)
 try:
-    import ref_libs as R
-    if R.have_fastgs():
-        fg = R.FastGS()
-
-        def ref(v):
-            w2c, cp, fx, fy, cx, cy = cams[v]
-            rimg, ral, counts = fg.forward(P["means"], P["scales"], P["rot"], P["op"], P["sh0"], P["shN"], w2c, cp, nb, W, H,
-                                           fx, fy, cx, cy)
-            rg = fg.backward(gi, ga, rimg, ral, P["means"], P["scales"], P["rot"], P["shN"], w2c, cp, nb, W, H, fx, fy, cx, cy)
-            return counts, rimg, rg
-
-        counts, rimg, rg = ref(0)
-        torch.cuda.synchronize()
-        out["ref_counts_view0"] = list(counts)
-        out["ref_vs_ours_image_rel"] = float((rimg - img).abs().max() / img.abs().max())
-        out["ref_vs_ours_grad_means_rel"] = float((rg["means"] - g[0]).abs().max() / g[0].abs().max())
-        out["ref_ms_per_view"] = timeit(ref)
-        out["speedup"] = out["ref_ms_per_view"] / out["ours_ms_per_view"]
-except Exception as e:  # the reference build is known to fail at 1080p on this image (profiles/r01_ref_fastgs_diagnosis.txt)
+    ref = make_step(R.fastgs_torch_module("ref"))
+    rcounts, rimg, rg = ref(0)
+    torch.cuda.synchronize()
+    out["ref_counts_view0"] = list(rcounts)
+    out["ref_vs_ours_image_rel"] = float((rimg - img).abs().max() / img.abs().max())
+    out["ref_vs_ours_grad_means_rel"] = float((rg[0] - g[0]).abs().max() / g[0].abs().max())
+    out["ref_ms_per_view"] = timeit(ref)
+    out["speedup"] = out["ref_ms_per_view"] / out["ours_ms_per_view"]
+except Exception as e:
     out["ref_error"] = repr(e)[:300]
 print(json.dumps(out))
