@@ -1311,10 +1311,11 @@ __device__ __forceinline__ void bwd_sp_bucket(const uint32_t b, const int lane, 
         const bool grad = EWA ? e.pass : (e.pass && e.a_raw <= kAlphaMax);
         const float vo = (EWA ? alpha : e.vis) * v_alpha;
         aop += grad ? vo : 0.f;
-        const float vN = EWA ? v_alpha * alpha * kLn2 : v_alpha * e.a_raw * kLn2 * e.rD;
+        // (the factor ln 2 of d 2^x / dx is applied once per instance, after the loop)
+        const float vN = EWA ? v_alpha * alpha : v_alpha * e.a_raw * e.rD;
         const float2 V = grad ? make_float2(vN, -vN * e.p2) : make_float2(0.f, 0.f);
         const float2 DX = make_float2(e.dx, e.dx), DY = make_float2(e.dy, e.dy);
-        G0.x += V.x, G0.y += V.y;
+        G0 = ffma2(V, make_float2(1.f, 1.f), G0);
         G1 = ffma2(V, DX, G1);
         G2 = ffma2(V, DY, G2);
         G3 = ffma2(V, fmul2(DX, DX), G3);
@@ -1343,8 +1344,8 @@ __device__ __forceinline__ void bwd_sp_bucket(const uint32_t b, const int lane, 
 
     if (!valid)
         return;
-    const float an0 = G0.x, an1 = G1.x, an2 = G2.x, an3 = G3.x, an4 = G4.x, an5 = G5.x;
-    const float ad0 = G0.y, ad1 = G1.y, ad2 = G2.y, ad3 = G3.y, ad4 = G4.y, ad5 = G5.y;
+    const float an0 = kLn2 * G0.x, an1 = kLn2 * G1.x, an2 = kLn2 * G2.x, an3 = kLn2 * G3.x, an4 = kLn2 * G4.x, an5 = kLn2 * G5.x;
+    const float ad0 = kLn2 * G0.y, ad1 = kLn2 * G1.y, ad2 = kLn2 * G2.y, ad3 = kLn2 * G3.y, ad4 = kLn2 * G4.y, ad5 = kLn2 * G5.y;
     const float acr = GC.x, acg = GC.y;
     if (EWA) {
         // ---- polynomial-coefficient gradients -> (conic, mean2d); e = mean2d - tile centre
