@@ -390,7 +390,8 @@ __global__ void __launch_bounds__(kRsThreads)
 
 // One pass.  status [n_tiles][256]: (flag << 30) | count, zeroed by the caller; ticket: tile counter of this pass (zeroed);
 // err: set to 1 on a look-back timeout.
-__global__ void __launch_bounds__(kRsThreads)
+template <int MODE> // ranking as in k_rs_scatter<MODE>
+__global__ void __launch_bounds__(kRsThreads, MODE == 1 ? 3 : 2)
     k_os_pass(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
               uint32_t* __restrict__ vals_out, uint32_t n_cap, const uint32_t* __restrict__ n_dev, const int shift,
               const int bits, const uint32_t* __restrict__ ghist /* [256] of this pass */, uint32_t* __restrict__ status,
@@ -417,15 +418,29 @@ __global__ void __launch_bounds__(kRsThreads)
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t wbase = blk_base + warp * (kRsItems * 32);
     uint32_t* wh = whist + warp * kOsDig;
-    uint32_t key[kRsItems], val[kRsItems], lrank[kRsItems];
+    uint32_t key[kRsItems], val[MODE == 0 ? kRsItems : 1], lrank[kRsItems];
 #pragma unroll
     for (int r = 0; r < kRsItems; ++r) {
         const uint32_t i = wbase + r * 32 + lane;
         const bool valid = i < n;
         key[r] = valid ? __ldg(keys_in + i) : 0u;
-        val[r] = valid ? __ldg(vals_in + i) : 0u;
+        if (MODE == 0)
+            val[r] = valid ? __ldg(vals_in + i) : 0u;
         const uint32_t d = valid ? ((key[r] >> shift) & dmask) : (uint32_t)kOsDig;
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        uint32_t peers;
+        if (MODE == 0) {
+            peers = __match_any_sync(0xffffffffu, d);
+        } else {
+            peers = __ballot_sync(0xffffffffu, valid);
+            if (!valid)
+                peers = ~peers;
+#pragma unroll
+            for (int b = 0; b < kOsBits; ++b)
+                if (b < bits) {
+                    const uint32_t m = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+                    peers &= ((d >> b) & 1u) ? m : ~m;
+                }
+        }
         const uint32_t rank = __popc(peers & lt_mask);
         const int leader = __ffs(peers) - 1;
         uint32_t before = 0;
@@ -492,7 +507,7 @@ __global__ void __launch_bounds__(kRsThreads)
             const uint32_t d = (key[r] >> shift) & dmask;
             const uint32_t lp = dstart[d] + wh[d] + lrank[r];
             skey[lp] = key[r];
-            sval[lp] = val[r];
+            sval[lp] = MODE == 0 ? val[r] : __ldg(vals_in + i);
         }
     }
     __syncthreads();
@@ -527,7 +542,11 @@ static int radix_sort_pairs_onesweep(uint32_t* keys_a, uint32_t* vals_a, uint32_
     LFS_LAUNCH_OK("k_os_hist");
     uint32_t *kin = keys_a, *vin = vals_a, *kout = keys_b, *vout = vals_b;
     for (int p = 0; p < plan.n_pass; ++p) {
-        k_os_pass<<<ntiles, kRsThreads, 0, stream>>>(kin, vin, kout, vout, n_cap, n_dev, plan.shift[p], plan.bits[p],
+if (g_sort_variant == 4)
+                    k_os_pass<1><<<ntiles, kRsThreads, 0, stream>>>(kin, vin, kout, vout, n_cap, n_dev, plan.shift[p], plan.bits[p],
+                                                     ghist + p * kOsDig, status + (size_t)p * ntiles * kOsDig, ticket + p, err);
+        else
+                    k_os_pass<0><<<ntiles, kRsThreads, 0, stream>>>(kin, vin, kout, vout, n_cap, n_dev, plan.shift[p], plan.bits[p],
                                                      ghist + p * kOsDig, status + (size_t)p * ntiles * kOsDig, ticket + p, err);
         LFS_LAUNCH_OK("k_os_pass");
         uint32_t* t = kin;
@@ -551,7 +570,8 @@ int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint3
         return LFS_OK;
     // variant 1: onesweep for every sort; variant 2: only where it does not add a pass (<= 16 key bits: the tile sort; the
     // 32-bit depth sort keeps three 11-bit passes instead of four 8-bit ones)
-    if ((g_sort_variant == 1 || (g_sort_variant == 2 && n_bits <= 2 * kOsBits)) && n_bits <= kOsBits * kOsMaxPass &&
+    if ((g_sort_variant == 1 || ((g_sort_variant == 2 || g_sort_variant == 4) && n_bits <= 2 * kOsBits)) &&
+        n_bits <= kOsBits * kOsMaxPass &&
         n_cap < (1u << 30))
         return radix_sort_pairs_onesweep(keys_a, vals_a, keys_b, vals_b, n_cap, n_dev, begin_bit, n_bits, scratch,
                                          result_in_b, stream);
@@ -573,7 +593,7 @@ int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint3
         LFS_LAUNCH_OK("k_rs_scan_rows");
         k_rs_scan_totals<<<1, 1024, 0, stream>>>(totals, base, ndig);
         LFS_LAUNCH_OK("k_rs_scan_totals");
-        if (g_sort_variant == 3)
+        if (g_sort_variant == 3 || g_sort_variant == 4)
             k_rs_scatter<1><<<nblk, kRsThreads, rs_scatter_smem(ndig), stream>>>(
                 kin, vin, kout, vout, n_cap, n_dev, plan.shift[p], ndig, nblk, table, base);
         else
