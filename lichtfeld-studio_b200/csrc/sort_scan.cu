@@ -578,6 +578,8 @@ int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint3
     // per-device attribute; cheap enough to set on every call (one process may drive several devices)
     LFS_CUDA_OK(cudaFuncSetAttribute(k_rs_scatter<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)rs_scatter_smem(1 << kRsMaxBits)));
+    LFS_CUDA_OK(cudaFuncSetAttribute(k_rs_scatter<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)rs_scatter_smem(1 << kRsMaxBits)));
     const RadixPlan plan = make_radix_plan(begin_bit, n_bits);
     const uint32_t nblk = div_up(n_cap, kRsTile);
     uint32_t* table = static_cast<uint32_t*>(scratch);
