@@ -345,7 +345,8 @@ def main():
     # workload (ncu cannot run inside a timed bench): newest profiles/rNN_ncu_full*.json that has the kernel
     traffic, traffic_src = None, None
     import glob
-    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full*.json")), reverse=True):
+    for path in (sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full*.json")), reverse=True)
+                 if a.config == "C3" else []):  # the capture is of the C3 view
         try:
             for k in json.load(open(path)):
                 if k["kernel"].startswith("k_blend_bwd"):
