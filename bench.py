@@ -146,7 +146,8 @@ def reference_gpu_leg(path: str, config: str, n_gaussians: int, views: int, step
     module 'b200': the SAME unchanged reference caller code linked against this library's host layer instead (the drop-in
     configuration a maintainer gets by switching the backend)."""
     cmd = [sys.executable, os.path.join(ROOT, "tools", "ref_train.py"), "--module", module, "--path", path, "--config",
-           config, "--views", str(views), "--steps", str(max(2, min(steps, 4))), "--warmup", "1"]
+           config, "--views", str(views), "--steps", str(max(2, min(steps, 4))), "--warmup", "2"]  # 2 warm-up steps: the
+    # caching allocator needs them to hold a block for every per-view blob size (8 views, 4 blobs each)
     if n_gaussians:
         cmd += ["--n-gaussians", str(n_gaussians)]
     try:

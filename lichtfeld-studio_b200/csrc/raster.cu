@@ -158,23 +158,28 @@ __device__ __forceinline__ void store_rec_pk(float4* d, const float4 A, const fl
 // Register-staged variant (round 1's kernel, kept for A/B measurements: lfs_set_option("fwd_variant", 1)): the GaussRec of
 // the next batch is gathered with LDG.128 into registers one batch ahead.  EWA: fastgs-surface records (2-D conic, D == 1);
 // PK: FFMA2 evaluation of (N', D) (not EWA).
-// Forward epilogue: the buckets of this tile that some pixel reaches (n_contrib > 32 * bucket) go onto the live list of the
-// backward.  Everything is re-read from global memory here so that nothing extra stays live across the blend loop.
-// s_base: one shared word the caller no longer needs.
-__device__ __noinline__ void append_live_buckets(const RasterBuffers& rb, const uint32_t ft, const uint32_t tile_max,
-                                                 const uint32_t tid, const uint32_t n_threads, uint32_t* s_base) {
+// After the forward: the buckets some pixel reaches (n_contrib > 32 * bucket) go onto the live list of the backward, one
+// thread per tile (a few microseconds; as an epilogue of the forward kernel it cost 5 % of that kernel).
+__global__ void __launch_bounds__(256) k_live_buckets(const RasterBuffers rb, const uint32_t n_tiles_total) {
+    const uint32_t ft = blockIdx.x * 256 + threadIdx.x;
+    if (ft >= n_tiles_total)
+        return;
     const int32_t start = rb.tile_off[ft], end = rb.tile_off[ft + 1];
     const uint32_t cnt_raw = end > start ? (uint32_t)(end - start) : 0u;
-    const uint32_t boff = rb.bucket_off[ft];
     const uint32_t nb = (cnt_raw + kBucket - 1) / kBucket;
-    const uint32_t n_live = min(nb, (tile_max + kBucket - 1) / kBucket);
-    __syncthreads();
-    if (tid == 0)
-        *s_base = n_live ? atomicAdd(rb.live, n_live) : 0u;
-    __syncthreads();
-    const uint32_t base = *s_base;
-    for (uint32_t k = tid; k < n_live; k += n_threads)
+    const uint32_t tmax = rb.tile_max_contrib[ft];
+    const uint32_t n_live = min(nb, (tmax + kBucket - 1) / kBucket);
+    if (n_live == 0)
+        return;
+    const uint32_t boff = rb.bucket_off[ft];
+    const uint32_t base = atomicAdd(rb.live, n_live);
+    for (uint32_t k = 0; k < n_live; ++k)
         rb.live[2 + base + k] = boff + k;
+}
+static int launch_live_buckets(const RasterBuffers& rb, const uint32_t n_tiles_total, cudaStream_t stream) {
+    k_live_buckets<<<div_up(n_tiles_total, 256), 256, 0, stream>>>(rb, n_tiles_total);
+    LFS_LAUNCH_OK("k_live_buckets");
+    return LFS_OK;
 }
 
 template <bool EWA, bool PK = false>
@@ -468,8 +473,6 @@ __global__ void __launch_bounds__(kFwdThreads)
     const uint32_t tile_max = max(s_warp_tot[0], s_warp_tot[1]);
     if (tid == 0)
         rb.tile_max_contrib[ft] = tile_max;
-    if (write_ckpt && rb.live != nullptr)
-        append_live_buckets(rb, ft, tile_max, tid, kFwdThreads, &s_nact[0]);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -766,8 +769,6 @@ __global__ void __launch_bounds__(kFwdThreads)
     const uint32_t tile_max = max(s_warp_tot[0], s_warp_tot[1]);
     if (tid == 0)
         rb.tile_max_contrib[ft] = tile_max;
-    if (write_ckpt && rb.live != nullptr)
-        append_live_buckets(rb, ft, tile_max, tid, kFwdThreads, &s_nact[0]);
 }
 
 int launch_blend_fwd(const RasterBuffers& rb, const ViewCam* cams_dev, uint32_t C, uint32_t width, uint32_t height,
@@ -785,6 +786,8 @@ int launch_blend_fwd(const RasterBuffers& rb, const ViewCam* cams_dev, uint32_t 
         k_blend_fwd_tg<false><<<grid, kFwdThreads, 0, stream>>>(rb, cams_dev, width, height, tile_w, tile_h, write_ckpt,
                                                                backgrounds, masks, renders, alphas, last_ids);
     LFS_LAUNCH_OK("k_blend_fwd");
+    if (rb.live && write_ckpt)
+        return launch_live_buckets(rb, tile_w * tile_h * C, stream);
     return LFS_OK;
 }
 
@@ -801,6 +804,8 @@ int launch_blend_fwd_ewa(const RasterBuffers& rb, uint32_t width, uint32_t heigh
         k_blend_fwd_tg<true><<<dim3(tile_w * tile_h, 1), kFwdThreads, 0, stream>>>(
             rb, nullptr, width, height, tile_w, tile_h, write_ckpt, nullptr, nullptr, nullptr, nullptr, nullptr);
     LFS_LAUNCH_OK("k_blend_fwd<ewa>");
+    if (rb.live && write_ckpt)
+        return launch_live_buckets(rb, tile_w * tile_h, stream);
     return LFS_OK;
 }
 
