@@ -100,7 +100,7 @@ int lfs_spherical_harmonics_bwd(uint32_t K, uint32_t degrees_to_use, const float
                                 float* v_dirs, void* stream);
 
 /* Replaces gsplat::intersect_tile (gsplat/Ops.h:28-38, gsplat/Intersect.cpp:15-122; kernels
- * gsplat/IntersectTile.cu:24-114 and the CUB sort :290-328).  Non-packed layout only.
+ * gsplat/IntersectTile.cu:24-114 and the CUB sort :290-328).  [C,N] layout; the packed layout is lfs_intersect_tile_packed.
  * means2d [C,N,2], radii [C,N,2] i32, depths [C,N] -> tiles_per_gauss [C,N] i32 (caller allocated),
  * and, through `alloc`, isect_ids [n_isects] i64 (tag 1) and flatten_ids [n_isects] i32 (tag 2); scratch is
  * requested with tag 0 and may be released when the call returns.  Like the reference this call blocks
@@ -112,6 +112,15 @@ int lfs_intersect_tile(const float* means2d, const int32_t* radii, const float* 
                        uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, int sort,
                        int32_t* tiles_per_gauss, lfs_alloc_fn alloc, void* alloc_ctx, int64_t** isect_ids,
                        int32_t** flatten_ids, int64_t* n_isects_host, void* stream);
+
+/* The packed layout of gsplat::intersect_tile (gsplat/Intersect.cpp:32-39, kernel IntersectTile.cu:83-90): means2d [nnz,2],
+ * radii [nnz,2], depths [nnz], camera_ids [nnz] i64 (the camera of every element; gaussian_ids is not needed, as in the
+ * reference kernel); flatten_ids index [nnz].  Same outputs, same key layout (camera | tile | depth bits), same order as
+ * the reference's 64-bit sort.  floor(log2 C) + floor(log2 n_tiles) + 2 <= 32 bits (the reference asserts the same). */
+int lfs_intersect_tile_packed(const float* means2d, const int32_t* radii, const float* depths, const int64_t* camera_ids,
+                              uint32_t nnz, uint32_t C, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
+                              int sort, int32_t* tiles_per_gauss, lfs_alloc_fn alloc, void* alloc_ctx, int64_t** isect_ids,
+                              int32_t** flatten_ids, int64_t* n_isects_host, void* stream);
 
 /* Replaces gsplat::intersect_offset (gsplat/Ops.h:39-43, kernel gsplat/IntersectTile.cu:206-252).
  * offsets [C, tile_height, tile_width] i32. */

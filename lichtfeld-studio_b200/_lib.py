@@ -95,6 +95,11 @@ SIGNATURES = {
         [_vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, C.c_int, _vp, ALLOC_FN, _vp, C.POINTER(_vp), C.POINTER(_vp),
          C.POINTER(_i64), _vp],
     ),
+    "lfs_intersect_tile_packed": (
+        C.c_int,
+        [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, C.c_int, _vp, ALLOC_FN, _vp, C.POINTER(_vp), C.POINTER(_vp),
+         C.POINTER(_i64), _vp],
+    ),
     "lfs_fastgs_forward": (
         C.c_int,
         [_vp] * 8 + [_u32] + [C.c_int] * 4 + [C.c_float] * 6 + [_vp, _vp, ALLOC_FN, _vp] + [C.POINTER(C.c_int)] * 4 + [_vp],

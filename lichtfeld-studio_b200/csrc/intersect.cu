@@ -222,6 +222,32 @@ __global__ void __launch_bounds__(kIsThreads)
     }
 }
 
+// ---- packed layout (gsplat/Intersect.cpp:32-39, IntersectTile.cu:83-90): element e belongs to camera camera_ids[e] ----
+// the camera id goes above the tile bits of the second-level key, as in the reference's 64-bit key
+__global__ void __launch_bounds__(kIsThreads)
+    k_add_camera_bits(uint32_t* __restrict__ tile_keys, const uint32_t* __restrict__ vals,
+                      const int64_t* __restrict__ camera_ids, const uint32_t n, const uint32_t tile_n_bits) {
+    const uint32_t j = blockIdx.x * kIsThreads + threadIdx.x;
+    if (j < n)
+        tile_keys[j] |= (uint32_t)__ldg(camera_ids + __ldg(vals + j)) << tile_n_bits;
+}
+__global__ void __launch_bounds__(kIsThreads)
+    k_emit_unsorted_packed(const uint32_t* __restrict__ off, const uint32_t n_gauss, const int64_t* __restrict__ camera_ids,
+                           const TileRect* __restrict__ rects, const float* __restrict__ depths, const uint32_t tile_w,
+                           const uint32_t tile_n_bits, const uint32_t n, int64_t* __restrict__ isect_ids,
+                           int32_t* __restrict__ flatten_ids) {
+    for (uint32_t j = blockIdx.x * kIsThreads + threadIdx.x; j < n; j += gridDim.x * kIsThreads) {
+        const uint32_t g = upper_slot(off, n_gauss, j);
+        const uint32_t k = j - __ldg(off + g);
+        const TileRect r = rects[g];
+        const uint32_t w = (uint32_t)r.x1 - (uint32_t)r.x0;
+        const int64_t tile_id = (int64_t)((r.y0 + k / w) * tile_w + (r.x0 + k % w));
+        const int64_t cid_enc = __ldg(camera_ids + g) << (32 + tile_n_bits);
+        isect_ids[j] = cid_enc | (tile_id << 32) | (int64_t)__float_as_uint(__ldg(depths + g));
+        flatten_ids[j] = (int32_t)g;
+    }
+}
+
 __global__ void __launch_bounds__(kIsThreads)
     k_intersect_offset(const int64_t* __restrict__ isect_ids, const uint32_t n, const uint32_t n_tiles,
                        const uint32_t tile_n_bits, const uint32_t total, int32_t* __restrict__ offsets) {
@@ -385,6 +411,112 @@ extern "C" int lfs_intersect_tile(const float* means2d, const int32_t* radii, co
                                                                             flat + cam_off);
         LFS_LAUNCH_OK("k_make_isect_ids");
         cam_off += nc;
+    }
+    *isect_ids = ids;
+    *flatten_ids = flat;
+    return LFS_OK;
+}
+
+extern "C" int lfs_intersect_tile_packed(const float* means2d, const int32_t* radii, const float* depths,
+                                         const int64_t* camera_ids, uint32_t nnz, uint32_t C, uint32_t tile_size,
+                                         uint32_t tile_width, uint32_t tile_height, int sort, int32_t* tiles_per_gauss,
+                                         lfs_alloc_fn alloc, void* alloc_ctx, int64_t** isect_ids, int32_t** flatten_ids,
+                                         int64_t* n_isects_host, void* stream_) {
+    using namespace lfs;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LFS_CHECK_ARG(alloc && isect_ids && flatten_ids && n_isects_host, "intersect_tile_packed: null callback / out pointer");
+    LFS_CHECK_ARG(tile_size > 0 && tile_width > 0 && tile_height > 0 && C > 0, "intersect_tile_packed: bad geometry");
+    LFS_CHECK_ARG(tile_width < 65536 && tile_height < 65536, "intersect_tile_packed: more than 65535 tiles per axis");
+    LFS_CHECK_ARG(nnz < (1u << 31), "intersect_tile_packed: nnz too large");
+    const uint32_t n = nnz, n_tiles = tile_width * tile_height;
+    const uint32_t tnb = ref_tile_n_bits(n_tiles), cnb = ref_tile_n_bits(C); // floor(log2) + 1, Intersect.cpp:46-47
+    LFS_CHECK_ARG(tnb + cnb <= 32, "intersect_tile_packed: camera and tile ids need %u bits (32 available)", tnb + cnb);
+    *isect_ids = nullptr;
+    *flatten_ids = nullptr;
+    *n_isects_host = 0;
+    if (n == 0)
+        return LFS_OK;
+    LFS_CHECK_ARG(means2d && radii && depths && camera_ids && tiles_per_gauss, "intersect_tile_packed: null input");
+
+    Carver ca(nullptr);
+    ca.take<TileRect>(n);
+    ca.take<uint32_t>(n), ca.take<uint32_t>(n), ca.take<uint32_t>(n), ca.take<uint32_t>(n), ca.take<uint32_t>(n);
+    ca.take<uint32_t>(4);
+    ca.take<char>(scan_scratch_bytes(n));
+    ca.take<char>(radix_scratch_bytes(n));
+    void* blob_a = alloc(alloc_ctx, LFS_TAG_SCRATCH, ca.total());
+    if (!blob_a) {
+        set_error("intersect_tile_packed: scratch allocation of %zu bytes failed", ca.total());
+        return LFS_ERR_ALLOC;
+    }
+    Carver a(blob_a);
+    TileRect* rects = a.take<TileRect>(n);
+    uint32_t *dk_a = a.take<uint32_t>(n), *dk_b = a.take<uint32_t>(n), *pm_a = a.take<uint32_t>(n), *pm_b = a.take<uint32_t>(n);
+    uint32_t* off = a.take<uint32_t>(n);
+    uint32_t* totals = a.take<uint32_t>(4);
+    void* scan_scr = a.take<char>(scan_scratch_bytes(n));
+    void* sort_scr = a.take<char>(radix_scratch_bytes(n));
+
+    int rc = launch_tile_count(means2d, radii, depths, n, (float)tile_size, tile_width, tile_height, tiles_per_gauss, rects,
+                               sort ? dk_a : nullptr, sort ? pm_a : nullptr, stream);
+    if (rc)
+        return rc;
+    const uint32_t* counts = reinterpret_cast<const uint32_t*>(tiles_per_gauss);
+    const uint32_t* perm = nullptr;
+    if (sort) { // level 1: all elements by depth bits (stable)
+        int in_b = 0;
+        rc = radix_sort_pairs(dk_a, pm_a, dk_b, pm_b, n, nullptr, 0, 32, sort_scr, &in_b, stream);
+        if (rc)
+            return rc;
+        perm = in_b ? pm_b : pm_a;
+    }
+    rc = exclusive_scan_u32(counts, perm, off, totals, n, nullptr, scan_scr, stream);
+    if (rc)
+        return rc;
+    uint32_t total = 0;
+    LFS_CUDA_OK(cudaMemcpyAsync(&total, totals, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    LFS_CUDA_OK(cudaStreamSynchronize(stream));
+    LFS_CHECK_ARG(total < (1u << 31), "intersect_tile_packed: n_isects %u does not fit int32 ids", total);
+    *n_isects_host = total;
+    if (total == 0)
+        return LFS_OK;
+    int64_t* ids = static_cast<int64_t*>(alloc(alloc_ctx, LFS_TAG_ISECT_IDS, sizeof(int64_t) * (size_t)total));
+    int32_t* flat = static_cast<int32_t*>(alloc(alloc_ctx, LFS_TAG_FLATTEN_IDS, sizeof(int32_t) * (size_t)total));
+    if (!ids || !flat) {
+        set_error("intersect_tile_packed: output allocation failed (n_isects=%u)", total);
+        return LFS_ERR_ALLOC;
+    }
+    const unsigned want = div_up(total, kIsThreads);
+    const unsigned grid = want < (unsigned)(num_sms() * 16) ? want : (unsigned)(num_sms() * 16);
+    if (!sort) {
+        k_emit_unsorted_packed<<<grid, kIsThreads, 0, stream>>>(off, n, camera_ids, rects, depths, tile_width, tnb, total, ids,
+                                                                flat);
+        LFS_LAUNCH_OK("k_emit_unsorted_packed");
+    } else { // level 2: (camera | tile) bits only, stable -> the order of the reference's 64-bit sort
+        Carver cb(nullptr);
+        cb.take<uint32_t>(total), cb.take<uint32_t>(total), cb.take<uint32_t>(total), cb.take<uint32_t>(total);
+        cb.take<char>(radix_scratch_bytes(total));
+        void* blob_b = alloc(alloc_ctx, LFS_TAG_SCRATCH, cb.total());
+        if (!blob_b) {
+            set_error("intersect_tile_packed: sort scratch allocation failed (n_isects=%u)", total);
+            return LFS_ERR_ALLOC;
+        }
+        Carver b(blob_b);
+        uint32_t *tk_a = b.take<uint32_t>(total), *tk_b = b.take<uint32_t>(total), *tv_a = b.take<uint32_t>(total),
+                 *tv_b = b.take<uint32_t>(total);
+        void* sort_scr_b = b.take<char>(radix_scratch_bytes(total));
+        rc = launch_emit_instances(perm, off, n, rects, tile_width, 0, total, nullptr, tk_a, tv_a, stream);
+        if (rc)
+            return rc;
+        k_add_camera_bits<<<div_up(total, kIsThreads), kIsThreads, 0, stream>>>(tk_a, tv_a, camera_ids, total, tnb);
+        LFS_LAUNCH_OK("k_add_camera_bits");
+        int in_b = 0;
+        rc = radix_sort_pairs(tk_a, tv_a, tk_b, tv_b, total, nullptr, 0, (int)(tnb + cnb), sort_scr_b, &in_b, stream);
+        if (rc)
+            return rc;
+        k_make_isect_ids<<<div_up(total, kIsThreads), kIsThreads, 0, stream>>>(in_b ? tk_b : tk_a, in_b ? tv_b : tv_a, depths,
+                                                                               total, 0, ids, flat);
+        LFS_LAUNCH_OK("k_make_isect_ids");
     }
     *isect_ids = ids;
     *flatten_ids = flat;

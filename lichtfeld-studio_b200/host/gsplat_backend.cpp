@@ -103,17 +103,29 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor> intersect_tile(const at::Tensor m
     CHECK_INPUT(means2d);
     CHECK_INPUT(radii);
     CHECK_INPUT(depths);
-    TORCH_CHECK(means2d.dim() == 3 && !camera_ids.has_value() && !gaussian_ids.has_value(),
-                "lfs_b200: the packed layout of intersect_tile is not implemented");
+    const bool packed = means2d.dim() == 2; // gsplat/Intersect.cpp:32-39
+    if (packed) {
+        TORCH_CHECK(camera_ids.has_value() && gaussian_ids.has_value(),
+                    "When packed is set, camera_ids and gaussian_ids must be provided.");
+        CHECK_INPUT(camera_ids.value());
+        CHECK_INPUT(gaussian_ids.value());
+    }
     at::Tensor tiles_per_gauss = at::empty_like(depths, depths.options().dtype(at::kInt));
     Alloc al{means2d.device(), {}, {}};
     int64_t* ids = nullptr;
     int32_t* flat = nullptr;
     int64_t n_isects = 0;
-    lfs_ok(lfs_intersect_tile(fp(means2d), radii.data_ptr<int32_t>(), fp(depths), C, (uint32_t)means2d.size(1),
-                              tile_size, tile_width, tile_height, sort ? 1 : 0, tiles_per_gauss.data_ptr<int32_t>(),
-                              &Alloc::fn, &al, &ids, &flat, &n_isects, cur_stream()),
-           "intersect_tile");
+    if (packed)
+        lfs_ok(lfs_intersect_tile_packed(fp(means2d), radii.data_ptr<int32_t>(), fp(depths),
+                                         camera_ids.value().data_ptr<int64_t>(), (uint32_t)means2d.size(0), C, tile_size,
+                                         tile_width, tile_height, sort ? 1 : 0, tiles_per_gauss.data_ptr<int32_t>(),
+                                         &Alloc::fn, &al, &ids, &flat, &n_isects, cur_stream()),
+               "intersect_tile (packed)");
+    else
+        lfs_ok(lfs_intersect_tile(fp(means2d), radii.data_ptr<int32_t>(), fp(depths), C, (uint32_t)means2d.size(1),
+                                  tile_size, tile_width, tile_height, sort ? 1 : 0, tiles_per_gauss.data_ptr<int32_t>(),
+                                  &Alloc::fn, &al, &ids, &flat, &n_isects, cur_stream()),
+               "intersect_tile");
     at::Tensor isect_ids, flatten_ids;
     if (n_isects > 0) {
         isect_ids = al.tagged[LFS_TAG_ISECT_IDS].view(at::kLong);

@@ -140,16 +140,23 @@ def intersect_tile(means2d, radii, depths, camera_ids, gaussian_ids, C_: int, ti
     """gsplat::intersect_tile (gsplat/Ops.h:28-38) -> (tiles_per_gauss, isect_ids, flatten_ids)."""
     lib = load()
     _chk(means2d, "means2d"), _chk(radii, "radii", torch.int32), _chk(depths, "depths")
-    if means2d.dim() == 2 or camera_ids is not None or gaussian_ids is not None:
-        raise _lib.LfsUnsupported(_lib.LFS_ERR_UNSUPPORTED, "intersect_tile: packed layout is not implemented")
-    N = means2d.shape[1]
+    packed = means2d.dim() == 2  # [nnz, 2]: every element carries its camera id (gsplat/Intersect.cpp:32-39)
+    if packed:
+        if camera_ids is None or gaussian_ids is None:
+            raise ValueError("When packed is set, camera_ids and gaussian_ids must be provided.")
+        _chk(camera_ids, "camera_ids", torch.int64), _chk(gaussian_ids, "gaussian_ids", torch.int64)
     dev = means2d.device
     tiles_per_gauss = torch.empty(depths.shape, dtype=torch.int32, device=dev)
     al = _Alloc(dev)
     ids_p, flat_p, n_is = C.c_void_p(), C.c_void_p(), C.c_int64(0)
-    check(lib.lfs_intersect_tile(_p(means2d), _p(radii), _p(depths), C_, N, tile_size, tile_width, tile_height,
-                                 1 if sort else 0, _p(tiles_per_gauss), al.cb, None, C.byref(ids_p), C.byref(flat_p),
-                                 C.byref(n_is), _stream()))
+    if packed:
+        check(lib.lfs_intersect_tile_packed(_p(means2d), _p(radii), _p(depths), _p(camera_ids), means2d.shape[0], C_,
+                                            tile_size, tile_width, tile_height, 1 if sort else 0, _p(tiles_per_gauss),
+                                            al.cb, None, C.byref(ids_p), C.byref(flat_p), C.byref(n_is), _stream()))
+    else:
+        check(lib.lfs_intersect_tile(_p(means2d), _p(radii), _p(depths), C_, means2d.shape[1], tile_size, tile_width,
+                                     tile_height, 1 if sort else 0, _p(tiles_per_gauss), al.cb, None, C.byref(ids_p),
+                                     C.byref(flat_p), C.byref(n_is), _stream()))
     n = int(n_is.value)
     if n == 0:
         return (tiles_per_gauss, torch.empty((0,), dtype=torch.int64, device=dev),

@@ -131,6 +131,18 @@ def diag_intersect():
             if srt:
                 off = ops.intersect_offset(ids, Cc, tw, th).cpu().numpy()
                 out[k + "_offsets_equal"] = bool(np.array_equal(off, O.intersect_offset(o_ids, Cc, tw, th)))
+            # packed layout (gsplat/Intersect.cpp:32-39): the visible elements only, each with its camera id; keys and order
+            # must be those of the [C,N] call, flatten_ids index the packed list
+            sel = np.flatnonzero((radii.reshape(-1, 2) > 0).all(-1))
+            if tag != "empty" and len(sel):
+                cam_ids = (sel // N).astype(np.int64)
+                p_tpg, p_ids, p_flat = ops.intersect_tile(T(m2d.reshape(-1, 2)[sel]), T(radii.reshape(-1, 2)[sel], torch.int32),
+                                                          T(dep.reshape(-1)[sel]), T(cam_ids, torch.int64),
+                                                          T((sel % N).astype(np.int64), torch.int64), Cc, 16, tw, th, srt)
+                out[k + "_packed_tpg_equal"] = bool(np.array_equal(p_tpg.cpu().numpy(), o_tpg.reshape(-1)[sel]))
+                out[k + "_packed_ids_equal"] = bool(p_ids.numel() == len(o_ids) and np.array_equal(p_ids.cpu().numpy(), o_ids))
+                out[k + "_packed_flat_equal"] = bool(p_flat.numel() == len(o_flat)
+                                                     and np.array_equal(sel[p_flat.cpu().numpy()], o_flat))
             if R.have_gsplat() and tag != "empty":
                 r_tpg, r_ids, r_flat = R.intersect_tile(T(m2d), T(radii, torch.int32), T(dep), 16, tw, th, srt)
                 out[k + "_ref_tpg_equal"] = bool(torch.equal(tpg, r_tpg))
