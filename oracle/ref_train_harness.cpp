@@ -295,6 +295,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("intersect_tile", [](Tensor means2d, Tensor radii, Tensor depths, int C, int tile_size, int tw, int th, bool sort) {
         return gsplat::intersect_tile(means2d, radii, depths, {}, {}, C, tile_size, tw, th, sort);
     });
+    m.def("intersect_tile_packed", [](Tensor means2d, Tensor radii, Tensor depths, Tensor camera_ids, Tensor gaussian_ids, int C,
+                                      int tile_size, int tw, int th, bool sort) {
+        return gsplat::intersect_tile(means2d, radii, depths, camera_ids, gaussian_ids, C, tile_size, tw, th, sort);
+    });
     m.def("intersect_offset", &gsplat::intersect_offset);
 #ifdef LFS_B200_LEGACY_OPS
     // legacy 2-D op surface of the reference's gtests: host layer -> C ABI -> csrc/legacy2d.cu

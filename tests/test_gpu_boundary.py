@@ -163,6 +163,16 @@ def test_intersect_ops_on_both_backends(mods):
     for x, y in zip(a, b):
         assert x.shape == y.shape and torch.equal(x, y)
     assert torch.equal(ref.intersect_offset(a[1], Cc, tw, th), b200.intersect_offset(b[1], Cc, tw, th))
+    # packed layout (gsplat/Intersect.cpp:32-39): a shuffled subset of the elements, each with its camera id
+    sel = torch.as_tensor(rng.permutation(Cc * N)[: Cc * N // 2].copy(), device="cuda")
+    pm, pr, pd = m2d.reshape(-1, 2)[sel].contiguous(), radii.reshape(-1, 2)[sel].contiguous(), dep.reshape(-1)[sel].contiguous()
+    cam, gid = (sel // N).contiguous(), (sel % N).contiguous()
+    for srt in (True, False):
+        a = ref.intersect_tile_packed(pm, pr, pd, cam, gid, Cc, 16, tw, th, srt)
+        b = b200.intersect_tile_packed(pm, pr, pd, cam, gid, Cc, 16, tw, th, srt)
+        assert a[1].numel() > 10000
+        for x, y in zip(a, b):
+            assert x.shape == y.shape and torch.equal(x, y), srt
 
 
 CAMERA_CASES = [
