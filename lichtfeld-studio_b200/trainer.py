@@ -151,11 +151,16 @@ class SplatTrainer:
         self.params, self.grads = new_p, new_g
         # NVSwitch multicast (NVLS) addresses of the same buffers, 0 when the fabric has none.  The in-switch variant
         # (multimem.ld_reduce / multimem.st: the reduction happens inside the switch, 1/W of the inbound traffic) is used
-        # whenever the fabric offers it; LFS_P2P_MULTICAST=0 falls back to plain peer loads / stores (tools/check_p2p.py
-        # validates both against ncclAllReduce + Adam)
+        # from 4 ranks on when the fabric offers it, plain peer loads / stores otherwise (tools/check_p2p.py validates both
+        # against ncclAllReduce + Adam)
         self._mc_grads = int(getattr(self._h_grads, "multicast_ptr", 0) or 0)
         self._mc_params = int(getattr(self._h_params, "multicast_ptr", 0) or 0)
-        if os.environ.get("LFS_P2P_MULTICAST", "1") == "0" or not (self._mc_grads and self._mc_params):
+        # measured (profiles/r02_bench_{2,8}gpu_*.json): at 8 GPUs the in-switch reduction wins (15.58 vs 15.68 ms per step) and
+        # is bit-identical to ncclAllReduce + Adam; at 2 GPUs a rank's own half would cross NVLink twice and plain peer
+        # loads are faster (15.23 vs 15.66 ms).  LFS_P2P_MULTICAST=1 / 0 forces either.
+        want = os.environ.get("LFS_P2P_MULTICAST", "auto")
+        use_mc = want == "1" or (want != "0" and self._p2p_world >= 4)
+        if not use_mc or not (self._mc_grads and self._mc_params):
             self._mc_grads = self._mc_params = 0
         self.p2p = True
 
