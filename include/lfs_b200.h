@@ -433,9 +433,11 @@ int lfs_trainer_set_profile(void* trainer, int enable);
 int lfs_trainer_get_profile(void* trainer, float* mean_ms /* [LFS_PROF_STAGES] */, int* counts /* or NULL */);
 
 /* library options (A/B switches between kernels that compute the same thing; the defaults are the measured best):
- *   "fwd_variant"  0 forward blend with TMA-gathered records (cp.async.bulk + mbarrier), 1 register-staged gather
+ *   "fwd_variant"  0 forward blend with TMA-gathered records (cp.async.bulk + mbarrier), 1 register-staged gather (round 1),
+ *                  2 = 0 bounded to 80 registers (12 CTAs per SM)
  *   "bwd_variant"  0 software-pipelined backward blend on a persistent grid over the live-bucket list, 1 lock-step backward
- *                  blend (round 1), 2 software-pipelined with one warp per bucket (no list)
+ *                  blend (round 1), 2 software-pipelined with one warp per bucket (no list), 3 = 0 bounded to 80 registers
+ *                  (6 CTAs per SM)
  *   "sort_variant" 0 histogram / scan / scatter radix passes, 1 onesweep (decoupled look-back) passes, 2 onesweep for keys
  *                  of <= 16 bits only, 3 the passes of 0 with ballot ranking, 4 = 2 + 3 (A/B switches, all bit-identical
  *                  results)

@@ -487,8 +487,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <bool EWA>
-__global__ void __launch_bounds__(kFwdThreads)
+template <bool EWA, int kMinBlocks = 10>
+__global__ void __launch_bounds__(kFwdThreads, kMinBlocks)
     k_blend_fwd_tg(const RasterBuffers rb, const ViewCam* __restrict__ cams, const uint32_t width, const uint32_t height,
                    const uint32_t tile_w, const uint32_t tile_h, const bool write_ckpt,
                    const float* __restrict__ backgrounds, const uint8_t* __restrict__ masks, float* __restrict__ renders,
@@ -782,6 +782,9 @@ int launch_blend_fwd(const RasterBuffers& rb, const ViewCam* cams_dev, uint32_t 
     if (raster_options().fwd_variant == 1)
         k_blend_fwd<false, true><<<grid, kFwdThreads, 0, stream>>>(rb, cams_dev, width, height, tile_w, tile_h, write_ckpt,
                                                                   backgrounds, masks, renders, alphas, last_ids);
+    else if (raster_options().fwd_variant == 2) // A/B: 12 CTAs per SM at 80 registers
+        k_blend_fwd_tg<false, 12><<<grid, kFwdThreads, 0, stream>>>(rb, cams_dev, width, height, tile_w, tile_h, write_ckpt,
+                                                                   backgrounds, masks, renders, alphas, last_ids);
     else
         k_blend_fwd_tg<false><<<grid, kFwdThreads, 0, stream>>>(rb, cams_dev, width, height, tile_w, tile_h, write_ckpt,
                                                                backgrounds, masks, renders, alphas, last_ids);
@@ -1383,9 +1386,10 @@ __device__ __forceinline__ void bwd_sp_bucket(const uint32_t b, const int lane, 
 // so that the ~86 % of the buckets no pixel reaches (C3: 32 k live of 232 k) cost nothing: with one warp per bucket they
 // still cost a CTA slot and three dependent loads each, and a CTA with one live and three dead buckets held the registers
 // of four warps (measured: 13.5 of the 20 possible warps per SM active).  Without the list: one warp per bucket.
-constexpr int kBwdBlocksPerSM = 5; // 94 registers x 128 threads
-template <bool EWA, int kBwdWarps>
-__global__ void __launch_bounds__(kBwdWarps * 32)
+// kMinBlocks = CTAs per SM the register allocation is bounded for (5: 96 registers, 6: 80 registers, neither spills) and the
+// persistent grid is sized with.
+template <bool EWA, int kBwdWarps, int kMinBlocks>
+__global__ void __launch_bounds__(kBwdWarps * 32, kMinBlocks)
     k_blend_bwd_sp(const RasterBuffers rb, const ViewCam* __restrict__ cams, const float4* __restrict__ v_pix,
                    const float* __restrict__ quats, const float* __restrict__ scales, const float* __restrict__ means,
                    const uint32_t N, const uint32_t width, const uint32_t height, const uint32_t tile_w,
@@ -1421,11 +1425,11 @@ __global__ void __launch_bounds__(kBwdWarps * 32)
     }
 }
 
-static unsigned bwd_sp_grid(const RasterBuffers& rb, const uint32_t n_bucket_cap) {
+static unsigned bwd_sp_grid(const RasterBuffers& rb, const uint32_t n_bucket_cap, const int blocks_per_sm) {
     const unsigned dense = div_up(n_bucket_cap, 4);
-    if (rb.live == nullptr || raster_options().bwd_variant == 1)
+    if (rb.live == nullptr)
         return dense;
-    const unsigned persistent = (unsigned)(num_sms() * kBwdBlocksPerSM);
+    const unsigned persistent = (unsigned)(num_sms() * blocks_per_sm);
     return persistent < dense ? persistent : dense;
 }
 
@@ -1447,7 +1451,12 @@ int launch_blend_bwd(const RasterBuffers& rb, const ViewCam* cams_dev, const flo
             rbl.live = nullptr;
         if (rbl.live) // work counter of the persistent grid (a forward may be followed by more than one backward)
             LFS_CUDA_OK(cudaMemsetAsync(rbl.live + 1, 0, sizeof(uint32_t), stream));
-        k_blend_bwd_sp<false, 4><<<bwd_sp_grid(rbl, n_bucket_cap), 4 * 32, 0, stream>>>(
+        if (raster_options().bwd_variant == 3) // A/B: 6 CTAs per SM at 80 registers
+            k_blend_bwd_sp<false, 4, 6><<<bwd_sp_grid(rbl, n_bucket_cap, 6), 4 * 32, 0, stream>>>(
+            rbl, cams_dev, v_pix, quats, scales, means, N, width, height, tile_w, tile_h, n_bucket_cap, n_buckets_dev,
+            v_means, v_quats, v_scales, v_colors, v_opacities);
+        else
+            k_blend_bwd_sp<false, 4, 5><<<bwd_sp_grid(rbl, n_bucket_cap, 5), 4 * 32, 0, stream>>>(
             rbl, cams_dev, v_pix, quats, scales, means, N, width, height, tile_w, tile_h, n_bucket_cap, n_buckets_dev,
             v_means, v_quats, v_scales, v_colors, v_opacities);
     }
@@ -1470,7 +1479,12 @@ int launch_blend_bwd_ewa(const RasterBuffers& rb, const float4* v_pix, uint32_t 
             rbl.live = nullptr;
         if (rbl.live) // work counter of the persistent grid (a forward may be followed by more than one backward)
             LFS_CUDA_OK(cudaMemsetAsync(rbl.live + 1, 0, sizeof(uint32_t), stream));
-        k_blend_bwd_sp<true, 4><<<bwd_sp_grid(rbl, n_bucket_cap), 4 * 32, 0, stream>>>(
+        if (raster_options().bwd_variant == 3) // A/B: 6 CTAs per SM at 80 registers
+            k_blend_bwd_sp<true, 4, 6><<<bwd_sp_grid(rbl, n_bucket_cap, 6), 4 * 32, 0, stream>>>(
+            rbl, nullptr, v_pix, nullptr, nullptr, nullptr, N, width, height, tile_w, tile_h, n_bucket_cap, n_buckets_dev,
+            v_mean2d, v_conic, nullptr, v_color, v_raw_opacity);
+        else
+            k_blend_bwd_sp<true, 4, 5><<<bwd_sp_grid(rbl, n_bucket_cap, 5), 4 * 32, 0, stream>>>(
             rbl, nullptr, v_pix, nullptr, nullptr, nullptr, N, width, height, tile_w, tile_h, n_bucket_cap, n_buckets_dev,
             v_mean2d, v_conic, nullptr, v_color, v_raw_opacity);
     }

@@ -58,8 +58,9 @@ struct RasterBuffers {
 // Tunables (process-wide; set through lfs_set_option).  The *_variant switches select kernels that compute the same
 // thing (A/B measurements); they may be changed at any time.
 struct RasterOptions {
-    int fwd_variant = 0; // forward blend: 0 TMA-gathered records (default), 1 register-staged gather (round 1)
-    int bwd_variant = 0; // backward blend: 0 software-pipelined (default), 1 lock-step (round 1)
+    int fwd_variant = 0; // forward blend: 0 TMA-gathered records (default), 1 register-staged gather (round 1), 2 = 0 at 80 regs
+    int bwd_variant = 0; // backward blend: 0 software-pipelined, persistent over live buckets (default), 1 lock-step (round 1),
+                         // 2 = 0 with one warp per bucket, 3 = 0 at 80 registers / 6 CTAs per SM
     int pre_bwd_split = 1; // trainer: SH / geometry halves of the per-Gaussian backward as two launches (A/B switch)
     int exact_cull = 1; // trainer: drop (tile, Gaussian) instances that provably hold no alpha >= 1/255 (intersect.cuh CullRec)
 };
