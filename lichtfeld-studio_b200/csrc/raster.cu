@@ -162,17 +162,27 @@ __device__ __forceinline__ void store_rec_pk(float4* d, const float4 A, const fl
 // thread per tile (a few microseconds; as an epilogue of the forward kernel it cost 5 % of that kernel).
 __global__ void __launch_bounds__(256) k_live_buckets(const RasterBuffers rb, const uint32_t n_tiles_total) {
     const uint32_t ft = blockIdx.x * 256 + threadIdx.x;
-    if (ft >= n_tiles_total)
-        return;
-    const int32_t start = rb.tile_off[ft], end = rb.tile_off[ft + 1];
-    const uint32_t cnt_raw = end > start ? (uint32_t)(end - start) : 0u;
-    const uint32_t nb = (cnt_raw + kBucket - 1) / kBucket;
-    const uint32_t tmax = rb.tile_max_contrib[ft];
-    const uint32_t n_live = min(nb, (tmax + kBucket - 1) / kBucket);
-    if (n_live == 0)
-        return;
-    const uint32_t boff = rb.bucket_off[ft];
-    const uint32_t base = atomicAdd(rb.live, n_live);
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t n_live = 0, boff = 0;
+    if (ft < n_tiles_total) {
+        const int32_t start = rb.tile_off[ft], end = rb.tile_off[ft + 1];
+        const uint32_t cnt_raw = end > start ? (uint32_t)(end - start) : 0u;
+        const uint32_t nb = (cnt_raw + kBucket - 1) / kBucket;
+        n_live = min(nb, (rb.tile_max_contrib[ft] + kBucket - 1) / kBucket);
+        boff = rb.bucket_off[ft];
+    }
+    // one atomic per warp (8160 same-address atomics took longer than the rest of the kernel)
+    uint32_t incl = n_live;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o)
+            incl += y;
+    }
+    uint32_t base = 0;
+    if (lane == 31 && incl)
+        base = atomicAdd(rb.live, incl);
+    base = __shfl_sync(0xffffffffu, base, 31) + incl - n_live;
     for (uint32_t k = 0; k < n_live; ++k)
         rb.live[2 + base + k] = boff + k;
 }
