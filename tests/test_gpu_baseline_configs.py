@@ -232,8 +232,11 @@ def _fastgs_vs_reference(cfg):
     rep["ref_counts"] = (int(r[6]), int(r[7]), int(r[8]))
     assert abs(ctx.n_visible_primitives - r[6]) <= 2, rep
     assert abs(ctx.n_instances - r[7]) <= 2 + r[7] // 5000, rep
-    gate_render(rep, "image", img, rimg)
-    gate_render(rep, "alpha", alpha, ralpha)
+    # measured over the runs of round 2: 99.967 .. 99.9993 % of the values inside the 1e-4 band, largest deviation 3.0e-3 (one
+    # alpha = 1/255 contribution): a handful of (tile, primitive) instances sit on the other side of the reference's exact tile
+    # test (n_instances differ by one at C3) and every such instance touches up to 256 pixels -> 99.9 % here
+    gate_render(rep, "image", img, rimg, min_frac=0.999)
+    gate_render(rep, "alpha", alpha, ralpha, min_frac=0.999)
     g = torch.Generator(device="cuda").manual_seed(2)
     gi = torch.randn(img.shape, device="cuda", generator=g)
     ga = torch.randn(alpha.shape, device="cuda", generator=g)
