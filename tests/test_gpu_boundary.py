@@ -62,12 +62,17 @@ def test_fastgs_callers_on_both_backends(mods):
     nb = (sc.sh_degree + 1) ** 2
     a = hr.view_grads(c["w2c"], c["campos"], c["k"], c["gt"], bg, 0.2, nb, sc.width, sc.height)
     b = hb.view_grads(c["w2c"], c["campos"], c["k"], c["gt"], bg, 0.2, nb, sc.width, sc.height)
-    gate_render(rep, "image", b[0], a[0])
-    gate_render(rep, "alpha", b[1], a[1])
+    # one (tile, primitive) instance on the boundary of the exact tile test, or one glitch of the reference's racy instance
+    # creation (see test_gpu_baseline_configs._fastgs_vs_reference), moves up to 256 pixels and one primitive's gradients:
+    # the element-wise fractions are the gate, the per-tensor maxima are bounded by one such event
+    gate_render(rep, "image", b[0], a[0], min_frac=0.999)
+    gate_render(rep, "alpha", b[1], a[1], min_frac=0.999)
     assert abs(float(a[2]) - float(b[2])) <= 1e-5 * abs(float(a[2])), (float(a[2]), float(b[2]))
     for name, x, y in zip(GRADS, b[3:], a[3:]):
-        gate(rep, "grad_" + name, x, y, 1e-3, 0.99)
-    assert torch.equal(hr.densification_info[0], hb.densification_info[0])  # visibility counts
+        mn, fr = strict(x, y, 1e-3)
+        rep["grad_" + name] = {"maxnorm": mn, "elementwise_pass_frac": fr, "rtol": 1e-3}
+        assert fr >= 0.999 and mn <= 1e-2, (name, rep["grad_" + name])
+    assert int((hr.densification_info[0] != hb.densification_info[0]).sum()) <= 2  # visibility counts
     gate(rep, "densification_norm", hb.densification_info[1], hr.densification_info[1], 1e-3, 0.99)
     print("fastgs callers:", rep)
 
