@@ -165,6 +165,29 @@ def reference_gpu_leg(path: str, config: str, n_gaussians: int, views: int, step
     return {"error": tail[-1][:300] if tail else f"exit code {r.returncode}"}
 
 
+def stage_roofline(prof, n, I, P, deg, peak):
+    """Algorithmic bytes per view of every stage (BASELINE.md section 5 formulas) over its measured time,
+    as a fraction of the measured HBM peak.  The blend stages are FP32/SFU-issue bound (their real DRAM traffic is a
+    fraction of these bytes), the per-Gaussian and sort stages stream."""
+    K = (deg + 1) ** 2
+    G = float(n)
+    bytes_of = {
+        "preprocess_fwd": (44 + 12 * K + 12) * G + 96 * G,        # raw params + SH + GaussRec / CullRec / keys out
+        "sort_intersect": 24 * G * 3 + 12 * I + 16 * I * 2 + 8 * I,  # 3 depth passes, emit, 2 tile passes, offsets
+        "blend_fwd": 60 * I + 20 * P,
+        "loss": 108 * P,
+        "blend_bwd": 172 * I + 24 * P,
+        "preprocess_bwd": (2 * 4 * (11 + 3 * K) + 64) * G,         # gradient planes read-modify-write + view accumulators
+    }
+    out = {}
+    for k, b in bytes_of.items():
+        ms = prof.get(k, 0.0)
+        if ms > 0:
+            gbs = b / (ms * 1e-3) / 1e9
+            out[k] = {"algorithmic_bytes": b, "ms": ms, "GBps": gbs, "frac_of_hbm_peak": gbs / peak if peak else None}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------------------
 def main():
     a = parse()
@@ -382,8 +405,7 @@ def main():
         "stage_ms_per_view": prof,
         "stage_ms_note": "profiling pass with a blocking event pair per stage (views do not overlap): the sum exceeds "
                          "ms_per_step / views_per_gpu by the overlap the timed run gets",
-        "stage_roofline": {"blend_fwd_GBps": fwd_bytes / (prof.get("blend_fwd", 0) * 1e-3) / 1e9
-                           if prof.get("blend_fwd", 0) > 0 else None},
+        "stage_roofline": stage_roofline(prof, n, I, P, deg, peak),
     }
     if world > 1:
         # exchange step: every rank sends / receives (W-1)/W of the gradient arena (reduce-scatter) and of the parameter
