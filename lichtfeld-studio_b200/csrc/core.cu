@@ -58,6 +58,10 @@ extern "C" int lfs_set_option(const char* name, int value) {
         lfs::raster_options().exact_cull = value;
         return LFS_OK;
     }
+    if (name && std::string(name) == "fg_variant") {
+        lfs::raster_options().fg_variant = value;
+        return LFS_OK;
+    }
     if (name && std::string(name) == "sort_variant") {
         lfs::set_sort_variant(value);
         return LFS_OK;

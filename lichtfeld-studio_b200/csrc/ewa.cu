@@ -257,6 +257,139 @@ __global__ void __launch_bounds__(128)
     atomicAdd(n_visible, 1u);
 }
 
+__global__ void __launch_bounds__(128)
+    k_fg_preprocess_coop(const float* __restrict__ means, const float* __restrict__ raw_scales,
+                    const float4* __restrict__ raw_rotations, const float* __restrict__ raw_opacities,
+                    const float* __restrict__ sh0, const float* __restrict__ sh_rest, const float4* __restrict__ w2c,
+                    const float* __restrict__ cam_position, const uint32_t N, const uint32_t grid_w,
+                    const uint32_t grid_h, const int active, const int total_rest, const float w, const float h,
+                    const float fx, const float fy, const float cx, const float cy, const float near_, const float far_,
+                    GaussRec* __restrict__ gauss, TileRect* __restrict__ rects, int32_t* __restrict__ counts,
+                    unsigned long long* __restrict__ masks, uint32_t* __restrict__ depth_keys,
+                    uint32_t* __restrict__ ident, uint32_t* __restrict__ n_visible) {
+    // Same results as k_fg_preprocess; the exact tile tests of a warp's 32 primitives are spread evenly over its lanes
+    // (k_fg_preprocess: every lane walks its own rectangle, 11.7 of 32 lanes active per instruction, 68 % issue-bound).
+    __shared__ __align__(16) float s_sh[128 * 45];
+    __shared__ float s_par[4][6][32];          // mx - 0.5, my - 0.5, conic a b c, power threshold
+    __shared__ uint32_t s_geo[4][32];          // x0 | y0 << 12 | w << 24
+    __shared__ uint32_t s_rcp[4][32];          // ceil(65536 / w)
+    __shared__ uint32_t s_pre[4][33];
+    __shared__ unsigned long long s_mask[4][32];
+    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    if (active > 1)
+        fg_stage_rows(sh_rest, s_sh, blockIdx.x * 128u, N, 3u * (uint32_t)total_rest);
+    bool alive = i < N;
+    f3 mean = mk3(0.f, 0.f, 0.f);
+    float depth = 0.f, opacity = 0.f, ca = 0.f, cb = 0.f, cc = 0.f, mx = 0.f, my = 0.f, pt = 0.f;
+    uint32_t x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+    if (alive) {
+        ident[i] = i;
+        counts[i] = 0;
+        rects[i] = TileRect{0, 0, 0, 0};
+        depth_keys[i] = 0xFFFFFFFFu;
+        mean = mk3(means[3 * (size_t)i], means[3 * (size_t)i + 1], means[3 * (size_t)i + 2]);
+        const float4 r1 = w2c[0], r2 = w2c[1], r3 = w2c[2];
+        FgGeom G;
+        fg_geometry(mean, mk3(raw_scales[3 * (size_t)i], raw_scales[3 * (size_t)i + 1], raw_scales[3 * (size_t)i + 2]),
+                    raw_rotations[i], r1, r2, r3, w, h, fx, fy, cx, cy, G);
+        depth = G.depth;
+        opacity = 1.0f / (1.0f + expf(-raw_opacities[i]));
+        const float det = G.a * G.c - G.b * G.b;
+        alive = !(G.depth < near_ || G.depth > far_) && !(opacity < 1.0f / kFgMinAlphaRcp || G.qn2 < 1e-8f) &&
+                (det >= 1e-8f); // :61-62, :75, :84, :146 (also rejects NaN)
+        if (alive) {
+            ca = G.c / det, cb = -G.b / det, cc = G.a / det;
+            mx = G.x * fx + cx, my = G.y * fy + cy;
+            pt = logf(opacity * kFgMinAlphaRcp);
+            const float ptf = sqrtf(2.0f * pt);
+            const float ex = fmaxf(ptf * sqrtf(G.a) - 0.5f, 0.0f), ey = fmaxf(ptf * sqrtf(G.c) - 0.5f, 0.0f);
+            x0 = min(grid_w, (uint32_t)max(0, __float2int_rd((mx - ex) / (float)kTile)));
+            x1 = min(grid_w, (uint32_t)max(0, __float2int_ru((mx + ex) / (float)kTile)));
+            y0 = min(grid_h, (uint32_t)max(0, __float2int_rd((my - ey) / (float)kTile)));
+            y1 = min(grid_h, (uint32_t)max(0, __float2int_ru((my + ey) / (float)kTile)));
+            alive = x1 > x0 && y1 > y0;
+        }
+    }
+    const uint32_t rw = alive ? x1 - x0 : 0u, area = alive ? rw * (y1 - y0) : 0u;
+    const uint32_t a_coop = area <= 64u ? area : 0u;
+    uint32_t incl = a_coop;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o)
+            incl += y;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    s_pre[warp][lane] = incl - a_coop;
+    if (lane == 31)
+        s_pre[warp][32] = total;
+    s_par[warp][0][lane] = mx - 0.5f, s_par[warp][1][lane] = my - 0.5f, s_par[warp][2][lane] = ca;
+    s_par[warp][3][lane] = cb, s_par[warp][4][lane] = cc, s_par[warp][5][lane] = pt;
+    s_geo[warp][lane] = x0 | (y0 << 12) | (rw << 24);
+    s_rcp[warp][lane] = rw ? (65536u + rw - 1u) / rw : 0u;
+    s_mask[warp][lane] = 0ull;
+    __syncwarp();
+    for (uint32_t t = lane; t < total; t += 32u) {
+        uint32_t lo = 0, hi = 32;
+#pragma unroll
+        for (int it = 0; it < 5; ++it) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (s_pre[warp][mid] <= t)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const uint32_t k = t - s_pre[warp][lo];
+        const uint32_t geo = s_geo[warp][lo];
+        const uint32_t row = (k * s_rcp[warp][lo]) >> 16, col = k - row * (geo >> 24);
+        if (fg_tile_test(s_par[warp][0][lo], s_par[warp][1][lo], s_par[warp][2][lo], s_par[warp][3][lo], s_par[warp][4][lo],
+                         (geo & 0xfffu) + col, ((geo >> 12) & 0xfffu) + row, s_par[warp][5][lo]))
+            atomicOr(&s_mask[warp][lo], 1ull << k);
+    }
+    __syncwarp();
+    __syncthreads(); // the staged SH rows
+    if (!alive)
+        return;
+    uint32_t nt = 0;
+    unsigned long long mask = 0ull;
+    if (area <= 64u) {
+        mask = s_mask[warp][lane];
+        nt = (uint32_t)__popcll(mask);
+    } else {
+        for (uint32_t ty = y0; ty < y1; ++ty)
+            for (uint32_t tx = x0; tx < x1; ++tx)
+                nt += fg_will_contribute(mx - 0.5f, my - 0.5f, ca, cb, cc, tx, ty, pt) ? 1u : 0u;
+    }
+    if (nt == 0)
+        return;
+    masks[i] = mask;
+    // colour, kernel_utils.cuh:15-39
+    f3 col = mk3(0.5f + 0.28209479177387814f * sh0[3 * (size_t)i], 0.5f + 0.28209479177387814f * sh0[3 * (size_t)i + 1],
+                 0.5f + 0.28209479177387814f * sh0[3 * (size_t)i + 2]);
+    if (active > 1) {
+        const f3 d = mk3(mean.x - cam_position[0], mean.y - cam_position[1], mean.z - cam_position[2]);
+        const float inv = rsqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+        float b[15];
+        const int nb = fg_sh_basis(active, d.x * inv, d.y * inv, d.z * inv, b);
+        const float* c = s_sh + 3 * (size_t)threadIdx.x * total_rest;
+#pragma unroll
+        for (int j = 0; j < 15; ++j)
+            if (j < nb) {
+                col.x = fmaf(b[j], c[3 * j], col.x), col.y = fmaf(b[j], c[3 * j + 1], col.y);
+                col.z = fmaf(b[j], c[3 * j + 2], col.z);
+            }
+    }
+    counts[i] = (int32_t)nt;
+    rects[i] = TileRect{(unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1};
+    depth_keys[i] = __float_as_uint(depth);
+    float4* og = reinterpret_cast<float4*>(gauss + i);
+    og[0] = make_float4(mx, my, ca, cb);
+    og[1] = make_float4(cc, opacity, col.x, col.y);
+    og[2] = make_float4(col.z, pt, 0.f, 0.f);
+    atomicAdd(n_visible, 1u);
+}
+
 // Instance emission with the exact tile test (kernels_forward.cuh:221-320): one thread per slot of the depth order
 // re-evaluates the test over its rectangle (same function, same inputs as the count in k_fg_preprocess) and writes its
 // run; see k_emit_instances for why this beats the warp-cooperative walk.
@@ -302,6 +435,104 @@ __global__ void __launch_bounds__(256)
                     vals[pos] = g;
                     ++pos;
                 }
+    }
+}
+
+// Warp-cooperative emission.  k_fg_emit gives every primitive to one thread, so a warp runs as long as its largest
+// rectangle and its stores scatter (measured: 6.6 of 32 lanes active per instruction, 0.16 ms at C3).  Here a warp takes 32
+// consecutive slots of the depth order, the instances of all of them form ONE contiguous output range (off is their
+// exclusive scan), and instance t of that range is written by lane t mod 32: its owner is found by a binary search in the
+// warp's prefix sums, its tile is the k-th set bit of the owner's mask.  Rectangles of more than 64 tiles (no mask) are
+// walked by their owner lane afterwards.
+constexpr int kEmitWarps = 8;
+__global__ void __launch_bounds__(kEmitWarps * 32)
+    k_fg_emit_coop(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ off, const uint32_t n_gauss,
+                   const TileRect* __restrict__ rects, const int32_t* __restrict__ counts,
+                   const unsigned long long* __restrict__ masks, const GaussRec* __restrict__ gauss, const uint32_t tile_w,
+                   const uint32_t n_cap, uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ vals) {
+    __shared__ uint32_t s_pre[kEmitWarps][33];
+    __shared__ unsigned long long s_mask[kEmitWarps][32];
+    __shared__ uint32_t s_geo[kEmitWarps][32];  // x0 | y0 << 12 | w << 24
+    __shared__ uint32_t s_rcp[kEmitWarps][32];  // ceil(65536 / w): bit / w == (bit * rcp) >> 16 for bit < 64
+    __shared__ uint32_t s_base[kEmitWarps][32]; // first output position of the owner
+    __shared__ uint32_t s_gid[kEmitWarps][32];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t n_groups = (n_gauss + 31u) / 32u;
+    for (uint32_t grp = blockIdx.x * kEmitWarps + warp; grp < n_groups; grp += gridDim.x * kEmitWarps) {
+        const uint32_t slot = grp * 32u + lane;
+        uint32_t g = 0, cnt = 0, base = 0;
+        TileRect r{0, 0, 0, 0};
+        if (slot < n_gauss) {
+            g = __ldg(perm + slot);
+            const int32_t c = counts[g];
+            if (c > 0) {
+                cnt = (uint32_t)c;
+                r = rects[g];
+                base = __ldg(off + slot);
+            }
+        }
+        const uint32_t w = (uint32_t)(r.x1 - r.x0), area = w * (uint32_t)(r.y1 - r.y0);
+        const bool big = cnt > 0 && area > 64u;
+        const uint32_t c_coop = big ? 0u : cnt;
+        uint32_t incl = c_coop;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t)o)
+                incl += y;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        s_pre[warp][lane] = incl - c_coop;
+        if (lane == 31)
+            s_pre[warp][32] = total;
+        s_mask[warp][lane] = c_coop ? masks[g] : 0ull;
+        s_geo[warp][lane] = (uint32_t)r.x0 | ((uint32_t)r.y0 << 12) | (w << 24);
+        s_rcp[warp][lane] = w ? (65536u + w - 1u) / w : 0u;
+        s_base[warp][lane] = base;
+        s_gid[warp][lane] = g;
+        __syncwarp();
+        for (uint32_t t = lane; t < total; t += 32u) {
+            // owner = last lane whose exclusive prefix is <= t (lanes without instances share their successor's prefix and
+            // are skipped by taking the LAST such lane ... that has instances: pre[o] <= t < pre[o + 1])
+            uint32_t lo = 0, hi = 32;
+#pragma unroll
+            for (int it = 0; it < 5; ++it) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (s_pre[warp][mid] <= t)
+                    lo = mid;
+                else
+                    hi = mid;
+            }
+            const uint32_t o = lo;
+            const uint32_t k = t - s_pre[warp][o];
+            const unsigned long long m = s_mask[warp][o];
+            const uint32_t mlo = (uint32_t)m, mhi = (uint32_t)(m >> 32);
+            const uint32_t clo = (uint32_t)__popc(mlo);
+            const uint32_t bit = k < clo ? __fns(mlo, 0, (int)k + 1) : 32u + __fns(mhi, 0, (int)(k - clo) + 1);
+            const uint32_t geo = s_geo[warp][o];
+            const uint32_t row = (bit * s_rcp[warp][o]) >> 16;
+            const uint32_t col = bit - row * (geo >> 24);
+            const uint32_t pos = s_base[warp][o] + k;
+            if (pos < n_cap) {
+                tile_keys[pos] = (((geo >> 12) & 0xfffu) + row) * tile_w + (geo & 0xfffu) + col;
+                vals[pos] = s_gid[warp][o];
+            }
+        }
+        if (big) { // the old walk, by the owner
+            const float4* gp = reinterpret_cast<const float4*>(gauss + g);
+            const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1), g2 = __ldg(gp + 2);
+            const float mx = g0.x - 0.5f, my = g0.y - 0.5f, ca = g0.z, cb = g0.w, cc = g1.x, pt = g2.y;
+            uint32_t pos = base;
+            const uint32_t end = base + cnt;
+            for (uint32_t ty = r.y0; ty < r.y1; ++ty)
+                for (uint32_t tx = r.x0; tx < r.x1; ++tx)
+                    if (fg_will_contribute(mx, my, ca, cb, cc, tx, ty, pt) && pos < end && pos < n_cap) {
+                        tile_keys[pos] = ty * tile_w + tx;
+                        vals[pos] = g;
+                        ++pos;
+                    }
+        }
+        __syncwarp();
     }
 }
 
@@ -606,6 +837,7 @@ extern "C" int lfs_fastgs_forward(const float* means, const float* scales_raw, c
     const uint32_t tile_w = (width + kTile - 1) / kTile, tile_h = (height + kTile - 1) / kTile, n_tiles = tile_w * tile_h;
     const uint32_t npix = (uint32_t)width * (uint32_t)height;
     LFS_UNSUPPORTED(n_tiles > 65535u, "fastgs_forward: %u tiles exceed the reference's 16-bit tile keys", n_tiles);
+    LFS_UNSUPPORTED(tile_w > 4095u || tile_h > 4095u, "fastgs_forward: more than 4095 tiles along one axis");
 
     void* prim_blob = alloc(alloc_ctx, LFS_TAG_FG_PER_PRIMITIVE, carve_prim(nullptr, N).bytes);
     void* tile_blob = alloc(alloc_ctx, LFS_TAG_FG_PER_TILE, carve_tile(nullptr, n_tiles, npix).bytes);
@@ -616,11 +848,18 @@ extern "C" int lfs_fastgs_forward(const float* means, const float* scales_raw, c
     const FgPrim P = carve_prim(prim_blob, N);
     const FgTile T = carve_tile(tile_blob, n_tiles, npix);
     LFS_CUDA_OK(cudaMemsetAsync(P.counters, 0, sizeof(uint32_t) * 8, stream));
-    k_fg_preprocess<<<div_up(N, 128), 128, 0, stream>>>(
-        means, scales_raw, reinterpret_cast<const float4*>(rotations_raw), opacities_raw, sh_coefficients_0,
-        sh_coefficients_rest, reinterpret_cast<const float4*>(w2c), cam_position, N, tile_w, tile_h, active_sh_bases,
-        total_bases_sh_rest, (float)width, (float)height, focal_x, focal_y, center_x, center_y, near_plane, far_plane,
-        P.gauss, P.rects, P.counts, P.masks, P.dk_a, P.pm_a, P.counters + 1);
+    if (raster_options().fg_variant == 1)
+        k_fg_preprocess<<<div_up(N, 128), 128, 0, stream>>>(
+            means, scales_raw, reinterpret_cast<const float4*>(rotations_raw), opacities_raw, sh_coefficients_0,
+            sh_coefficients_rest, reinterpret_cast<const float4*>(w2c), cam_position, N, tile_w, tile_h, active_sh_bases,
+            total_bases_sh_rest, (float)width, (float)height, focal_x, focal_y, center_x, center_y, near_plane, far_plane,
+            P.gauss, P.rects, P.counts, P.masks, P.dk_a, P.pm_a, P.counters + 1);
+    else
+        k_fg_preprocess_coop<<<div_up(N, 128), 128, 0, stream>>>(
+            means, scales_raw, reinterpret_cast<const float4*>(rotations_raw), opacities_raw, sh_coefficients_0,
+            sh_coefficients_rest, reinterpret_cast<const float4*>(w2c), cam_position, N, tile_w, tile_h, active_sh_bases,
+            total_bases_sh_rest, (float)width, (float)height, focal_x, focal_y, center_x, center_y, near_plane, far_plane,
+            P.gauss, P.rects, P.counts, P.masks, P.dk_a, P.pm_a, P.counters + 1);
     LFS_LAUNCH_OK("k_fg_preprocess");
     int in_b = 0;
     int rc = radix_sort_pairs(P.dk_a, P.pm_a, P.dk_b, P.pm_b, N, nullptr, 0, 32, P.sort_scr, &in_b, stream);
@@ -649,8 +888,15 @@ extern "C" int lfs_fastgs_forward(const float* means, const float* scales_raw, c
     if (n_inst > 0) {
         const unsigned want = div_up(N, 256);
         const unsigned grid = want < (unsigned)(num_sms() * 16) ? want : (unsigned)(num_sms() * 16);
-        k_fg_emit<<<grid, 256, 0, stream>>>(perm, P.off, N, P.rects, P.counts, P.masks, P.gauss, tile_w, n_inst, I.tk_a,
-                                            I.tv_a);
+        if (raster_options().fg_variant == 1) // round-2 first version, kept for A/B
+            k_fg_emit<<<grid, 256, 0, stream>>>(perm, P.off, N, P.rects, P.counts, P.masks, P.gauss, tile_w, n_inst, I.tk_a,
+                                                I.tv_a);
+        else
+        {
+            const unsigned want_c = div_up(div_up(N, 32), kEmitWarps), cap_c = (unsigned)(num_sms() * 8);
+            k_fg_emit_coop<<<want_c < cap_c ? want_c : cap_c, kEmitWarps * 32, 0, stream>>>(
+                perm, P.off, N, P.rects, P.counts, P.masks, P.gauss, tile_w, n_inst, I.tk_a, I.tv_a);
+        }
         LFS_LAUNCH_OK("k_fg_emit");
         rc = radix_sort_pairs(I.tk_a, I.tv_a, I.tk_b, I.tv_b, n_inst, nullptr, 0, tile_key_bits(n_tiles), I.sort_scr, &in_b,
                               stream);

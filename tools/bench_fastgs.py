@@ -20,7 +20,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import ref_libs as R  # noqa: E402
+import lichtfeld_studio_b200 as L  # noqa: E402
 from lichtfeld_studio_b200 import scene as S  # noqa: E402
+
+L.load()  # applies LFS_OPTIONS (A/B switches) to the one liblfs_b200.so of this process, the host layer's included
 
 cfg = sys.argv[1] if len(sys.argv) > 1 else "C2"
 n, V, W, H, deg = S.CONFIGS[cfg]
