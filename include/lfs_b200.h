@@ -441,7 +441,8 @@ int lfs_trainer_get_profile(void* trainer, float* mean_ms /* [LFS_PROF_STAGES] *
  *   "sort_variant" 0 histogram / scan / scatter radix passes, 1 onesweep (decoupled look-back) passes, 2 onesweep for keys
  *                  of <= 16 bits only, 3 the passes of 0 with ballot ranking, 4 = 2 + 3 (A/B switches, all bit-identical
  *                  results)
- *   "fg_variant"   fastgs surface: 0 warp-cooperative exact tile tests and emission, 1 one thread per primitive (identical results)
+ *   "fg_variant"   fastgs surface: 0 one thread per primitive, 1 warp-cooperative exact tile tests and emission (identical
+ *                  results, measured slower)
  *   "emit_variant" trainer emission of the tile instances: 0 one thread per Gaussian, 1 warp-cooperative from tile masks
  *   "exact_cull"   1 trainer drops tile instances that provably hold no alpha >= 1/255, 0 the reference's AABB rule
  *   "pre_bwd_split" 1 per-Gaussian backward as two launches (SH, geometry), 0 one launch */

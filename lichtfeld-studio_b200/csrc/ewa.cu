@@ -267,8 +267,9 @@ __global__ void __launch_bounds__(128)
                     GaussRec* __restrict__ gauss, TileRect* __restrict__ rects, int32_t* __restrict__ counts,
                     unsigned long long* __restrict__ masks, uint32_t* __restrict__ depth_keys,
                     uint32_t* __restrict__ ident, uint32_t* __restrict__ n_visible) {
-    // Same results as k_fg_preprocess; the exact tile tests of a warp's 32 primitives are spread evenly over its lanes
-    // (k_fg_preprocess: every lane walks its own rectangle, 11.7 of 32 lanes active per instruction, 68 % issue-bound).
+    // A/B variant (fg_variant = 1, measured slower, see k_fg_emit_coop).  Same results as k_fg_preprocess; the exact tile
+    // tests of a warp's 32 primitives are spread evenly over its lanes (k_fg_preprocess: every lane walks its own
+    // rectangle, 11.7 of 32 lanes active per instruction, 68 % issue-bound).
     __shared__ __align__(16) float s_sh[128 * 45];
     __shared__ float s_par[4][6][32];          // mx - 0.5, my - 0.5, conic a b c, power threshold
     __shared__ uint32_t s_geo[4][32];          // x0 | y0 << 12 | w << 24
@@ -438,7 +439,9 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// Warp-cooperative emission.  k_fg_emit gives every primitive to one thread, so a warp runs as long as its largest
+// Warp-cooperative emission (A/B variant, fg_variant = 1; measured SLOWER on C3: the op surface takes 1.96 instead of 1.90 ms
+// per view with this and k_fg_preprocess_coop -- the owner search and the shared-memory traffic cost more than the idle
+// lanes they remove).  k_fg_emit gives every primitive to one thread, so a warp runs as long as its largest
 // rectangle and its stores scatter (measured: 6.6 of 32 lanes active per instruction, 0.16 ms at C3).  Here a warp takes 32
 // consecutive slots of the depth order, the instances of all of them form ONE contiguous output range (off is their
 // exclusive scan), and instance t of that range is written by lane t mod 32: its owner is found by a binary search in the
@@ -848,7 +851,7 @@ extern "C" int lfs_fastgs_forward(const float* means, const float* scales_raw, c
     const FgPrim P = carve_prim(prim_blob, N);
     const FgTile T = carve_tile(tile_blob, n_tiles, npix);
     LFS_CUDA_OK(cudaMemsetAsync(P.counters, 0, sizeof(uint32_t) * 8, stream));
-    if (raster_options().fg_variant == 1)
+    if (raster_options().fg_variant != 1)
         k_fg_preprocess<<<div_up(N, 128), 128, 0, stream>>>(
             means, scales_raw, reinterpret_cast<const float4*>(rotations_raw), opacities_raw, sh_coefficients_0,
             sh_coefficients_rest, reinterpret_cast<const float4*>(w2c), cam_position, N, tile_w, tile_h, active_sh_bases,
@@ -888,7 +891,7 @@ extern "C" int lfs_fastgs_forward(const float* means, const float* scales_raw, c
     if (n_inst > 0) {
         const unsigned want = div_up(N, 256);
         const unsigned grid = want < (unsigned)(num_sms() * 16) ? want : (unsigned)(num_sms() * 16);
-        if (raster_options().fg_variant == 1) // round-2 first version, kept for A/B
+        if (raster_options().fg_variant != 1) // one thread per primitive: measured faster than the cooperative walk
             k_fg_emit<<<grid, 256, 0, stream>>>(perm, P.off, N, P.rects, P.counts, P.masks, P.gauss, tile_w, n_inst, I.tk_a,
                                                 I.tv_a);
         else
