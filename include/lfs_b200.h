@@ -443,7 +443,6 @@ int lfs_trainer_get_profile(void* trainer, float* mean_ms /* [LFS_PROF_STAGES] *
  *                  results)
  *   "fg_variant"   fastgs surface: 0 one thread per primitive, 1 warp-cooperative exact tile tests and emission (identical
  *                  results, measured slower)
- *   "emit_variant" trainer emission of the tile instances: 0 one thread per Gaussian, 1 warp-cooperative from tile masks
  *   "exact_cull"   1 trainer drops tile instances that provably hold no alpha >= 1/255, 0 the reference's AABB rule
  *   "pre_bwd_split" 1 per-Gaussian backward as two launches (SH, geometry), 0 one launch */
 int lfs_set_option(const char* name, int value);

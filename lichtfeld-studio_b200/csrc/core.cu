@@ -62,10 +62,6 @@ extern "C" int lfs_set_option(const char* name, int value) {
         lfs::raster_options().fg_variant = value;
         return LFS_OK;
     }
-    if (name && std::string(name) == "emit_variant") {
-        lfs::raster_options().emit_variant = value;
-        return LFS_OK;
-    }
     if (name && std::string(name) == "sort_variant") {
         lfs::set_sort_variant(value);
         return LFS_OK;

@@ -152,119 +152,6 @@ int launch_emit_instances_cull(const uint32_t* perm, const uint32_t* off, uint32
     return LFS_OK;
 }
 
-// Warp-cooperative emission from per-Gaussian tile masks (trainer: `emit_variant` 1).  A warp takes 32 consecutive slots of
-// the depth order; their instances are ONE contiguous output range (off is their exclusive scan) and instance t of it is
-// written by lane t mod 32 -- owner by binary search in the warp's prefix sums, tile = k-th set bit of the owner's mask -- so
-// the lanes are evenly loaded and the stores coalesce (k_emit_instances_cull: 12.6 of 32 lanes active per instruction).
-// Rectangles of more than 64 tiles carry no mask and are walked by their owner lane with the row-span predicate.
-constexpr int kEmitWarps = 8;
-__global__ void __launch_bounds__(kEmitWarps * 32)
-    k_emit_instances_coop(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ off, const uint32_t n_gauss,
-                          const TileRect* __restrict__ rects, const int32_t* __restrict__ counts,
-                          const unsigned long long* __restrict__ masks, const CullRec* __restrict__ cull,
-                          const uint32_t tile_w, const uint32_t n_cap, const uint32_t* __restrict__ n_dev,
-                          uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ vals) {
-    __shared__ uint32_t s_pre[kEmitWarps][33];
-    __shared__ unsigned long long s_mask[kEmitWarps][32];
-    __shared__ uint32_t s_geo[kEmitWarps][32];  // x0 | y0 << 12 | w << 24
-    __shared__ uint32_t s_rcp[kEmitWarps][32];  // ceil(65536 / w): bit / w == (bit * rcp) >> 16 for bit < 64
-    __shared__ uint32_t s_base[kEmitWarps][32];
-    __shared__ uint32_t s_gid[kEmitWarps][32];
-    uint32_t n = n_cap;
-    if (n_dev) {
-        const uint32_t nd = *n_dev;
-        n = nd < n_cap ? nd : n_cap;
-    }
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const uint32_t n_groups = (n_gauss + 31u) / 32u;
-    for (uint32_t grp = blockIdx.x * kEmitWarps + warp; grp < n_groups; grp += gridDim.x * kEmitWarps) {
-        const uint32_t slot = grp * 32u + lane;
-        uint32_t g = 0, cnt = 0, base = 0;
-        TileRect r{0, 0, 0, 0};
-        if (slot < n_gauss) {
-            g = perm ? __ldg(perm + slot) : slot;
-            const int32_t c = counts[g];
-            if (c > 0) {
-                cnt = (uint32_t)c;
-                r = rects[g];
-                base = __ldg(off + slot);
-            }
-        }
-        const uint32_t w = (uint32_t)(r.x1 - r.x0), area = w * (uint32_t)(r.y1 - r.y0);
-        const bool big = cnt > 0 && area > 64u;
-        const uint32_t c_coop = big ? 0u : cnt;
-        uint32_t incl = c_coop;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= (uint32_t)o)
-                incl += y;
-        }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        s_pre[warp][lane] = incl - c_coop;
-        if (lane == 31)
-            s_pre[warp][32] = total;
-        s_mask[warp][lane] = c_coop ? masks[g] : 0ull;
-        s_geo[warp][lane] = (uint32_t)r.x0 | ((uint32_t)r.y0 << 12) | (w << 24);
-        s_rcp[warp][lane] = w ? (65536u + w - 1u) / w : 0u;
-        s_base[warp][lane] = base;
-        s_gid[warp][lane] = g;
-        __syncwarp();
-        for (uint32_t t = lane; t < total; t += 32u) {
-            uint32_t lo = 0, hi = 32; // pre[lo] <= t < pre[hi]
-#pragma unroll
-            for (int it = 0; it < 5; ++it) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (s_pre[warp][mid] <= t)
-                    lo = mid;
-                else
-                    hi = mid;
-            }
-            const uint32_t k = t - s_pre[warp][lo];
-            const unsigned long long m = s_mask[warp][lo];
-            const uint32_t mlo = (uint32_t)m, mhi = (uint32_t)(m >> 32), clo = (uint32_t)__popc(mlo);
-            const uint32_t bit = k < clo ? __fns(mlo, 0, (int)k + 1) : 32u + __fns(mhi, 0, (int)(k - clo) + 1);
-            const uint32_t geo = s_geo[warp][lo];
-            const uint32_t row = (bit * s_rcp[warp][lo]) >> 16, col = bit - row * (geo >> 24);
-            const uint32_t pos = s_base[warp][lo] + k;
-            if (pos < n) {
-                tile_keys[pos] = (((geo >> 12) & 0xfffu) + row) * tile_w + (geo & 0xfffu) + col;
-                vals[pos] = s_gid[warp][lo];
-            }
-        }
-        if (big) {
-            const float4* cp = reinterpret_cast<const float4*>(cull + g);
-            const float4 c0 = __ldg(cp), c1 = __ldg(cp + 1);
-            const CullRec cr{c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-            uint32_t pos = base;
-            for (uint32_t ty = r.y0; ty < r.y1; ++ty) {
-                int first, last;
-                cull_row_span(cr, ty, r.x0, r.x1, first, last);
-                for (int tx = first; tx <= last; ++tx, ++pos)
-                    if (pos < n) {
-                        tile_keys[pos] = ty * tile_w + (uint32_t)tx;
-                        vals[pos] = g;
-                    }
-            }
-        }
-        __syncwarp();
-    }
-}
-
-int launch_emit_instances_coop(const uint32_t* perm, const uint32_t* off, uint32_t n_gauss, const TileRect* rects,
-                               const int32_t* counts, const unsigned long long* masks, const CullRec* cull,
-                               uint32_t tile_w, uint32_t n_cap, const uint32_t* n_dev, uint32_t* tile_keys, uint32_t* vals,
-                               cudaStream_t stream) {
-    if (n_cap == 0 || n_gauss == 0)
-        return LFS_OK;
-    const unsigned want = div_up(div_up(n_gauss, 32), kEmitWarps), cap = (unsigned)(num_sms() * 8);
-    k_emit_instances_coop<<<want < cap ? want : cap, kEmitWarps * 32, 0, stream>>>(perm, off, n_gauss, rects, counts, masks,
-                                                                                    cull, tile_w, n_cap, n_dev, tile_keys,
-                                                                                    vals);
-    LFS_LAUNCH_OK("k_emit_instances_coop");
-    return LFS_OK;
-}
-
 __global__ void __launch_bounds__(kIsThreads)
     k_tile_offsets(const uint32_t* __restrict__ keys, const uint32_t n_cap, const uint32_t* __restrict__ n_dev,
                    const uint32_t n_tiles, int32_t* __restrict__ offsets) {

@@ -97,10 +97,6 @@ int launch_tile_count(const float* means2d, const int32_t* radii, const float* d
 int launch_emit_instances_cull(const uint32_t* perm, const uint32_t* off, uint32_t n_gauss, const TileRect* rects,
                                const int32_t* counts, const CullRec* cull, uint32_t tile_w, uint32_t n_cap,
                                const uint32_t* n_dev, uint32_t* tile_keys, uint32_t* vals, cudaStream_t stream);
-int launch_emit_instances_coop(const uint32_t* perm, const uint32_t* off, uint32_t n_gauss, const TileRect* rects,
-                               const int32_t* counts, const unsigned long long* masks, const CullRec* cull,
-                               uint32_t tile_w, uint32_t n_cap, const uint32_t* n_dev, uint32_t* tile_keys, uint32_t* vals,
-                               cudaStream_t stream);
 int launch_emit_instances(const uint32_t* perm, const uint32_t* off, uint32_t n_gauss, const TileRect* rects,
                           uint32_t tile_w, uint32_t id_offset, uint32_t n_cap, const uint32_t* n_dev,
                           uint32_t* tile_keys, uint32_t* vals, cudaStream_t stream);

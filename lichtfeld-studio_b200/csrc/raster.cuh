@@ -63,7 +63,6 @@ struct RasterOptions {
                          // 2 = 0 with one warp per bucket, 3 = 0 at 80 registers / 6 CTAs per SM
     int pre_bwd_split = 1; // trainer: SH / geometry halves of the per-Gaussian backward as two launches (A/B switch)
     int fg_variant = 0; // fastgs surface: 0 one thread per primitive (default), 1 warp-cooperative tile tests + emission (A/B)
-    int emit_variant = 0; // trainer emission: 0 one thread per Gaussian, 1 warp-cooperative from tile masks (A/B)
     int exact_cull = 1; // trainer: drop (tile, Gaussian) instances that provably hold no alpha >= 1/255 (intersect.cuh CullRec)
 };
 RasterOptions& raster_options();

@@ -43,7 +43,6 @@ struct Trainer {
     GaussRec* gauss;
     TileRect* rects;
     CullRec* cull;
-    unsigned long long* masks; // kept tiles per Gaussian (rectangles of <= 64 tiles), row-major bits
     int32_t* counts;
     uint32_t *dk_a, *dk_b, *pm_a, *pm_b, *off;
     uint32_t* n_inst; // [4] device counters: n_inst, n_buckets, high-water mark of n_inst since creation
@@ -86,7 +85,6 @@ static size_t trainer_carve(Trainer& t, void* base) {
     t.gauss = c.take<GaussRec>(N);
     t.rects = c.take<TileRect>(N);
     t.cull = c.take<CullRec>(N);
-    t.masks = c.take<unsigned long long>(N);
     t.counts = c.take<int32_t>(N);
     t.dk_a = c.take<uint32_t>(N), t.dk_b = c.take<uint32_t>(N);
     t.pm_a = c.take<uint32_t>(N), t.pm_b = c.take<uint32_t>(N);
@@ -169,9 +167,7 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __ex
 __global__ void __launch_bounds__(256)
     k_preprocess_fwd(const float* __restrict__ arena, const Planes pl, const uint32_t N, const ViewCam cam,
                      const PreCfg cfg, GaussRec* __restrict__ gauss, TileRect* __restrict__ rects,
-                     CullRec* __restrict__ cull /* null: keep every tile of the AABB */,
-                     unsigned long long* __restrict__ masks /* null, or: kept tiles of a rectangle of <= 64 tiles */,
-                     int32_t* __restrict__ counts, uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ ident,
+                     CullRec* __restrict__ cull /* null: keep every tile of the AABB */, int32_t* __restrict__ counts, uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ ident,
                      float* __restrict__ act_means, float* __restrict__ act_quats, float* __restrict__ act_scales) {
     const uint32_t g = blockIdx.x * 256 + threadIdx.x;
     if (g >= N)
@@ -251,21 +247,11 @@ __global__ void __launch_bounds__(256)
         }
         cull[g] = cr;
         int32_t hit = 0;
-        unsigned long long mask = 0ull; // row-major bit per kept tile (rectangles of <= 64 tiles): the emission walks bits
-        const uint32_t rw = x1 - x0;
-        const bool small = rw * (y1 - y0) <= 64u;
         for (uint32_t ty = y0; ty < y1; ++ty) {
             int first, last;
             cull_row_span(cr, ty, x0, x1, first, last);
-            if (last >= first) {
-                const int len = last - first + 1;
-                hit += len;
-                if (small)
-                    mask |= (len >= 64 ? ~0ull : ((1ull << len) - 1ull)) << ((ty - y0) * rw + ((uint32_t)first - x0));
-            }
+            hit += last >= first ? last - first + 1 : 0;
         }
-        if (masks)
-            masks[g] = mask;
         cnt = hit;
     }
     counts[g] = cnt;
@@ -949,8 +935,7 @@ extern "C" int lfs_trainer_view_forward(void* h, const float* params_arena, cons
     t->mark(0, stream);
     const bool exact_cull = raster_options().exact_cull != 0;
     k_preprocess_fwd<<<div_up(N, 256), 256, 0, stream>>>(params_arena, t->pl, N, t->cam_host, cfg, t->gauss, t->rects,
-                                                         exact_cull ? t->cull : nullptr, exact_cull ? t->masks : nullptr,
-                                                         t->counts, t->dk_a, t->pm_a, t->act_means, t->act_quats,
+                                                         exact_cull ? t->cull : nullptr, t->counts, t->dk_a, t->pm_a, t->act_means, t->act_quats,
                                                          t->act_scales);
     LFS_LAUNCH_OK("k_preprocess_fwd");
     t->mark(1, stream);
@@ -965,10 +950,7 @@ extern "C" int lfs_trainer_view_forward(void* h, const float* params_arena, cons
         return rc;
     k_high_water<<<1, 1, 0, stream>>>(t->n_inst);
     LFS_LAUNCH_OK("k_high_water");
-    if (exact_cull && raster_options().emit_variant == 1)
-        rc = launch_emit_instances_coop(perm, t->off, N, t->rects, t->counts, t->masks, t->cull, t->tile_w, t->inst_cap,
-                                        t->n_inst, t->tk_a, t->tv_a, stream);
-    else if (exact_cull)
+    if (exact_cull)
         rc = launch_emit_instances_cull(perm, t->off, N, t->rects, t->counts, t->cull, t->tile_w, t->inst_cap, t->n_inst,
                                         t->tk_a, t->tv_a, stream);
     else
