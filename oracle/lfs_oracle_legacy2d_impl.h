@@ -14,8 +14,9 @@
  *     T <= 1e-4, back-to-front backward with T /= (1 - alpha)) with the 2-D conic response
  *     sigma = 1/2 (a dx^2 + c dy^2) + b dx dy of the upstream gsplat kernel those launchers belong to
  *     (nerfstudio-project/gsplat v1.x, rasterize_to_pixels_3dgs_{fwd,bwd}.cu -- third-party, absent here).
- *     Parity of the 2-D blend is therefore pinned by finite differences (tests/test_oracle_legacy2d.py) and by the identity
- *     "EWA-projected small Gaussians render like the from-world kernel", not by a reference run.
+ *     PARITY UNPINNED for the 2-D blend: there is no reference implementation, golden vector or fixture of it in the tree to
+ *     pin against.  What holds it: finite differences of its own forward (tests/test_oracle_legacy2d.py) and the identity
+ *     "EWA-projected small Gaussians render like the from-world kernel" (whose oracle IS pinned on the reference CUDA build).
  */
 
 #define CAT_(a, b) a##b
