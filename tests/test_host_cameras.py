@@ -26,8 +26,8 @@ W, H = 640, 480
 K = np.array([[420.0, 0, 318.5], [0, 415.0, 241.25], [0, 0, 1]], np.float32)
 
 
-@pytest.fixture(scope="module")
-def lib():
+def build_lib():
+    """Builds (if stale) and loads the host library; also used by tests/test_glm_shim.py."""
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         pytest.skip("nvcc not available")
@@ -38,6 +38,11 @@ def lib():
                             SRC], capture_output=True, text=True)
         assert r.returncode == 0, r.stdout + r.stderr
     return C.CDLL(OUT)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return build_lib()
 
 
 def _f(a):
